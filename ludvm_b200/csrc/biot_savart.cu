@@ -1,0 +1,406 @@
+// biot_savart.cu -- generic all-pairs entry points: ludvm_induced_velocity (LUDVM.py:549-570),
+// ludvm_selfconv_step (LUDVM.py:1095-1127 without the aerofoil), ludvm_flowfield_* (LUDVM.py:1186-1298).
+#include "biot_savart.cuh"
+
+namespace ludvm {
+
+// ---------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------
+template <class Tgt>
+__global__ void __launch_bounds__(256) k_exact_rows(SrcView S, Tgt T, int nrows, int d, double *pu, double *pw_)
+{
+    int lane = threadIdx.x & 31;
+    long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    long ntasks = (long)((nrows + 3) >> 2) << d;
+    for (long t = gw; t < ntasks; t += nwarps) exact_rows_warp_task(S, T, nrows, d, t, lane, pu, pw_);
+}
+
+template <class Tgt>
+__global__ void __launch_bounds__(256) k_fast_rows(SrcView S, Tgt T, int nrows, int nchunks, double *pu, double *pw_)
+{
+    int lane = threadIdx.x & 31;
+    long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    long nwarps = (long)gridDim.x * (blockDim.x >> 5);
+    long ntasks = (long)((nrows + 3) >> 2) * nchunks;
+    for (long t = gw; t < ntasks; t += nwarps) fast_rows_warp_task(S, T, nrows, nchunks, t, lane, pu, pw_);
+}
+
+template <int R, class Tgt>
+__global__ void __launch_bounds__(FT_THREADS, 2)
+k_fast_tiled(SrcView S, Tgt T, int nrows, int chunk_len, double *pu, double *pw_)
+{
+    __shared__ double sx[FT_TILE], sz[FT_TILE], sg[FT_TILE], sv[FT_TILE];
+    int c0 = blockIdx.y * chunk_len, c1 = min(S.n, c0 + chunk_len);
+    size_t po = (size_t)blockIdx.y * nrows;
+    fast_tiled_block<R>(S, T, nrows, blockIdx.x, c0, c1, pu + po, pw_ + po, sx, sz, sg, sv);
+}
+
+template <int R, class Tgt>
+__global__ void __launch_bounds__(FT_THREADS, 2)
+k_fast32_tiled(SrcView S, Tgt T, int nrows, int chunk_len, double *pu, double *pw_)
+{
+    __shared__ float4 ssrc[FT_TILE];
+    int c0 = blockIdx.y * chunk_len, c1 = min(S.n, c0 + chunk_len);
+    size_t po = (size_t)blockIdx.y * nrows;
+    fast32_tiled_block<R>(S, T, nrows, blockIdx.x, c0, c1, pu + po, pw_ + po, ssrc);
+}
+
+// Fold partials.  exact: nfold = tree depth d; fast: nfold = number of chunks.  Optional second partial set
+// (the reference's `u_wake + u_foil`, LUDVM.py:1108, :1219) and optional forward-Euler update (LUDVM.py:1108-1127).
+struct CombineArgs {
+    const double *pu, *pw;   // [fold][nrows]
+    const double *qu, *qw;   // second set or nullptr
+    int nfold, qfold;
+    int exact;
+    int nrows;
+    double *u, *w;           // nullable
+    const double *x, *z;     // Euler: inputs (already offset to the shard's first row)
+    double *xo, *zo;         // Euler: outputs (nullable)
+    double dt;
+};
+
+__global__ void __launch_bounds__(256) k_combine(CombineArgs a)
+{
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= a.nrows) return;
+    double u, w;
+    if (a.exact) {
+        u = exact_combine_row(a.pu, a.nrows, row, a.nfold);
+        w = exact_combine_row(a.pw, a.nrows, row, a.nfold);
+        if (a.qu) {
+            u = __dadd_rn(u, exact_combine_row(a.qu, a.nrows, row, a.qfold));
+            w = __dadd_rn(w, exact_combine_row(a.qw, a.nrows, row, a.qfold));
+        }
+    } else {
+        u = fast_combine_row(a.pu, a.nrows, row, a.nfold);
+        w = fast_combine_row(a.pw, a.nrows, row, a.nfold);
+        if (a.qu) {
+            u += fast_combine_row(a.qu, a.nrows, row, a.qfold);
+            w += fast_combine_row(a.qw, a.nrows, row, a.qfold);
+        }
+    }
+    if (a.u) {
+        a.u[row] = u;
+        a.w[row] = w;
+    }
+    if (a.xo) {
+        a.xo[row] = __dadd_rn(a.x[row], __dmul_rn(a.dt, u));
+        a.zo[row] = __dadd_rn(a.z[row], __dmul_rn(a.dt, w));
+    }
+}
+
+// Vorticity stencil, LUDVM.py:1222-1292: clamped neighbours reproduce the centred / one-sided variants.
+__global__ void __launch_bounds__(256) k_vorticity(const double *x1, int nx, const double *z1, int nz, const double *u,
+                                                   const double *w, int ns, double *ome)
+{
+    long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    long per = (long)nx * nz;
+    if (idx >= per * ns) return;
+    long s = idx / per, r = idx - s * per;
+    int i = (int)(r / nz), j = (int)(r - (long)i * nz);
+    int ip = min(i + 1, nx - 1), im = max(i - 1, 0), jp = min(j + 1, nz - 1), jm = max(j - 1, 0);
+    const double *us = u + s * per, *ws = w + s * per;
+    double dx = __dsub_rn(x1[ip], x1[im]);
+    double dz = __dsub_rn(z1[jp], z1[jm]);
+    double dw = __dsub_rn(ws[(long)ip * nz + j], ws[(long)im * nz + j]);
+    double du = __dsub_rn(us[(long)i * nz + jp], us[(long)i * nz + jm]);
+    ome[idx] = __dsub_rn(__ddiv_rn(dw, dx), __ddiv_rn(du, dz));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host-side planning and launch
+// ---------------------------------------------------------------------------------------------------
+static int ilog2_ceil(long v)
+{
+    int l = 0;
+    while ((1L << l) < v) l++;
+    return l;
+}
+
+// Evaluate partial row sums for `nrows` targets against S; on return *nfold and the partial buffers (scratch
+// slots slot/slot+1) describe what k_combine must fold.
+template <class Tgt>
+static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt &T, long nrows, int slot,
+                           double **pu, double **pw_, int *nfold)
+{
+    const int sm = ctx->sm_count;
+    if (mode == LUDVM_EXACT_F64) {
+        long nquads = (nrows + 3) / 4;
+        int want = ilog2_ceil(std::max(1L, (long)sm * 64 / std::max(1L, nquads)));
+        int d = std::min(pw_max_depth(S.n), want);
+        size_t bytes = sizeof(double) * (size_t)nrows * ((size_t)1 << d);
+        void *a, *b;
+        int rc;
+        if ((rc = scratch_reserve(ctx, slot, bytes, &a))) return rc;
+        if ((rc = scratch_reserve(ctx, slot + 1, bytes, &b))) return rc;
+        long ntasks = nquads << d;
+        int blocks = (int)std::min((ntasks + 7) / 8, (long)sm * 16);
+        k_exact_rows<<<blocks, 256, 0, ctx->stream>>>(S, T, (int)nrows, d, (double *)a, (double *)b);
+        ctx->launches++;
+        *pu = (double *)a; *pw_ = (double *)b; *nfold = d;
+        return LUDVM_OK;
+    }
+    const bool f32 = (mode == LUDVM_FAST_F32);
+    if (f32 || nrows >= 8192) {
+        int R = 4;
+        if (!f32) {
+            while (R > 1 && ceil_div(nrows, FT_THREADS * R) < sm) R >>= 1;
+        }
+        int row_blocks = ceil_div(nrows, FT_THREADS * R);
+        long target = (long)sm * 2 * 6;
+        long chunks = std::max(1L, std::min((target + row_blocks - 1) / row_blocks, (long)S.n / (FT_TILE * 2)));
+        int chunk_len = (int)(((S.n + chunks - 1) / chunks + FT_TILE - 1) / FT_TILE * FT_TILE);
+        chunks = ((long)S.n + chunk_len - 1) / chunk_len;
+        size_t bytes = sizeof(double) * (size_t)nrows * (size_t)chunks;
+        void *a, *b;
+        int rc;
+        if ((rc = scratch_reserve(ctx, slot, bytes, &a))) return rc;
+        if ((rc = scratch_reserve(ctx, slot + 1, bytes, &b))) return rc;
+        dim3 grid(row_blocks, (unsigned)chunks);
+        if (f32) k_fast32_tiled<4><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
+        else if (R == 4) k_fast_tiled<4><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
+        else if (R == 2) k_fast_tiled<2><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
+        else k_fast_tiled<1><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
+        ctx->launches++;
+        *pu = (double *)a; *pw_ = (double *)b; *nfold = (int)chunks;
+        return LUDVM_OK;
+    }
+    long nquads = (nrows + 3) / 4;
+    long chunks = std::max(1L, std::min((long)sm * 64 / std::max(1L, nquads), ((long)S.n + 63) / 64));
+    size_t bytes = sizeof(double) * (size_t)nrows * (size_t)chunks;
+    void *a, *b;
+    int rc;
+    if ((rc = scratch_reserve(ctx, slot, bytes, &a))) return rc;
+    if ((rc = scratch_reserve(ctx, slot + 1, bytes, &b))) return rc;
+    long ntasks = nquads * chunks;
+    int blocks = (int)std::min((ntasks + 7) / 8, (long)sm * 16);
+    k_fast_rows<<<blocks, 256, 0, ctx->stream>>>(S, T, (int)nrows, (int)chunks, (double *)a, (double *)b);
+    ctx->launches++;
+    *pu = (double *)a; *pw_ = (double *)b; *nfold = (int)chunks;
+    return LUDVM_OK;
+}
+
+static int launch_combine(ludvm_ctx *ctx, const CombineArgs &a)
+{
+    k_combine<<<ceil_div(a.nrows, 256), 256, 0, ctx->stream>>>(a);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LUDVM_OK;
+}
+
+// Copy a host array to device scratch (slot) on the context's stream.
+static int stage_in(ludvm_ctx *ctx, int slot, const double *host, size_t n, double **dev)
+{
+    void *p;
+    int rc = scratch_reserve(ctx, slot, std::max<size_t>(n, 1) * sizeof(double), &p);
+    if (rc) return rc;
+    if (n) CUDA_TRY(cudaMemcpyAsync(p, host, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    *dev = (double *)p;
+    return LUDVM_OK;
+}
+
+static int check_mode(int mode)
+{
+    if (mode != LUDVM_EXACT_F64 && mode != LUDVM_FAST_F64 && mode != LUDVM_FAST_F32)
+        return set_error(LUDVM_E_ARG, "unknown arithmetic mode %d", mode);
+    return LUDVM_OK;
+}
+
+}  // namespace ludvm
+
+using namespace ludvm;
+
+// Scratch slot map for the generic entry points: 0,1 partials A; 2,3 partials B; 4 inputs; 5 outputs; 6 grid axes.
+LUDVM_API int ludvm_induced_velocity(ludvm_ctx *ctx, int mode, const double *gamma, long ngamma, const double *xw,
+                                     const double *zw, const double *vc4_per_source, double vc4, long nw,
+                                     const double *xp, const double *zp, long np_, double *u, double *w, int ptr_kind)
+{
+    ARG_CHECK(ctx != nullptr);
+    int rc = check_mode(mode);
+    if (rc) return rc;
+    ARG_CHECK(nw >= 0 && np_ >= 0 && nw < (1L << 30) && np_ < (1L << 30));
+    ARG_CHECK(ngamma == nw || ngamma == 1);
+    ARG_CHECK(ptr_kind == LUDVM_PTR_HOST || ptr_kind == LUDVM_PTR_DEVICE);
+    if (np_ == 0) return LUDVM_OK;
+    ARG_CHECK(u && w && xp && zp);
+    ARG_CHECK(nw == 0 || (gamma && xw && zw));
+    DeviceGuard g(ctx->device);
+
+    const double *dg = gamma, *dxw = xw, *dzw = zw, *dvc = vc4_per_source, *dxp = xp, *dzp = zp;
+    double *du = u, *dw = w;
+    if (ptr_kind == LUDVM_PTR_HOST) {
+        // one staging buffer: [g | xw | zw | vc | xp | zp], outputs in slot 5
+        size_t nsrc = (size_t)nw, ntg = (size_t)np_;
+        size_t total = (size_t)ngamma + 2 * nsrc + (vc4_per_source ? nsrc : 0) + 2 * ntg;
+        void *p;
+        if ((rc = scratch_reserve(ctx, 4, (total + 8) * sizeof(double), &p))) return rc;
+        double *b = (double *)p;
+        auto put = [&](const double *h, size_t n, const double **d) -> int {
+            if (n) CUDA_TRY(cudaMemcpyAsync(b, h, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            *d = b;
+            b += n;
+            return LUDVM_OK;
+        };
+        if (nw) {
+            if ((rc = put(gamma, (size_t)ngamma, &dg))) return rc;
+            if ((rc = put(xw, nsrc, &dxw))) return rc;
+            if ((rc = put(zw, nsrc, &dzw))) return rc;
+            if (vc4_per_source && (rc = put(vc4_per_source, nsrc, &dvc))) return rc;
+        }
+        if ((rc = put(xp, ntg, &dxp))) return rc;
+        if ((rc = put(zp, ntg, &dzp))) return rc;
+        void *o;
+        if ((rc = scratch_reserve(ctx, 5, 2 * ntg * sizeof(double), &o))) return rc;
+        du = (double *)o;
+        dw = du + ntg;
+    }
+    if (nw == 0) {  // np.sum over an empty axis
+        CUDA_TRY(cudaMemsetAsync(du, 0, (size_t)np_ * sizeof(double), ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)np_ * sizeof(double), ctx->stream));
+    } else {
+        SrcView S = make_src(dg, ngamma == nw ? 1 : 0, dxw, dzw, dvc, vc4, (int)nw);
+        TgtArray T{dxp, dzp};
+        CombineArgs a{};
+        if ((rc = launch_partials(ctx, mode, S, T, np_, 0, (double **)&a.pu, (double **)&a.pw, &a.nfold))) return rc;
+        CUDA_TRY(cudaGetLastError());
+        a.exact = (mode == LUDVM_EXACT_F64);
+        a.nrows = (int)np_;
+        a.u = du;
+        a.w = dw;
+        if ((rc = launch_combine(ctx, a))) return rc;
+    }
+    if (ptr_kind == LUDVM_PTR_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(u, du, (size_t)np_ * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(w, dw, (size_t)np_ * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return LUDVM_OK;
+}
+
+LUDVM_API int ludvm_selfconv_step(ludvm_ctx *ctx, int mode, const double *gamma, const double *x, const double *z,
+                                  const double *vc4_per_source, double vc4, long n, long row0, long nrows, double dt,
+                                  double *x_out, double *z_out, double *u_out, double *w_out)
+{
+    ARG_CHECK(ctx != nullptr);
+    int rc = check_mode(mode);
+    if (rc) return rc;
+    ARG_CHECK(n > 0 && n < (1L << 30) && row0 >= 0 && nrows >= 0 && row0 + nrows <= n);
+    ARG_CHECK(gamma && x && z && x_out && z_out);
+    if (nrows == 0) return LUDVM_OK;
+    DeviceGuard g(ctx->device);
+    SrcView S = make_src(gamma, 1, x, z, vc4_per_source, vc4, (int)n);
+    TgtArray T{x + row0, z + row0};
+    CombineArgs a{};
+    if ((rc = launch_partials(ctx, mode, S, T, nrows, 0, (double **)&a.pu, (double **)&a.pw, &a.nfold))) return rc;
+    CUDA_TRY(cudaGetLastError());
+    a.exact = (mode == LUDVM_EXACT_F64);
+    a.nrows = (int)nrows;
+    a.u = u_out;
+    a.w = w_out;
+    a.x = x + row0;
+    a.z = z + row0;
+    a.xo = x_out + row0;
+    a.zo = z_out + row0;
+    a.dt = dt;
+    return launch_combine(ctx, a);
+}
+
+LUDVM_API int ludvm_flowfield_velocity(ludvm_ctx *ctx, int mode, const double *ga, const double *xa, const double *za,
+                                       long na, const double *gb, const double *xb, const double *zb, long nb,
+                                       double vc4, const double *x1, long nx, const double *z1, long nz, long row0,
+                                       long nrows, double *u, double *w, int ptr_kind)
+{
+    ARG_CHECK(ctx != nullptr);
+    int rc = check_mode(mode);
+    if (rc) return rc;
+    ARG_CHECK(na > 0 && nb >= 0 && nx > 0 && nz > 0 && row0 >= 0 && nrows >= 0 && row0 + nrows <= nx);
+    ARG_CHECK(na < (1L << 30) && nb < (1L << 30) && nrows * nz < (1L << 31) - 1024);
+    ARG_CHECK(ga && xa && za && x1 && z1 && u && w && (nb == 0 || (gb && xb && zb)));
+    ARG_CHECK(ptr_kind == LUDVM_PTR_HOST || ptr_kind == LUDVM_PTR_DEVICE);
+    if (nrows == 0) return LUDVM_OK;
+    DeviceGuard g(ctx->device);
+    long npts = nrows * nz;
+    const double *dga = ga, *dxa = xa, *dza = za, *dgb = gb, *dxb = xb, *dzb = zb, *dx1 = x1, *dz1 = z1;
+    double *du = u, *dw = w;
+    if (ptr_kind == LUDVM_PTR_HOST) {
+        size_t total = 3 * (size_t)na + 3 * (size_t)nb + (size_t)nx + (size_t)nz + 8;
+        void *p;
+        if ((rc = scratch_reserve(ctx, 4, total * sizeof(double), &p))) return rc;
+        double *b = (double *)p;
+        auto put = [&](const double *h, size_t n, const double **d) -> int {
+            if (n) CUDA_TRY(cudaMemcpyAsync(b, h, n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            *d = b;
+            b += n;
+            return LUDVM_OK;
+        };
+        if ((rc = put(ga, na, &dga)) || (rc = put(xa, na, &dxa)) || (rc = put(za, na, &dza))) return rc;
+        if (nb && ((rc = put(gb, nb, &dgb)) || (rc = put(xb, nb, &dxb)) || (rc = put(zb, nb, &dzb)))) return rc;
+        if ((rc = put(x1, nx, &dx1)) || (rc = put(z1, nz, &dz1))) return rc;
+        void *o;
+        if ((rc = scratch_reserve(ctx, 5, 2 * (size_t)npts * sizeof(double), &o))) return rc;
+        du = (double *)o;
+        dw = du + npts;
+    }
+    TgtGrid T{dx1, dz1, (int)nz, (int)row0};
+    CombineArgs a{};
+    SrcView SA = make_src(dga, 1, dxa, dza, nullptr, vc4, (int)na);
+    if ((rc = launch_partials(ctx, mode, SA, T, npts, 0, (double **)&a.pu, (double **)&a.pw, &a.nfold))) return rc;
+    if (nb) {
+        SrcView SB = make_src(dgb, 1, dxb, dzb, nullptr, vc4, (int)nb);
+        if ((rc = launch_partials(ctx, mode, SB, T, npts, 2, (double **)&a.qu, (double **)&a.qw, &a.qfold))) return rc;
+    }
+    CUDA_TRY(cudaGetLastError());
+    a.exact = (mode == LUDVM_EXACT_F64);
+    a.nrows = (int)npts;
+    a.u = du;
+    a.w = dw;
+    if ((rc = launch_combine(ctx, a))) return rc;
+    if (ptr_kind == LUDVM_PTR_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(u, du, (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(w, dw, (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return LUDVM_OK;
+}
+
+LUDVM_API int ludvm_flowfield_vorticity(ludvm_ctx *ctx, const double *x1, long nx, const double *z1, long nz,
+                                        const double *u, const double *w, long ns, double *ome, int ptr_kind)
+{
+    ARG_CHECK(ctx && x1 && z1 && u && w && ome);
+    ARG_CHECK(nx >= 2 && nz >= 2 && ns >= 1);
+    ARG_CHECK(ptr_kind == LUDVM_PTR_HOST || ptr_kind == LUDVM_PTR_DEVICE);
+    DeviceGuard g(ctx->device);
+    size_t tot = (size_t)ns * nx * nz;
+    const double *dx1 = x1, *dz1 = z1, *du = u, *dw = w;
+    double *dome = ome;
+    int rc;
+    if (ptr_kind == LUDVM_PTR_HOST) {
+        double *a, *b, *c;
+        if ((rc = stage_in(ctx, 6, x1, nx, &a))) return rc;
+        dx1 = a;
+        void *p;
+        if ((rc = scratch_reserve(ctx, 4, (2 * tot + nz + 8) * sizeof(double), &p))) return rc;
+        b = (double *)p;
+        CUDA_TRY(cudaMemcpyAsync(b, z1, nz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        dz1 = b;
+        b += nz;
+        CUDA_TRY(cudaMemcpyAsync(b, u, tot * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        du = b;
+        b += tot;
+        CUDA_TRY(cudaMemcpyAsync(b, w, tot * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        dw = b;
+        if ((rc = scratch_reserve(ctx, 5, tot * sizeof(double), &p))) return rc;
+        c = (double *)p;
+        dome = c;
+    }
+    k_vorticity<<<ceil_div((long)tot, 256), 256, 0, ctx->stream>>>(dx1, (int)nx, dz1, (int)nz, du, dw, (int)ns, dome);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (ptr_kind == LUDVM_PTR_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(ome, dome, tot * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return LUDVM_OK;
+}

@@ -1,0 +1,343 @@
+// biot_savart.cuh -- device templates of the all-pairs Vatistas-core Biot-Savart sum (LUDVM.py:549-570).
+//
+// Three evaluation strategies, all writing PARTIAL row sums [chunk][row] that a combine step folds in a fixed
+// order (so results never depend on grid size, GPU count or scheduling):
+//
+//   exact  lane-group   8 lanes own one target row and reproduce numpy's pairwise-summation tree: lane k owns
+//                       accumulator r[k] of the 8-way unrolled leaf loop, the leaf is closed with an xor-butterfly
+//                       ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) and the up-to-7 tail terms are added in order; leaves
+//                       are folded with an explicit stack exactly as the recursion does.  A "chunk" is a node of
+//                       the tree at depth d, so 2^d warps can share one row and the combine is the top of the tree.
+//   fast   lane-group   same decomposition with FMA arithmetic and equal-length chunks (few targets, many sources:
+//                       the 80 chord stations of airfoil_downwash, LUDVM.py:572-595).
+//   fast   tiled        one thread owns R target rows in registers, sources are staged through shared memory in
+//                       tiles and broadcast to the warp (the O(N^2) convection, LUDVM.py:1095-1127, flow-field
+//                       grids, LUDVM.py:1193-1220).  13 FP64-pipe slots + 1 MUFU per pair.
+#pragma once
+#include "common.cuh"
+
+namespace ludvm {
+
+// Logical concatenation of up to three physical segments of one SoA (TEV ++ LEV ++ FREE, LUDVM.py:743-745).
+struct SrcView {
+    const double *x, *z, *g, *vc4;  // vc4 == nullptr: scalar core
+    double vc4s;
+    int n;         // logical length
+    int n0, n01;   // logical [0,n0) -> phys [0,n0); [n0,n01) -> phys o1+..; [n01,n) -> phys o2+..
+    int o1, o2;
+    int gstride;   // 0: broadcast g[0]
+    __device__ __forceinline__ int phys(int j) const
+    {
+        return j < n0 ? j : (j < n01 ? j - n0 + o1 : j - n01 + o2);
+    }
+};
+
+__host__ __device__ inline SrcView make_src(const double *g, int gstride, const double *x, const double *z,
+                                            const double *vc4, double vc4s, int n)
+{
+    SrcView s;
+    s.x = x; s.z = z; s.g = g; s.vc4 = vc4; s.vc4s = vc4s;
+    s.n = n; s.n0 = n; s.n01 = n; s.o1 = 0; s.o2 = 0; s.gstride = gstride;
+    return s;
+}
+
+struct TgtArray {
+    const double *x, *z;
+    __device__ __forceinline__ void get(int r, double &xp, double &zp) const { xp = x[r]; zp = z[r]; }
+};
+
+// 'ij' mesh of x1 x z1 (LUDVM.py:1193-1195): row r -> (x1[row0 + r / nz], z1[r % nz]).
+struct TgtGrid {
+    const double *x1, *z1;
+    int nz, row0;
+    __device__ __forceinline__ void get(int r, double &xp, double &zp) const
+    {
+        int i = r / nz;
+        xp = x1[row0 + i];
+        zp = z1[r - i * nz];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// exact lane-group
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void exact_term(const SrcView &S, double xp, double zp, int j, double &tu, double &tw)
+{
+    int p = S.phys(j);
+    double vc4 = S.vc4 ? S.vc4[p] : S.vc4s;
+    pair_exact(xp, zp, S.x[p], S.z[p], S.g[p * S.gstride], vc4, tu, tw);
+}
+
+// One leaf (n <= 128) of numpy's pairwise sum, evaluated by the 8 lanes of a group.  Result on every lane.
+__device__ __forceinline__ void exact_leaf_group(const SrcView &S, double xp, double zp, int off, int m, int lane8,
+                                                 double &ru, double &rw)
+{
+    const unsigned full = 0xffffffffu;
+    int body = (m >= 8) ? (m & ~7) : 0;
+    double au = -0.0, aw = -0.0;
+    if (body) {
+        exact_term(S, xp, zp, off + lane8, au, aw);
+        for (int i = 8; i < body; i += 8) {
+            double tu, tw;
+            exact_term(S, xp, zp, off + i + lane8, tu, tw);
+            au = __dadd_rn(au, tu);
+            aw = __dadd_rn(aw, tw);
+        }
+#pragma unroll
+        for (int s = 1; s < 8; s <<= 1) {
+            au = __dadd_rn(au, __shfl_xor_sync(full, au, s));
+            aw = __dadd_rn(aw, __shfl_xor_sync(full, aw, s));
+        }
+    }
+    int rem = m - body;  // 0..7, uniform across the warp
+    if (rem) {
+        double tu = 0.0, tw = 0.0;
+        if (lane8 < rem) exact_term(S, xp, zp, off + body + lane8, tu, tw);
+        for (int t = 0; t < rem; t++) {
+            au = __dadd_rn(au, __shfl_sync(full, tu, t, 8));
+            aw = __dadd_rn(aw, __shfl_sync(full, tw, t, 8));
+        }
+    }
+    ru = au;
+    rw = aw;
+}
+
+// Pairwise sum over the logical source range [off, off+n) -- a node of the tree -- for the group's target.
+// Must be called by all 32 lanes with identical (off, n).
+__device__ inline void exact_node_group(const SrcView &S, double xp, double zp, int off, int n, int lane8,
+                                        double &su, double &sw)
+{
+    int r_off[PW_MAX_STACK], r_len[PW_MAX_STACK];
+    double l_u[PW_MAX_STACK], l_w[PW_MAX_STACK];
+    unsigned has_l = 0;
+    int sp = 0;
+    for (;;) {
+        while (n > PW_BLOCK) {
+            int n2 = pw_left(n);
+            r_off[sp] = off + n2;
+            r_len[sp] = n - n2;
+            has_l &= ~(1u << sp);
+            sp++;
+            n = n2;
+        }
+        double ru, rw;
+        exact_leaf_group(S, xp, zp, off, n, lane8, ru, rw);
+        for (;;) {
+            if (sp == 0) {
+                su = ru;
+                sw = rw;
+                return;
+            }
+            if (!((has_l >> (sp - 1)) & 1u)) {
+                l_u[sp - 1] = ru;
+                l_w[sp - 1] = rw;
+                has_l |= 1u << (sp - 1);
+                off = r_off[sp - 1];
+                n = r_len[sp - 1];
+                break;
+            }
+            ru = __dadd_rn(l_u[sp - 1], ru);
+            rw = __dadd_rn(l_w[sp - 1], rw);
+            sp--;
+        }
+    }
+}
+
+// Warp task t -> (tree node b, row quad q).  Partials: pu[b * nrows + row].
+template <class Tgt>
+__device__ __forceinline__ void exact_rows_warp_task(const SrcView &S, const Tgt &T, int nrows, int d, long t,
+                                                     int lane, double *__restrict__ pu, double *__restrict__ pw_)
+{
+    int nquads = (nrows + 3) >> 2;
+    int b = (int)(t / nquads);
+    int q = (int)(t - (long)b * nquads);
+    int row = q * 4 + (lane >> 3);
+    bool valid = row < nrows;
+    double xp, zp;
+    T.get(valid ? row : nrows - 1, xp, zp);
+    int off, len;
+    pw_node(S.n, d, b, off, len);
+    double su, sw;
+    exact_node_group(S, xp, zp, off, len, lane & 7, su, sw);
+    if (valid && (lane & 7) == 0) {
+        pu[(size_t)b * nrows + row] = su;
+        pw_[(size_t)b * nrows + row] = sw;
+    }
+}
+
+// Fold the 2^d node partials of one row: the top d levels of the tree are a perfect binary tree in index order;
+// finish with numpy's additive identity (np.sum = 0.0 + pairwise).
+__device__ __forceinline__ double exact_combine_row(const double *part, int nrows, int row, int d)
+{
+    double st[PW_MAX_STACK];
+    int sp = 0;
+    int nn = 1 << d;
+    for (int i = 0; i < nn; i++) {
+        double v = part[(size_t)i * nrows + row];
+        for (int k = i; k & 1; k >>= 1) v = __dadd_rn(st[--sp], v);
+        st[sp++] = v;
+    }
+    return __dadd_rn(0.0, st[0]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fast lane-group (few targets)
+// ---------------------------------------------------------------------------------------------------
+template <class Tgt>
+__device__ __forceinline__ void fast_rows_warp_task(const SrcView &S, const Tgt &T, int nrows, int nchunks, long t,
+                                                    int lane, double *__restrict__ pu, double *__restrict__ pw_)
+{
+    const unsigned full = 0xffffffffu;
+    int nquads = (nrows + 3) >> 2;
+    int c = (int)(t / nquads);
+    int q = (int)(t - (long)c * nquads);
+    int row = q * 4 + (lane >> 3);
+    bool valid = row < nrows;
+    double xp, zp;
+    T.get(valid ? row : nrows - 1, xp, zp);
+    int clen = (S.n + nchunks - 1) / nchunks;
+    clen = (clen + 7) & ~7;
+    int j0 = c * clen, j1 = min(S.n, j0 + clen);
+    double au = 0.0, aw = 0.0, bu = 0.0, bw = 0.0;
+    int j = j0 + (lane & 7);
+    for (; j + 8 < j1; j += 16) {  // two independent chains
+        int p = S.phys(j), p2 = S.phys(j + 8);
+        pair_fast(xp, zp, S.x[p], S.z[p], S.g[p * S.gstride] * LUDVM_INV_TWO_PI, S.vc4 ? S.vc4[p] : S.vc4s, au, aw);
+        pair_fast(xp, zp, S.x[p2], S.z[p2], S.g[p2 * S.gstride] * LUDVM_INV_TWO_PI, S.vc4 ? S.vc4[p2] : S.vc4s, bu, bw);
+    }
+    if (j < j1) {
+        int p = S.phys(j);
+        pair_fast(xp, zp, S.x[p], S.z[p], S.g[p * S.gstride] * LUDVM_INV_TWO_PI, S.vc4 ? S.vc4[p] : S.vc4s, au, aw);
+    }
+    au += bu;
+    aw += bw;
+#pragma unroll
+    for (int s = 1; s < 8; s <<= 1) {
+        au += __shfl_xor_sync(full, au, s);
+        aw += __shfl_xor_sync(full, aw, s);
+    }
+    if (valid && (lane & 7) == 0) {
+        pu[(size_t)c * nrows + row] = au;
+        pw_[(size_t)c * nrows + row] = aw;
+    }
+}
+
+__device__ __forceinline__ double fast_combine_row(const double *part, int nrows, int row, int nchunks)
+{
+    double s = 0.0;
+    for (int c = 0; c < nchunks; c++) s += part[(size_t)c * nrows + row];
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fast tiled (many targets).  Block = 256 threads, R rows per thread (row = base + r*256 + tid: coalesced),
+// sources [c0, c1) of the block's chunk in tiles of FT_TILE.
+// ---------------------------------------------------------------------------------------------------
+#define FT_THREADS 256
+#define FT_TILE 512
+
+template <int R, class Tgt>
+__device__ __forceinline__ void fast_tiled_block(const SrcView &S, const Tgt &T, int nrows, int row_block, int c0,
+                                                 int c1, double *__restrict__ pu, double *__restrict__ pw_,
+                                                 double *sx, double *sz, double *sg, double *sv)
+{
+    double tx[R], tz[R], au[R], aw[R];
+    int base = row_block * (FT_THREADS * R) + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        int row = min(base + r * FT_THREADS, nrows - 1);
+        T.get(row, tx[r], tz[r]);
+        au[r] = 0.0;
+        aw[r] = 0.0;
+    }
+    for (int t0 = c0; t0 < c1; t0 += FT_TILE) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < FT_TILE; j += FT_THREADS) {
+            int s = t0 + j;
+            bool ok = s < c1;
+            int p = ok ? S.phys(s) : 0;
+            sx[j] = ok ? S.x[p] : 0.0;
+            sz[j] = ok ? S.z[p] : 0.0;
+            sg[j] = ok ? S.g[p * S.gstride] * LUDVM_INV_TWO_PI : 0.0;
+            sv[j] = ok ? (S.vc4 ? S.vc4[p] : S.vc4s) : 1.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int j = 0; j < FT_TILE; j++) {
+            double x = sx[j], z = sz[j], g = sg[j], v = sv[j];
+#pragma unroll
+            for (int r = 0; r < R; r++) pair_fast(tx[r], tz[r], x, z, g, v, au[r], aw[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        int row = base + r * FT_THREADS;
+        if (row < nrows) {
+            pu[row] = au[r];
+            pw_[row] = aw[r];
+        }
+    }
+}
+
+// fp32 pair arithmetic; R rows per thread.
+template <int R, class Tgt>
+__device__ __forceinline__ void fast32_tiled_block(const SrcView &S, const Tgt &T, int nrows, int row_block, int c0,
+                                                   int c1, double *__restrict__ pu, double *__restrict__ pw_,
+                                                   float4 *ssrc)
+{
+    float tx[R], tz[R];
+    double au[R], aw[R];  // per-tile fp32 sums are flushed into fp64 row accumulators
+    int base = row_block * (FT_THREADS * R) + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        int row = min(base + r * FT_THREADS, nrows - 1);
+        double xd, zd;
+        T.get(row, xd, zd);
+        tx[r] = (float)xd;
+        tz[r] = (float)zd;
+        au[r] = 0.0;
+        aw[r] = 0.0;
+    }
+    for (int t0 = c0; t0 < c1; t0 += FT_TILE) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < FT_TILE; j += FT_THREADS) {
+            int s = t0 + j;
+            bool ok = s < c1;
+            int p = ok ? S.phys(s) : 0;
+            float4 v;
+            v.x = ok ? (float)S.x[p] : 0.f;
+            v.y = ok ? (float)S.z[p] : 0.f;
+            v.z = ok ? (float)(S.g[p * S.gstride] * LUDVM_INV_TWO_PI) : 0.f;
+            v.w = ok ? (float)(S.vc4 ? S.vc4[p] : S.vc4s) : 1.f;
+            ssrc[j] = v;
+        }
+        __syncthreads();
+        float fu[R], fw[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            fu[r] = 0.f;
+            fw[r] = 0.f;
+        }
+#pragma unroll 8
+        for (int j = 0; j < FT_TILE; j++) {
+            float4 v = ssrc[j];
+#pragma unroll
+            for (int r = 0; r < R; r++) pair_fast32(tx[r], tz[r], v.x, v.y, v.z, v.w, fu[r], fw[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            au[r] += (double)fu[r];
+            aw[r] += (double)fw[r];
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        int row = base + r * FT_THREADS;
+        if (row < nrows) {
+            pu[row] = au[r];
+            pw_[row] = aw[r];
+        }
+    }
+}
+
+}  // namespace ludvm

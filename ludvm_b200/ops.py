@@ -1,0 +1,69 @@
+"""Array-level entry points over the C ABI (numpy in / numpy out, or torch CUDA tensors in place)."""
+import numpy as np
+
+from . import _lib
+from ._lib import MODES, PTR_DEVICE, PTR_HOST, check, f64, load, ptr
+
+
+def _mode(mode):
+    return MODES[mode] if isinstance(mode, str) else int(mode)
+
+
+def induced_velocity(circulation, xw, zw, xp, zp, v_core, viscous=True, mode="exact", ctx=None, vc4_per_source=None):
+    """LUDVM.induced_velocity (LUDVM.py:549-570) on the GPU with host (numpy) buffers.
+
+    `v_core` is the core radius (the reference reads `self.v_core`); `viscous=False` uses point vortices."""
+    ctx = ctx or _lib.default_context()
+    g, xw, zw, xp, zp = (f64(np.atleast_1d(a)) for a in (circulation, xw, zw, xp, zp))
+    if xw.size != zw.size or xp.size != zp.size or g.size not in (1, xw.size):
+        raise ValueError("shape mismatch: circulation %d, xw %d, zw %d, xp %d, zp %d"
+                         % (g.size, xw.size, zw.size, xp.size, zp.size))
+    vc4 = float(v_core) ** 4 if viscous == True else 0.0  # noqa: E712 (LUDVM.py:562 compares with ==)
+    vcs = f64(vc4_per_source) if vc4_per_source is not None else None
+    u, w = np.empty(xp.size), np.empty(xp.size)
+    check(load().ludvm_induced_velocity(ctx.handle, _mode(mode), ptr(g), g.size, ptr(xw), ptr(zw), ptr(vcs), vc4,
+                                        xw.size, ptr(xp), ptr(zp), xp.size, ptr(u), ptr(w), PTR_HOST))
+    return u, w
+
+
+def induced_velocity_device(ctx, mode, g, xw, zw, xp, zp, vc4, u, w, vc4_per_source=None):
+    """Same with torch CUDA float64 tensors (results written into u, w; asynchronous on ctx's stream)."""
+    check(load().ludvm_induced_velocity(ctx.handle, _mode(mode), ptr(g), g.numel(), ptr(xw), ptr(zw),
+                                        ptr(vc4_per_source), float(vc4), xw.numel(), ptr(xp), ptr(zp), xp.numel(),
+                                        ptr(u), ptr(w), PTR_DEVICE))
+
+
+def selfconv_step(ctx, mode, g, x, z, vc4, dt, x_out, z_out, row0=0, nrows=None, u_out=None, w_out=None,
+                  vc4_per_source=None):
+    """One forward-Euler self-convection step of rows [row0, row0+nrows) (torch CUDA float64 tensors)."""
+    n = x.numel()
+    nrows = n - row0 if nrows is None else nrows
+    check(load().ludvm_selfconv_step(ctx.handle, _mode(mode), ptr(g), ptr(x), ptr(z), ptr(vc4_per_source), float(vc4),
+                                     n, int(row0), int(nrows), float(dt), ptr(x_out), ptr(z_out), ptr(u_out),
+                                     ptr(w_out)))
+
+
+def flowfield_velocity(ga, xa, za, gb, xb, zb, vc4, x1, z1, row0=0, nrows=None, mode="exact", ctx=None):
+    """Velocity of up to two source sets on the 'ij' mesh x1 x z1 (LUDVM.py:1193-1220), host buffers."""
+    ctx = ctx or _lib.default_context()
+    ga, xa, za, x1, z1 = (f64(a) for a in (ga, xa, za, x1, z1))
+    nb = 0 if gb is None else len(gb)
+    if nb:
+        gb, xb, zb = (f64(a) for a in (gb, xb, zb))
+    nrows = x1.size - row0 if nrows is None else nrows
+    u, w = np.empty((nrows, z1.size)), np.empty((nrows, z1.size))
+    check(load().ludvm_flowfield_velocity(ctx.handle, _mode(mode), ptr(ga), ptr(xa), ptr(za), ga.size,
+                                          ptr(gb) if nb else None, ptr(xb) if nb else None, ptr(zb) if nb else None,
+                                          nb, float(vc4), ptr(x1), x1.size, ptr(z1), z1.size, int(row0), int(nrows),
+                                          ptr(u), ptr(w), PTR_HOST))
+    return u, w
+
+
+def flowfield_vorticity(x1, z1, u, w, ctx=None):
+    """Finite-difference vorticity of LUDVM.py:1222-1292 on [ns,nx,nz] fields, host buffers."""
+    ctx = ctx or _lib.default_context()
+    x1, z1, u, w = (f64(a) for a in (x1, z1, u, w))
+    ome = np.empty_like(u)
+    check(load().ludvm_flowfield_vorticity(ctx.handle, ptr(x1), x1.size, ptr(z1), z1.size, ptr(u), ptr(w), u.shape[0],
+                                           ptr(ome), PTR_HOST))
+    return ome
