@@ -119,6 +119,7 @@ typedef struct {
     double dt, Uinf, chord, rho, piv, lespcrit;
     double vc4;        /* v_core**4                            LUDVM.py:260, :565 */
     double ic;         /* circulation['IC']                    LUDVM.py:649 */
+    double sum_free;   /* np.sum(circulation['FREE'])          LUDVM.py:759 */
     double a0_init, a1_init; /* fourier[0,0,:2]                LUDVM.py:645-647 */
     double maxerror, epsilon; /* Newton constants              LUDVM.py:248-250 */
     int64_t maxiter;

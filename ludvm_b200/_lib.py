@@ -28,7 +28,7 @@ class SimParams(C.Structure):
                 ("method", C.c_int32), ("mode", C.c_int32), ("store_history", C.c_int32),
                 ("steps_per_graph", C.c_int32),
                 ("dt", C.c_double), ("Uinf", C.c_double), ("chord", C.c_double), ("rho", C.c_double),
-                ("piv", C.c_double), ("lespcrit", C.c_double), ("vc4", C.c_double), ("ic", C.c_double),
+                ("piv", C.c_double), ("lespcrit", C.c_double), ("vc4", C.c_double), ("ic", C.c_double), ("sum_free", C.c_double),
                 ("a0_init", C.c_double), ("a1_init", C.c_double), ("maxerror", C.c_double),
                 ("epsilon", C.c_double), ("maxiter", C.c_int64)]
 
@@ -109,11 +109,17 @@ def ptr(a):
 
 
 class Context:
-    """One device + stream + scratch.  `stream` is a raw cudaStream_t (int) or None for a private stream."""
+    """One device + stream + scratch.  `stream` is a raw cudaStream_t (int), e.g.
+    `torch.cuda.current_stream().cuda_stream`; 0 means the legacy default stream (PyTorch's default stream);
+    None lets the library create a private non-blocking stream."""
+
+    CUDA_STREAM_LEGACY = 0x1
 
     def __init__(self, device=0, stream=None):
         self._h = c_vp()
-        check(load().ludvm_ctx_create(int(device), c_vp(stream) if stream else None, C.byref(self._h)))
+        if stream is not None and int(stream) == 0:
+            stream = self.CUDA_STREAM_LEGACY
+        check(load().ludvm_ctx_create(int(device), c_vp(stream) if stream is not None else None, C.byref(self._h)))
         self.device = int(device)
 
     @property

@@ -11,9 +11,9 @@ LIB = os.path.join(HERE, "libludvm_b200.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
-# Per-file flags.  sim_step.cu holds the scalar phases of the time step, written as plain C expressions that
+# Per-file flags.  sim.cu holds the scalar phases of the time step, written as plain C expressions that
 # must not be contracted into FMAs (bit parity with numpy).
-PER_FILE = {"sim_step.cu": ["-fmad=false"]}
+PER_FILE = {"sim.cu": ["-fmad=false"]}
 
 
 def _nvcc():

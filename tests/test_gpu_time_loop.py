@@ -1,0 +1,127 @@
+"""GPU parity tests of the on-device time loop (C ABI ludvm_sim_*, replacing LUDVM.time_loop,
+LUDVM.py:597-1171) against the golden histories of the unmodified reference and against the CPU oracle."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from conftest import biteq, golden_tables, load_golden
+
+pytestmark = pytest.mark.gpu
+
+HIST = ("Fn", "Fs", "L", "D", "T", "M", "LESP", "LESP_prev", "LEV_shed", "fourier")
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _kw(g):
+    kw = dict(g["kw"])
+    for k in ("circulation_freevort", "xy_freevort"):
+        if k in kw:
+            kw[k] = np.array(kw[k])
+    return kw
+
+
+def _run_from_tables(g, **extra):
+    from ludvm_b200 import LUDVM
+    tb = golden_tables(g)
+    tb["sum_free"] = float(np.sum(tb["free_g"]))
+    s = LUDVM(**_kw(g), verbose=False, run=False, **extra)
+    s.time_loop(tables=tb)
+    s.compute_coefficients()
+    return s
+
+
+@pytest.mark.parametrize("name", ["readme", "freevort_tf3", "hires_200"])
+def test_exact_mode_bit_equal_to_reference_golden(name):
+    """Exact mode from the fixture's host tables: every stored output of the reference run is reproduced
+    bit-for-bit (BASELINE.json asks Cl/Cd/Cm/LESP within 1e-8 over the full run; the run is chaotic, so this
+    is the only way to meet it -- SURVEY.md 4.3)."""
+    g = load_golden(name)
+    s = _run_from_tables(g)
+    for k in HIST + ("Cl", "Cd", "Cm", "Cn", "Cs", "Ct"):
+        assert biteq(getattr(s, k), g[k]), k
+    for k in ("TEV", "LEV", "bound"):
+        assert biteq(s.circulation[k], g["circ_" + k]), k
+    for k in ("airfoil", "gamma_airfoil", "Gamma_airfoil"):
+        assert biteq(s.circulation[k][g["circ_rows"]], g["circ_" + k + "_rows"]), k
+        assert sha(s.circulation[k]) == str(g["circ_" + k + "_sha256"]), k
+    for k in ("TEV", "LEV", "FREE"):
+        assert biteq(s.path[k][g["path_rows"]], g["path_" + k + "_rows"]), k
+        assert sha(s.path[k]) == str(g["path_" + k + "_sha256"]), k
+    assert [s.itev, s.ilev] == list(g["itev_ilev"])
+    assert s.steps_done == s.nt - 1
+
+
+def test_readme_tolerance_statement():
+    """The BASELINE.json tolerance as written: Cl, Cd, Cm, LESP within 1e-8 relative over the full README run."""
+    g = load_golden("readme")
+    s = _run_from_tables(g)
+    for k in ("Cl", "Cd", "Cm", "LESP"):
+        ref = g[k]
+        assert np.max(np.abs(getattr(s, k) - ref)) <= 1e-8 * np.max(np.abs(ref)), k
+
+
+@pytest.mark.parametrize("over", [dict(tf=6), dict(tf=4, LESPcrit=0.11, k=0.9),
+                                  dict(tf=3, dt=2e-2, Npoints=61, Ncoeffs=12, chord=1.3, Uinf=1.7, alpha_m=3,
+                                       alpha_max=20, k=0.7),
+                                  dict(tf=1.0, dt=2e-3)])
+def test_exact_mode_full_class_vs_oracle(oracle, over):
+    """The whole drop-in class (own host geometry/kinematics) against the oracle on the same host."""
+    from ludvm_b200 import LUDVM
+    kw = dict(t0=0, tf=20, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012")
+    kw.update(over)
+    s = LUDVM(**kw, verbose=False)
+    o = oracle.OracleLUDVM(**kw)
+    for k in ("alpha", "alpha_dot", "h_dot", "alpha_e"):
+        assert biteq(getattr(s, k), getattr(o, k)), k
+    for k in ("airfoil", "airfoil_gamma_points"):
+        assert biteq(s.path[k], o.path[k]), k
+    for k in s.airfoil:
+        assert biteq(s.airfoil[k], o.airfoil[k]), k
+    for k in HIST + ("Cl", "Cd", "Cm"):
+        assert biteq(getattr(s, k), getattr(o, k)), k
+    for k in ("TEV", "LEV", "FREE"):
+        assert biteq(s.path[k], o.path[k]), k
+    for k in ("TEV", "LEV", "bound", "airfoil", "gamma_airfoil", "Gamma_airfoil"):
+        assert biteq(s.circulation[k], o.circulation[k]), k
+    assert (s.itev, s.ilev) == (o.itev, o.ilev)
+
+
+def test_steps_per_graph_and_chunking_do_not_change_results():
+    g = load_golden("freevort_tf3")
+    a = _run_from_tables(g, steps_per_graph=7)
+    b = _run_from_tables(g, steps_per_graph=60)
+    for k in ("L", "M", "LESP"):
+        assert biteq(getattr(a, k), getattr(b, k)) and biteq(getattr(a, k), g[k])
+    assert biteq(a.path["TEV"], b.path["TEV"])
+
+
+def test_fast_mode_tracks_reference_before_chaos():
+    """Fast (FMA) arithmetic is not bit-exact; it must stay inside the reference's own re-ordering envelope
+    (1e-12 by step 100, 3e-10 by step 200) and obey the invariants of SURVEY.md 4.2."""
+    g = load_golden("readme")
+    s = _run_from_tables(g, mode="fast")
+    ref = g["Cl"]
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(s.Cl[:100] - ref[:100])) <= 1e-9 * scale
+    assert np.max(np.abs(s.Cl[:200] - ref[:200])) <= 1e-6 * scale
+    assert np.array_equal(s.LEV_shed[:200], g["LEV_shed"][:200])
+    nt = s.nt
+    # Kelvin: bound + shed circulation is conserved (IC = 0 here)
+    cs_t, cs_l = np.cumsum(s.circulation["TEV"]), np.cumsum(s.circulation["LEV"])
+    nlev = np.cumsum(s.LEV_shed[1:] != -1)
+    lev_sum = np.where(nlev > 0, cs_l[np.maximum(nlev - 1, 0)], 0.0)
+    assert np.max(np.abs(s.circulation["bound"] + cs_t + lev_sum)) < 1e-12
+    assert np.max(np.abs(s.LESP[:nt - 1])) <= 0.2 + 1e-14
+
+
+def test_no_history_mode():
+    g = load_golden("hires_200")
+    s = _run_from_tables(g, store_history=False)
+    assert biteq(s.L, g["L"]) and biteq(s.M, g["M"])
+    assert "TEV" not in s.path
+    last = g["path_TEV_rows"][-1]   # row 200 = final positions
+    assert biteq(s.path["TEV_last"], last)
