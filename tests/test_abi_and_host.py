@@ -1,0 +1,92 @@
+"""CPU tests: the C-ABI library loads and exports every symbol include/ludvm_b200.h declares (no compute without a
+GPU), fails loudly without a device, and the host-side logic of the drop-in class matches the oracle's tables."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, biteq
+
+
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "ludvm_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(ludvm_[a-z0-9_]+)\s*\(", txt)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as ge
+    ge.build()
+    from ludvm_b200 import _lib
+    return _lib
+
+
+def test_library_exports_every_declared_symbol(built):
+    L = ctypes.CDLL(built.LIB_PATH)
+    syms = _declared_symbols()
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(L, s), "missing export: " + s
+    assert set(syms) == set(built.SIGNATURES), "ctypes binding and header disagree"
+    assert built.load().ludvm_abi_version() == 1
+
+
+def test_no_cpu_fallback(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(built.LudvmError, match="no CUDA device"):
+        built.Context(0)
+    from ludvm_b200 import ops
+    with pytest.raises(built.LudvmError):
+        ops.induced_velocity(np.ones(3), np.zeros(3), np.zeros(3), np.ones(2), np.ones(2), 0.1)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ludvm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "ludvm_oracle" not in txt, f
+
+
+@pytest.mark.parametrize("over", [dict(), dict(dt=1e-2, tf=2, Npoints=61, Ncoeffs=12, chord=1.3, Uinf=1.7, alpha_m=3,
+                                               alpha_max=20, k=0.7, h_max=0.4, phi=75)])
+def test_host_tables_equal_oracle_tables(oracle, over):
+    from ludvm_b200 import LUDVM
+    kw = dict(t0=0, tf=20, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012")
+    kw.update(over)
+    s = LUDVM(**kw, verbose=False, run=False)
+    o = oracle.OracleLUDVM(**kw, run=False)
+    ts, to = s.step_tables(), oracle.tables_from(o)
+    for k, v in to.items():
+        assert biteq(ts[k], v) if isinstance(v, np.ndarray) else ts[k] == v, k
+    assert ts["sum_free"] == float(np.sum(o.circulation_freevort))
+    for k in o.airfoil:
+        assert biteq(s.airfoil[k], o.airfoil[k]), k
+
+
+def test_host_tables_equal_golden_tables():
+    """Same check against the tables of the real reference run (committed fixture)."""
+    from conftest import golden_tables, load_golden
+    from ludvm_b200 import LUDVM
+    g = load_golden("readme")
+    s = LUDVM(**g["kw"], verbose=False, run=False)
+    if not biteq(s.alpha, g["alpha"]):
+        pytest.skip("this host's libm rounds differently from the fixture's host")
+    ts, tg = s.step_tables(), golden_tables(g)
+    for k, v in tg.items():
+        assert biteq(ts[k], v) if isinstance(v, np.ndarray) else ts[k] == v, k
+
+
+def test_motion_plunge_fixed_and_cambered_section():
+    from ludvm_b200 import LUDVM
+    s = LUDVM(tf=3, dt=5e-2, Npoints=41, verbose=False, run=False, Naca="2412")
+    assert s.airfoil["eta"].max() > 0.015 and abs(s.airfoil["eta"][0]) < 1e-15
+    s.motion_plunge(G=1, T=2)          # the reference raises TypeError here (LUDVM.py:520)
+    assert s.alpha_e.shape == (s.nt,) and np.all(np.diff(s.hpiv) <= 1e-15)
+    assert s.hpiv[-1] == s.hpiv[np.searchsorted(s.t, 2.0, side="right") - 1]
