@@ -556,6 +556,8 @@ struct ludvm_sim {
     int K = 50;
     std::map<int, cudaGraphExec_t> graphs;  // (bracket, length) -> instantiated graph
     size_t solve_smem = 0, finish_smem = 0;
+    cudaStream_t cap_stream = nullptr;  // private stream used only to record graphs (the context's stream may be
+                                        // the legacy default stream, which cannot be captured)
 };
 
 namespace ludvm {
@@ -618,15 +620,17 @@ static int build_graph(ludvm_sim *s, int bracket, int ksteps, cudaGraphExec_t *o
     int g4 = 1 + (int)std::max<long>(1, std::min<long>((nw + 255) / 256, (long)sm * 8));
 
     cudaGraph_t graph;
-    CUDA_TRY(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+    if (!s->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
+    cudaStream_t cs = s->cap_stream;
+    CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
     for (int k = 0; k < ksteps; k++) {
-        k_wake_on_foil<<<g1, 256, 0, ctx->stream>>>(D, k);
-        k_solve<<<1, SOLVE_THREADS, s->solve_smem, ctx->stream>>>(D, k);
-        k_conv_partials<<<g3, 256, 0, ctx->stream>>>(D, k);
-        k_finish<<<g4, 256, s->finish_smem, ctx->stream>>>(D, k);
+        k_wake_on_foil<<<g1, 256, 0, cs>>>(D, k);
+        k_solve<<<1, SOLVE_THREADS, s->solve_smem, cs>>>(D, k);
+        k_conv_partials<<<g3, 256, 0, cs>>>(D, k);
+        k_finish<<<g4, 256, s->finish_smem, cs>>>(D, k);
     }
-    k_advance<<<1, 1, 0, ctx->stream>>>(D, ksteps);
-    cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+    k_advance<<<1, 1, 0, cs>>>(D, ksteps);
+    cudaError_t e = cudaStreamEndCapture(cs, &graph);
     if (e != cudaSuccess) return set_error(LUDVM_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
     e = cudaGraphInstantiate(out, graph, 0);
     cudaGraphDestroy(graph);
@@ -850,6 +854,7 @@ LUDVM_API int ludvm_sim_destroy(ludvm_sim *s)
     DeviceGuard g(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
     for (auto &kv : s->graphs) cudaGraphExecDestroy(kv.second);
+    if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     for (void *p : s->allocs) cudaFree(p);
     delete s;
     return LUDVM_OK;
