@@ -170,6 +170,20 @@ int ludvm_sim_field_bytes(ludvm_sim *sim, int field, size_t *out);
 int ludvm_sim_destroy(ludvm_sim *sim);
 
 /*
+ * Batched parameter sweep (BASELINE.json configs[3]: e.g. 4096 cases LESPcrit x reduced frequency): `ncases`
+ * independent time loops, one persistent CTA per case, all steps in one launch, no collective.  All cases must
+ * share nt, P, Nc, nfree; table sets shared by several cases (identical host pointers) are uploaded once.
+ * out is a host buffer [ncases][LUDVM_SWEEP_FIELDS][nt] (out_doubles_per_case = LUDVM_SWEEP_FIELDS * nt) with rows
+ * Fn, Fs, L, D, T, M, LESP, LESP_prev, LEV_shed, circulation TEV, LEV, bound (the last three hold nt-1 values).
+ * To split a sweep over GPUs call it once per device with that device's slice of the cases.
+ */
+#define LUDVM_SWEEP_FIELDS 12
+enum { LUDVM_SW_FN = 0, LUDVM_SW_FS, LUDVM_SW_L, LUDVM_SW_D, LUDVM_SW_T, LUDVM_SW_M, LUDVM_SW_LESP,
+       LUDVM_SW_LESP_PREV, LUDVM_SW_LEV_SHED, LUDVM_SW_G_TEV, LUDVM_SW_G_LEV, LUDVM_SW_G_BOUND };
+int ludvm_sweep_run(ludvm_ctx *ctx, long ncases, const ludvm_sim_params *params, const ludvm_sim_tables *tables,
+                    double *out, size_t out_doubles_per_case);
+
+/*
  * Roofline denominator: sustained FP64 FMA issue rate of this GPU, measured with a register-resident DFMA
  * chain kernel (MEASURED_PEAKS.json has no FP64 entry).  Returns DFMA/s (x2 = FLOP/s) over `ms_target` ms.
  */

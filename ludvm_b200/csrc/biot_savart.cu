@@ -144,15 +144,17 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
     }
     const bool f32 = (mode == LUDVM_FAST_F32);
     if (f32 || nrows >= 8192) {
-        int R = 4;
-        if (!f32) {
-            while (R > 1 && ceil_div(nrows, FT_THREADS * R) < sm) R >>= 1;
-        }
-        int row_blocks = ceil_div(nrows, FT_THREADS * R);
-        long target = (long)sm * 2 * 6;
-        long chunks = std::max(1L, std::min((target + row_blocks - 1) / row_blocks, (long)S.n / (FT_TILE * 2)));
+        // The source chunking depends on the number of SOURCES only, so a row's sum does not depend on how the
+        // target rows are sharded over GPUs (G-rank results are bitwise equal to 1-rank results); the rows-per-
+        // thread factor R adapts to the number of rows to keep >= ~6 waves of 2 CTAs/SM in flight.
+        long chunks = std::max(1L, std::min(8L, (long)S.n / (FT_TILE * 2)));
         int chunk_len = (int)(((S.n + chunks - 1) / chunks + FT_TILE - 1) / FT_TILE * FT_TILE);
         chunks = ((long)S.n + chunk_len - 1) / chunk_len;
+        int R = 4;
+        if (!f32) {
+            while (R > 1 && (long)ceil_div(nrows, FT_THREADS * R) * chunks < (long)sm * 2 * 6) R >>= 1;
+        }
+        int row_blocks = ceil_div(nrows, FT_THREADS * R);
         size_t bytes = sizeof(double) * (size_t)nrows * (size_t)chunks;
         void *a, *b;
         int rc;

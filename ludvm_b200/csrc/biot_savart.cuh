@@ -77,7 +77,18 @@ __device__ __forceinline__ void exact_leaf_group(const SrcView &S, double xp, do
     double au = -0.0, aw = -0.0;
     if (body) {
         exact_term(S, xp, zp, off + lane8, au, aw);
-        for (int i = 8; i < body; i += 8) {
+        int i = 8;
+        // four independent pair evaluations in flight (the div/sqrt chains are long); the adds keep numpy's order
+        for (; i + 24 < body; i += 32) {
+            double t0u, t0w, t1u, t1w, t2u, t2w, t3u, t3w;
+            exact_term(S, xp, zp, off + i + lane8, t0u, t0w);
+            exact_term(S, xp, zp, off + i + 8 + lane8, t1u, t1w);
+            exact_term(S, xp, zp, off + i + 16 + lane8, t2u, t2w);
+            exact_term(S, xp, zp, off + i + 24 + lane8, t3u, t3w);
+            au = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(au, t0u), t1u), t2u), t3u);
+            aw = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(aw, t0w), t1w), t2w), t3w);
+        }
+        for (; i < body; i += 8) {
             double tu, tw;
             exact_term(S, xp, zp, off + i + lane8, tu, tw);
             au = __dadd_rn(au, tu);

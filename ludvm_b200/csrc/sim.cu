@@ -1,25 +1,29 @@
-// sim.cu -- the on-device time step of LUDVM.time_loop (LUDVM.py:597-1171), replayed as a CUDA graph.
+// sim.cu -- the on-device time step of LUDVM.time_loop (LUDVM.py:597-1171).
 //
 // This translation unit is compiled with -fmad=false: the scalar phases of the step are written as plain C
 // expressions in the reference's operation order and must not be contracted into FMAs.
 // The fast pair arithmetic uses explicit fma() and is unaffected.
 //
-// One time step i (Faure method) = four kernels; the vortex state (x, z, Gamma of TEV | LEV | FREE) stays in
-// HBM in one SoA with three fixed segments, addressed through the logical->physical map of SrcView so that the
-// reference's np.append(TEV[:..], LEV[:..], FREE) ordering -- which fixes the shape of numpy's summation tree --
-// is reproduced without moving data:
+// The vortex state (x, z, Gamma of TEV | LEV | FREE) stays in HBM in one SoA with three fixed segments, addressed
+// through the logical->physical map of SrcView so that the reference's np.append(TEV[:..], LEV[:..], FREE)
+// ordering -- which fixes the shape of numpy's summation tree -- is reproduced without moving data.
 //
-//   k_wake_on_foil   partial sums of the existing wake at the P gamma points           (LUDVM.py:743-746)
-//   k_solve          1 CTA: TEV placement, T1/T2/T3, Kelvin + LESP 2x2 solve, Fourier coefficients, bound
-//                    vortex distribution                                              (LUDVM.py:672-681, 741-1010)
-//   k_conv_partials  partial sums of the updated wake at the gamma points (loads) and at every wake vortex
-//                    (convection), plus the bound vortices on the wake                (LUDVM.py:1049-1054, 1095-1124)
-//   k_finish         block 0: loads Fn, Fs, L, D, T, M; other blocks: fold partials, forward-Euler update in
-//                    place, history snapshot                                          (LUDVM.py:1069-1090, 1108-1127)
-//
-// The step index is read from device memory (counters[0] + offset baked into the node), so one captured graph of
-// K steps is replayed for the whole run; the number of vortices is read from device memory too, kernels are
-// grid-stride over tasks, and graphs are cached per power-of-two bracket of the vortex-count upper bound.
+// One time step i is four phases (device functions below):
+//   phase_wake_on_foil   partial sums of the existing wake at the P gamma points          (LUDVM.py:743-746)
+//   phase_solve          one CTA: TEV placement, T1/T2/T3, Kelvin + LESP solve (Faure closed form / 2x2, or the
+//                        Ramesh Newton iterations), Fourier coefficients, bound vortices  (LUDVM.py:672-1010)
+//   phase_conv_partials  partial sums of the updated wake at the gamma points (loads) and at every wake vortex
+//                        (convection), plus the bound vortices on the wake               (LUDVM.py:1049-1054, 1095-1124)
+//   phase_finish_*       loads Fn, Fs, L, D, T, M; fold partials, forward-Euler update in place, history snapshot
+//                                                                                         (LUDVM.py:1069-1090, 1108-1127)
+// and two drivers run them:
+//   * graph path  -- four kernels per step, grid-wide warp pools, K steps captured once in a CUDA graph and replayed
+//                    (step index and vortex counts are read from device memory; graphs cached per power-of-two
+//                    bracket of the wake size).  Used for one simulation of any size (configs 1, 2).
+//   * CTA path    -- k_sim_cta: one persistent CTA runs ALL steps of one case with __syncthreads() between phases;
+//                    cases are pulled from an atomic counter.  Used for batched parameter sweeps (config 4: 4096
+//                    independent cases, no collective) and for method='Ramesh', whose Newton loops have a
+//                    data-dependent trip count.
 #include <algorithm>
 #include <map>
 
@@ -29,16 +33,21 @@ namespace ludvm {
 
 #define SIM_DMAX 11          // at most 2^11 tree nodes per row are evaluated by separate warps
 #define SOLVE_THREADS 256
-#define SUM_NODES_MAX 4096   // block_np_sum: tree nodes held in shared memory
+#define CTA_THREADS 256
+#define RAMESH_THREADS 1024
+#define PI_D 3.141592653589793
 
 struct SimDev {
     int nt, P, Nc, nfree, nv, method, mode, store_history;
-    int target_warps;  // parallelism target used to pick split depths (same value in every kernel)
-    double dt, Uinf, chord, rho, piv, vc4, ic, sum_free, maxerror, epsilon;
+    int target_warps;   // parallelism target used to pick split depths (same value in every phase of a case)
+    int sum_nodes;      // block_np_sum: tree nodes held in shared memory (power of two)
+    int af_stride;      // row stride of the [nv,P] bound-vortex arrays (P, or 0 in compact sweep mode)
+    int fourier_rows;   // nt, or 2 in compact sweep mode (row i lives at i % fourier_rows)
+    double dt, Uinf, chord, rho, piv, vc4, ic, sum_free, maxerror, epsilon, lespcrit0, a0_init, a1_init;
     int maxiter;
     // tables
     const double *cos_a, *sin_a, *alpha_dot, *h_dot, *gp, *le, *te;
-    const double *detadx_p, *eta_p, *x_p, *theta_p, *dtheta, *cos_tp, *sin_tp, *cosn, *sinn;
+    const double *detadx_p, *eta_p, *x_p, *theta_p, *dtheta, *cos_tp, *sin_tp, *cosn, *sinn, *free_g, *free_xz;
     // resident vortex state: [TEV nv | LEV nv | FREE nfree]
     double *wx, *wz, *wg;
     // results
@@ -50,8 +59,8 @@ struct SimDev {
     int *ilev_arr;        // [nt+1]: ilev at the start of step i
     double *lespcrit_cur; // sign-carrying LESPcrit (LUDVM.py:802-805)
     // scratch
-    double *pa_u, *pa_w;  // phase-C partials   [2^d1][P]
-    double *pb_u, *pb_w;  // loads+convection partials [2^d2][P + Nw2]
+    double *pa_u, *pa_w;  // wake-on-foil partials        [2^d1][P]
+    double *pb_u, *pb_w;  // loads+convection partials    [2^d2][P + Nw2]
     double *foil_u, *foil_w;  // bound vortices on the wake [Nw2]
 };
 
@@ -62,7 +71,7 @@ __host__ __device__ __forceinline__ int ilog2_ceil_i(int v)
     return l;
 }
 
-// Split depth for `nrows` target rows against n sources (identical on host and device, in every kernel).
+// Split depth for `nrows` target rows against n sources (identical on host and device, in every phase).
 __host__ __device__ __forceinline__ int sim_depth(int n, int nrows, int target_warps)
 {
     int quads = (nrows + 3) >> 2;
@@ -81,6 +90,31 @@ __host__ __device__ __forceinline__ int sim_chunks(int n, int nrows, int target_
 struct Step {
     int i, itev, ilev;
 };
+
+struct Pool {  // the warps / threads that cooperate on a phase
+    int wid, nwarps, lane, tid, nth;
+};
+
+__device__ __forceinline__ Pool grid_pool()
+{
+    Pool p;
+    p.lane = threadIdx.x & 31;
+    p.wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    p.nwarps = gridDim.x * (blockDim.x >> 5);
+    p.tid = blockIdx.x * blockDim.x + threadIdx.x;
+    p.nth = gridDim.x * blockDim.x;
+    return p;
+}
+__device__ __forceinline__ Pool block_pool()
+{
+    Pool p;
+    p.lane = threadIdx.x & 31;
+    p.wid = threadIdx.x >> 5;
+    p.nwarps = blockDim.x >> 5;
+    p.tid = threadIdx.x;
+    p.nth = blockDim.x;
+    return p;
+}
 
 __device__ __forceinline__ bool step_begin(const SimDev &S, int s, Step &st)
 {
@@ -135,37 +169,53 @@ struct TgtWake {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// kernel 1: existing wake on the gamma points (LUDVM.py:743-746 -> :584)
+// phase 1: wake TEV[:nT] ++ LEV[:nL] ++ FREE on the gamma points (LUDVM.py:584 via :692, :746)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_wake_on_foil(SimDev S, int s)
+__device__ __forceinline__ void phase_wake_on_foil(const SimDev &S, const Step &st, int nT, int nL, const Pool &pl)
 {
-    Step st;
-    if (!step_begin(S, s, st)) return;
-    SrcView W = wake_view(S, st.itev, st.ilev);
+    SrcView W = wake_view(S, nT, nL);
     TgtGamma T{S.gp + ((size_t)st.i * 2 + 0) * S.P, S.gp + ((size_t)st.i * 2 + 1) * S.P};
-    int lane = threadIdx.x & 31;
-    long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     long nquads = (S.P + 3) >> 2;
     if (S.mode == LUDVM_EXACT_F64) {
         int d = sim_depth(W.n, S.P, S.target_warps);
-        for (long t = gw; t < (nquads << d); t += nwarps) exact_rows_warp_task(W, T, S.P, d, t, lane, S.pa_u, S.pa_w);
+        for (long t = pl.wid; t < (nquads << d); t += pl.nwarps)
+            exact_rows_warp_task(W, T, S.P, d, t, pl.lane, S.pa_u, S.pa_w);
     } else {
         int c = sim_chunks(W.n, S.P, S.target_warps);
-        for (long t = gw; t < nquads * c; t += nwarps) fast_rows_warp_task(W, T, S.P, c, t, lane, S.pa_u, S.pa_w);
+        for (long t = pl.wid; t < nquads * c; t += pl.nwarps)
+            fast_rows_warp_task(W, T, S.P, c, t, pl.lane, S.pa_u, S.pa_w);
+    }
+}
+
+// Fold the phase-1 partials into u1, w1 (block-strided).
+__device__ __forceinline__ void fold_wake_on_foil(const SimDev &S, int n1, double *u1, double *w1)
+{
+    const int P = S.P;
+    if (S.mode == LUDVM_EXACT_F64) {
+        int d = sim_depth(n1, P, S.target_warps);
+        for (int j = threadIdx.x; j < P; j += blockDim.x) {
+            u1[j] = exact_combine_row(S.pa_u, P, j, d);
+            w1[j] = exact_combine_row(S.pa_w, P, j, d);
+        }
+    } else {
+        int c = sim_chunks(n1, P, S.target_warps);
+        for (int j = threadIdx.x; j < P; j += blockDim.x) {
+            u1[j] = fast_combine_row(S.pa_u, P, j, c);
+            w1[j] = fast_combine_row(S.pa_w, P, j, c);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// kernel 2: the scalar phases (one CTA)
+// phase 2 helpers
 // ---------------------------------------------------------------------------------------------------
 
 // np.sum(a[:n]) by the whole block: tree nodes at depth d are summed by one thread each, thread 0 folds them.
-__device__ double block_np_sum(const double *a, int n, double *s_nodes, double *s_out)
+__device__ double block_np_sum(const double *a, int n, double *s_nodes, int max_nodes, double *s_out)
 {
     __syncthreads();
-    int d = min(pw_max_depth(n), ilog2_ceil_i(SUM_NODES_MAX) - 0);
-    while ((1 << d) > SUM_NODES_MAX) d--;
+    int d = pw_max_depth(n);
+    while ((1 << d) > max_nodes) d--;
     int nn = 1 << d;
     auto f = [a](int j) { return a[j]; };
     for (int b = threadIdx.x; b < nn; b += blockDim.x) {
@@ -228,40 +278,80 @@ __device__ __forceinline__ void solve2x2(double a00, double a01, double a10, dou
     x0 = fma(-a01, x1, b0) / a00;
 }
 
-#define PI_D 3.141592653589793
-
-__global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SimDev S, int s)
+// A0 = -1/pi*trapz(W/Uinf), An = 2/pi*trapz(W/Uinf*cos(n theta))  (LUDVM.py:694-695, :769-771)
+__device__ __forceinline__ double fourier_coeff(const SimDev &S, const double *W, int n)
 {
-    extern __shared__ double sm[];
-    Step st;
-    if (!step_begin(S, s, st)) return;
+    const double Uinf = S.Uinf;
+    if (n == 0) return (-1 / PI_D) * trapz_seq([&](int j) { return W[j] / Uinf; }, S.theta_p, S.P);
+    const double *cn = S.cosn + (size_t)n * S.P;
+    return (2 / PI_D) * trapz_seq([&](int j) { return W[j] / Uinf * cn[j]; }, S.theta_p, S.P);
+}
+
+struct Kin {  // per-step kinematics
+    double ca, sa, ad, hd;
+    const double *xa, *za;
+};
+
+// airfoil_downwash epilogue (LUDVM.py:587-593): global (u1,w1) at the gamma points -> normal downwash W
+__device__ __forceinline__ void downwash_from_uw(const SimDev &S, const Kin &k, const double *u1, const double *w1,
+                                                 double *W)
+{
+    double s1 = S.Uinf * k.ca + k.hd * k.sa, us = S.Uinf * k.sa, hc = k.hd * k.ca;
+    for (int j = threadIdx.x; j < S.P; j += blockDim.x) {
+        double u = u1[j] * k.ca - w1[j] * k.sa;
+        double w = u1[j] * k.sa + w1[j] * k.ca;
+        W[j] = S.detadx_p[j] * (s1 + u - k.ad * S.eta_p[j]) - us - k.ad * (S.x_p[j] - S.piv) + hc - w;
+    }
+}
+
+// Whole-block airfoil_downwash of the wake TEV[:nT] ++ LEV[:nL] ++ FREE (used by the Ramesh iterations).
+__device__ void cta_downwash(const SimDev &S, const Step &st, const Kin &k, int nT, int nL, double *u1, double *w1,
+                             double *W)
+{
+    __syncthreads();  // circulation guesses written by thread 0 are visible
+    phase_wake_on_foil(S, st, nT, nL, block_pool());
+    __syncthreads();
+    fold_wake_on_foil(S, nT + nL + S.nfree, u1, w1);
+    __syncthreads();
+    downwash_from_uw(S, k, u1, w1, W);
+    __syncthreads();
+}
+
+// Kelvin residual of the Newton loops (LUDVM.py:697-699, :825-827); A0 on thread 0, A1 on thread 32.
+__device__ double cta_kelvin_f(const SimDev &S, const Step &st, const double *W, double *sc, double *nodes)
+{
+    if (threadIdx.x == 0) sc[20] = fourier_coeff(S, W, 0);
+    if (threadIdx.x == 32) sc[21] = fourier_coeff(S, W, 1);
+    double sT = block_np_sum(S.wg, st.itev + 1, nodes, S.sum_nodes, &sc[22]);
+    double sL = block_np_sum(S.wg + S.nv, st.ilev + 1, nodes, S.sum_nodes, &sc[23]);
+    if (threadIdx.x == 0) {
+        double cb = S.Uinf * S.chord * PI_D * (sc[20] + sc[21] / 2);
+        sc[24] = cb;
+        sc[25] = cb + sT + sL + S.sum_free - S.ic;
+    }
+    __syncthreads();
+    return sc[25];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// phase 2: the scalar phases (one CTA).  Faure expects the phase-1 partials of TEV[:itev] ++ LEV[:ilev] ++ FREE.
+// ---------------------------------------------------------------------------------------------------
+__device__ void phase_solve(const SimDev &S, const Step &st, double *sm)
+{
     const int P = S.P, Nc = S.Nc, tid = threadIdx.x, nth = blockDim.x;
     const int i = st.i, itev = st.itev, ilev = st.ilev, nv = S.nv;
     double *u1 = sm, *w1 = u1 + P, *T1 = w1 + P, *T2 = T1 + P, *T3 = T2 + P, *W = T3 + P, *dG = W + P;
     double *A = dG + P, *sc = A + Nc, *nodes = sc + 32;
     // sc[]: 0 xt, 1 zt, 2 sT, 3 sL, 4 I1, 5 I2, 6 I3, 7 J1, 8 J2, 9 J3, 10 gtev, 11 glev, 12 shed, 13 xl, 14 zl,
-    //       15 lespcrit, 16 scratch
-    const double ca = S.cos_a[i], sa = S.sin_a[i], ad = S.alpha_dot[i], hd = S.h_dot[i];
-    const double *xa = S.gp + ((size_t)i * 2 + 0) * P, *za = S.gp + ((size_t)i * 2 + 1) * P;
+    //       15 lespcrit, 16 bound, 20.. Newton scratch
+    Kin k{S.cos_a[i], S.sin_a[i], S.alpha_dot[i], S.h_dot[i], S.gp + ((size_t)i * 2 + 0) * P,
+          S.gp + ((size_t)i * 2 + 1) * P};
+    const double ca = k.ca, sa = k.sa;
     const double Uinf = S.Uinf, chord = S.chord, dt = S.dt;
+    const bool ramesh = S.method == LUDVM_METHOD_RAMESH;
+    double *F = S.fourier + (size_t)(i % S.fourier_rows) * 2 * Nc;
+    const double *Fprev = S.fourier + (size_t)((i - 1) % S.fourier_rows) * 2 * Nc;
 
-    // fold the phase-C partials (LUDVM.py:584)
-    {
-        int n1 = itev + ilev + S.nfree;
-        if (S.mode == LUDVM_EXACT_F64) {
-            int d = sim_depth(n1, P, S.target_warps);
-            for (int j = tid; j < P; j += nth) {
-                u1[j] = exact_combine_row(S.pa_u, P, j, d);
-                w1[j] = exact_combine_row(S.pa_w, P, j, d);
-            }
-        } else {
-            int c = sim_chunks(n1, P, S.target_warps);
-            for (int j = tid; j < P; j += nth) {
-                u1[j] = fast_combine_row(S.pa_u, P, j, c);
-                w1[j] = fast_combine_row(S.pa_w, P, j, c);
-            }
-        }
-    }
     // TEV placement (LUDVM.py:672-681)
     if (tid == 0) {
         double xt, zt;
@@ -278,49 +368,76 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SimDev S, int s)
         S.wx[itev] = xt;
         S.wz[itev] = zt;
         sc[15] = *S.lespcrit_cur;
-    }
-    // np.sum(circulation['TEV'][:itev]), np.sum(circulation['LEV'][:ilev])  (LUDVM.py:758-759)
-    double sT = block_np_sum(S.wg, itev, nodes, &sc[2]);
-    double sL = block_np_sum(S.wg + nv, ilev, nodes, &sc[3]);
-    const double xt = sc[0], zt = sc[1];
-    // T1 = airfoil_downwash(existing wake) (LUDVM.py:587-593), T2 = unit TEV influence (LUDVM.py:749-754)
-    {
-        double s1 = Uinf * ca + hd * sa, us = Uinf * sa, hc = hd * ca;
-        for (int j = tid; j < P; j += nth) {
-            double u = u1[j] * ca - w1[j] * sa;
-            double w = u1[j] * sa + w1[j] * ca;
-            T1[j] = S.detadx_p[j] * (s1 + u - ad * S.eta_p[j]) - us - ad * (S.x_p[j] - S.piv) + hc - w;
-            T2[j] = unit_T(S, xa[j], za[j], xt, zt, ca, sa, S.detadx_p[j]);
-        }
-    }
-    __syncthreads();
-    // I1, I2 (LUDVM.py:756-757) on two different warps
-    if (tid == 0) sc[4] = trapz_seq([&](int j) { return T1[j] * (S.cos_tp[j] - 1); }, S.theta_p, P);
-    if (tid == 32) sc[5] = trapz_seq([&](int j) { return T2[j] * (S.cos_tp[j] - 1); }, S.theta_p, P);
-    __syncthreads();
-    if (tid == 0) {
-        double I1 = sc[4], I2 = sc[5];
-        sc[10] = -(I1 + sT + sL + S.sum_free - S.ic) / (1 + I2);  // LUDVM.py:758-760
         sc[11] = 0.0;
-        sc[16] = I1 + sc[10] * I2;                                // circulation['bound'], LUDVM.py:762
-    }
-    __syncthreads();
-    for (int j = tid; j < P; j += nth) W[j] = T1[j] + sc[10] * T2[j];  // LUDVM.py:767
-    __syncthreads();
-    // Fourier coefficients and their derivatives (LUDVM.py:769-773); thread n*8 keeps them on distinct warps
-    double *F = S.fourier + (size_t)i * 2 * Nc;
-    const double *Fprev = S.fourier + (size_t)(i - 1) * 2 * Nc;
-    for (int n = tid; n < Nc; n += nth) {
-        double a;
-        if (n == 0) a = (-1 / PI_D) * trapz_seq([&](int j) { return W[j] / Uinf; }, S.theta_p, P);
-        else {
-            const double *cn = S.cosn + (size_t)n * P;
-            a = (2 / PI_D) * trapz_seq([&](int j) { return W[j] / Uinf * cn[j]; }, S.theta_p, P);
+        if (ramesh && ilev < nv) {  // row i of path['LEV'] starts with a zero slot
+            S.wx[nv + ilev] = 0.0;
+            S.wz[nv + ilev] = 0.0;
         }
-        A[n] = a;
-        F[Nc + n] = (a - Fprev[n]) / dt;
     }
-    __syncthreads();
+    if (!ramesh) {
+        // Faure closed form (LUDVM.py:741-773)
+        fold_wake_on_foil(S, itev + ilev + S.nfree, u1, w1);
+        double sT = block_np_sum(S.wg, itev, nodes, S.sum_nodes, &sc[2]);       // LUDVM.py:758-759
+        double sL = block_np_sum(S.wg + nv, ilev, nodes, S.sum_nodes, &sc[3]);
+        downwash_from_uw(S, k, u1, w1, T1);
+        for (int j = tid; j < P; j += nth) T2[j] = unit_T(S, k.xa[j], k.za[j], sc[0], sc[1], ca, sa, S.detadx_p[j]);
+        __syncthreads();
+        if (tid == 0) sc[4] = trapz_seq([&](int j) { return T1[j] * (S.cos_tp[j] - 1); }, S.theta_p, P);
+        if (tid == 32) sc[5] = trapz_seq([&](int j) { return T2[j] * (S.cos_tp[j] - 1); }, S.theta_p, P);
+        __syncthreads();
+        if (tid == 0) {
+            double I1 = sc[4], I2 = sc[5];
+            sc[10] = -(I1 + sT + sL + S.sum_free - S.ic) / (1 + I2);  // LUDVM.py:758-760
+            sc[16] = I1 + sc[10] * I2;                                // circulation['bound'], LUDVM.py:762
+        }
+        __syncthreads();
+        for (int j = tid; j < P; j += nth) W[j] = T1[j] + sc[10] * T2[j];  // LUDVM.py:767
+        __syncthreads();
+        for (int n = tid; n < Nc; n += nth) {                              // LUDVM.py:769-773
+            double a = fourier_coeff(S, W, n);
+            A[n] = a;
+            F[Nc + n] = (a - Fprev[n]) / dt;
+        }
+        __syncthreads();
+    } else {
+        // Ramesh 1-D Newton on the TEV strength (LUDVM.py:683-739)
+        if (tid == 0) {
+            sc[26] = 1.0;   // f
+            sc[27] = -1.0;  // shed_vortex_gamma
+        }
+        __syncthreads();
+        int niter = 1;
+        while (fabs(sc[26]) > S.maxerror && niter < S.maxiter) {
+            double shed = sc[27];
+            if (tid == 0) S.wg[itev] = shed;
+            cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
+            double f = cta_kelvin_f(S, st, W, sc, nodes);
+            if (tid == 0) S.wg[itev] = shed + S.epsilon;
+            cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
+            double fdelta = cta_kelvin_f(S, st, W, sc, nodes);
+            __syncthreads();
+            if (tid == 0) {
+                double fprime = (fdelta - f) / S.epsilon;
+                sc[27] = shed - f / fprime;
+                sc[26] = f;
+                S.wg[itev] = sc[27];
+            }
+            __syncthreads();
+            niter++;
+        }
+        cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
+        for (int n = tid; n < Nc; n += nth) {
+            double a = fourier_coeff(S, W, n);
+            A[n] = a;
+            F[Nc + n] = (a - Fprev[n]) / dt;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            sc[10] = S.wg[itev];
+            sc[16] = Uinf * chord * PI_D * (A[0] + A[1] / 2);  // LUDVM.py:734
+        }
+        __syncthreads();
+    }
     // LESP test (LUDVM.py:775-781)
     if (tid == 0) {
         S.lesp_prev[itev] = A[0];
@@ -339,33 +456,84 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SimDev S, int s)
             sc[14] = zl;
             sc[15] = (A[0] < 0) ? -fabs(sc[15]) : fabs(sc[15]);
             S.lev_shed[i] = (double)ilev;
+            if (ramesh) {
+                S.wx[nv + ilev] = xl;
+                S.wz[nv + ilev] = zl;
+            }
         }
         __syncthreads();
-        for (int j = tid; j < P; j += nth) T3[j] = unit_T(S, xa[j], za[j], sc[13], sc[14], ca, sa, S.detadx_p[j]);
-        __syncthreads();
-        // I3, J1, J2, J3 (LUDVM.py:936-942)
-        if (tid == 0) sc[6] = trapz_seq([&](int j) { return T3[j] * (S.cos_tp[j] - 1); }, S.theta_p, P);
-        if (tid == 32) sc[7] = (-1 / PI_D) * trapz_seq([&](int j) { return T1[j]; }, S.theta_p, P);
-        if (tid == 64) sc[8] = (-1 / PI_D) * trapz_seq([&](int j) { return T2[j]; }, S.theta_p, P);
-        if (tid == 96) sc[9] = (-1 / PI_D) * trapz_seq([&](int j) { return T3[j]; }, S.theta_p, P);
-        __syncthreads();
-        if (tid == 0) {  // LUDVM.py:945-959
-            double I1 = sc[4], I2 = sc[5], I3 = sc[6], J1 = sc[7], J2 = sc[8], J3 = sc[9];
-            double b1 = -(I1 + sT + sL + S.sum_free - S.ic), b2 = sc[15] - J1, x0, x1;
-            solve2x2(1 + I2, 1 + I3, J2, J3, b1, b2, x0, x1);
-            sc[10] = x0;
-            sc[11] = x1;
-            sc[16] = I1 + x0 * I2 + x1 * I3;
-            A[0] = J1 + x0 * J2 + x1 * J3;
+        if (!ramesh) {
+            // Faure 2x2 linear system (LUDVM.py:916-961); T1, T2, I1, I2 are unchanged recomputations there
+            for (int j = tid; j < P; j += nth) T3[j] = unit_T(S, k.xa[j], k.za[j], sc[13], sc[14], ca, sa, S.detadx_p[j]);
+            __syncthreads();
+            if (tid == 0) sc[6] = trapz_seq([&](int j) { return T3[j] * (S.cos_tp[j] - 1); }, S.theta_p, P);
+            if (tid == 32) sc[7] = (-1 / PI_D) * trapz_seq([&](int j) { return T1[j]; }, S.theta_p, P);
+            if (tid == 64) sc[8] = (-1 / PI_D) * trapz_seq([&](int j) { return T2[j]; }, S.theta_p, P);
+            if (tid == 96) sc[9] = (-1 / PI_D) * trapz_seq([&](int j) { return T3[j]; }, S.theta_p, P);
+            __syncthreads();
+            if (tid == 0) {  // LUDVM.py:945-959
+                double I1 = sc[4], I2 = sc[5], I3 = sc[6], J1 = sc[7], J2 = sc[8], J3 = sc[9];
+                double b1 = -(I1 + sc[2] + sc[3] + S.sum_free - S.ic), b2 = sc[15] - J1, x0, x1;
+                solve2x2(1 + I2, 1 + I3, J2, J3, b1, b2, x0, x1);
+                sc[10] = x0;
+                sc[11] = x1;
+                sc[16] = I1 + x0 * I2 + x1 * I3;
+                A[0] = J1 + x0 * J2 + x1 * J3;
+            }
+            __syncthreads();
+            for (int j = tid; j < P; j += nth) W[j] = T1[j] + sc[10] * T2[j] + sc[11] * T3[j];
+            __syncthreads();
+            for (int n = 1 + tid; n < Nc; n += nth) A[n] = fourier_coeff(S, W, n);  // LUDVM.py:960-961
+            __syncthreads();
+        } else {
+            // Ramesh 2-D Newton on (LEV, TEV) strengths (LUDVM.py:807-909)
+            if (tid == 0) {
+                sc[26] = 0.1;          // f1
+                sc[27] = 0.1;          // f2
+                sc[28] = S.wg[itev];   // TEV_shed_gamma
+                sc[29] = S.wg[itev];   // LEV_shed_gamma
+            }
+            __syncthreads();
+            int niter = 1;
+            while ((fabs(sc[26]) > S.maxerror || fabs(sc[27]) > S.maxerror) && niter < S.maxiter) {
+                double tg = sc[28], lg = sc[29];
+                if (tid == 0) { S.wg[itev] = tg; S.wg[nv + ilev] = lg; }
+                cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
+                double f1 = cta_kelvin_f(S, st, W, sc, nodes);
+                double cbound = sc[24], f2 = sc[15] - sc[20];
+                __syncthreads();
+                if (tid == 0) { S.wg[itev] = tg + S.epsilon; S.wg[nv + ilev] = lg; }
+                cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
+                double f1dT = cta_kelvin_f(S, st, W, sc, nodes), f2dT = sc[15] - sc[20];
+                __syncthreads();
+                if (tid == 0) { S.wg[itev] = tg; S.wg[nv + ilev] = lg + S.epsilon; }
+                cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
+                double f1dL = cta_kelvin_f(S, st, W, sc, nodes), f2dL = sc[15] - sc[20];
+                __syncthreads();
+                if (tid == 0) {
+                    double eps = S.epsilon, x0, x1;
+                    solve2x2((f1dL - f1) / eps, (f1dT - f1) / eps, (f2dL - f2) / eps, (f2dT - f2) / eps, f1, f2, x0, x1);
+                    sc[29] = lg + (-x0);
+                    sc[28] = tg + (-x1);
+                    sc[26] = f1;
+                    sc[27] = f2;
+                    S.wg[itev] = sc[28];
+                    S.wg[nv + ilev] = sc[29];
+                    sc[16] = cbound;
+                }
+                __syncthreads();
+                niter++;
+            }
+            cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
+            for (int n = tid; n < Nc; n += nth) A[n] = fourier_coeff(S, W, n);  // LUDVM.py:902-909
+            __syncthreads();
+            if (tid == 0) {
+                sc[10] = S.wg[itev];
+                sc[11] = S.wg[nv + ilev];
+                sc[16] = Uinf * chord * PI_D * (A[0] + A[1] / 2);
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        for (int j = tid; j < P; j += nth) W[j] = T1[j] + sc[10] * T2[j] + sc[11] * T3[j];
-        __syncthreads();
-        for (int n = 1 + tid; n < Nc; n += nth) {  // LUDVM.py:960-961 (derivatives keep their values, :963-966)
-            const double *cn = S.cosn + (size_t)n * P;
-            A[n] = (2 / PI_D) * trapz_seq([&](int j) { return W[j] / Uinf * cn[j]; }, S.theta_p, P);
-        }
-        __syncthreads();
     }
     // commit the step's circulations and bookkeeping
     if (tid == 0) {
@@ -385,6 +553,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SimDev S, int s)
     }
     for (int n = tid; n < Nc; n += nth) F[n] = A[n];
     // bound-vortex distribution (LUDVM.py:986-1010)
+    const size_t arow = (size_t)itev * S.af_stride;
     for (int j = tid; j < P; j += nth) {
         double term2 = 0;
         for (int n = 1; n < Nc; n++) term2 = A[n] * S.sinn[(size_t)n * P + j] + term2;
@@ -392,106 +561,109 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SimDev S, int s)
         double gamma = 2 * Uinf * (term1 + term2);
         double dg = gamma * chord / 2 * S.sin_tp[j] * S.dtheta[j];
         dG[j] = dg;
-        S.g_airfoil[(size_t)itev * P + j] = dg;
-        S.gamma_airfoil[(size_t)itev * P + j] = gamma;
+        S.g_airfoil[arow + j] = dg;
+        S.gamma_airfoil[arow + j] = gamma;
     }
     __syncthreads();
     for (int j = tid; j < P; j += nth) {
-        auto f = [&](int k) { return dG[k]; };
-        S.Gamma_airfoil[(size_t)itev * P + j] = 0.0 + pw_seq(f, 0, j + 1);
+        auto f = [&](int kk) { return dG[kk]; };
+        S.Gamma_airfoil[arow + j] = 0.0 + pw_seq(f, 0, j + 1);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// kernel 3: updated wake on (gamma points ++ wake) and bound vortices on the wake
+// phase 3: updated wake on (gamma points ++ wake) and bound vortices on the wake
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_conv_partials(SimDev S, int s)
+__device__ __forceinline__ void phase_conv_partials(const SimDev &S, const Step &st, const Pool &pl)
 {
-    Step st;
-    if (!step_begin(S, s, st)) return;
     const int P = S.P;
-    SrcView W = wake_view(S, st.itev + 1, S.ilev_arr[st.i] + 1);
+    SrcView W = wake_view(S, st.itev + 1, st.ilev + 1);
     const double *gx = S.gp + ((size_t)st.i * 2 + 0) * P, *gz = S.gp + ((size_t)st.i * 2 + 1) * P;
     TgtGammaWake TA{gx, gz, P, W};
     TgtWake TW{W};
-    SrcView Fo = make_src(S.g_airfoil + (size_t)st.itev * P, 1, gx, gz, nullptr, S.vc4, P);
+    SrcView Fo = make_src(S.g_airfoil + (size_t)st.itev * S.af_stride, 1, gx, gz, nullptr, S.vc4, P);
     const int nrows = P + W.n;
-    int lane = threadIdx.x & 31;
-    long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     long nquadsA = (nrows + 3) >> 2, nquadsW = (W.n + 3) >> 2;
     if (S.mode == LUDVM_EXACT_F64) {
         int d = sim_depth(W.n, nrows, S.target_warps);
         long nA = nquadsA << d;
-        for (long t = gw; t < nA + nquadsW; t += nwarps) {
-            if (t < nA) exact_rows_warp_task(W, TA, nrows, d, t, lane, S.pb_u, S.pb_w);
-            else exact_rows_warp_task(Fo, TW, W.n, 0, t - nA, lane, S.foil_u, S.foil_w);
+        for (long t = pl.wid; t < nA + nquadsW; t += pl.nwarps) {
+            if (t < nA) exact_rows_warp_task(W, TA, nrows, d, t, pl.lane, S.pb_u, S.pb_w);
+            else exact_rows_warp_task(Fo, TW, W.n, 0, t - nA, pl.lane, S.foil_u, S.foil_w);
         }
     } else {
         int c = sim_chunks(W.n, nrows, S.target_warps);
         long nA = nquadsA * c;
-        for (long t = gw; t < nA + nquadsW; t += nwarps) {
-            if (t < nA) fast_rows_warp_task(W, TA, nrows, c, t, lane, S.pb_u, S.pb_w);
-            else fast_rows_warp_task(Fo, TW, W.n, 1, t - nA, lane, S.foil_u, S.foil_w);
+        for (long t = pl.wid; t < nA + nquadsW; t += pl.nwarps) {
+            if (t < nA) fast_rows_warp_task(W, TA, nrows, c, t, pl.lane, S.pb_u, S.pb_w);
+            else fast_rows_warp_task(Fo, TW, W.n, 1, t - nA, pl.lane, S.foil_u, S.foil_w);
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// kernel 4: loads (block 0) and convection update + history (other blocks)
+// phase 4: loads (one CTA) and convection update + history (thread pool)
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_finish(SimDev S, int s)
+__device__ __forceinline__ int conv_fold(const SimDev &S, const Step &st)
 {
-    extern __shared__ double sm[];
-    Step st;
-    if (!step_begin(S, s, st)) return;
-    const int P = S.P, i = st.i, itev = st.itev, ilev = st.ilev, nv = S.nv, tid = threadIdx.x, nth = blockDim.x;
-    const int nT = itev + 1, nL = ilev + 1;
+    int nw = st.itev + 1 + st.ilev + 1 + S.nfree;
+    return S.mode == LUDVM_EXACT_F64 ? sim_depth(nw, S.P + nw, S.target_warps) : sim_chunks(nw, S.P + nw, S.target_warps);
+}
+
+__device__ void phase_finish_loads(const SimDev &S, const Step &st, double *sm)  // LUDVM.py:1035-1090
+{
+    const int P = S.P, i = st.i, itev = st.itev, tid = threadIdx.x, nth = blockDim.x;
+    const int nrows = P + st.itev + 1 + st.ilev + 1 + S.nfree;
+    const bool exact = S.mode == LUDVM_EXACT_F64;
+    const int fold = conv_fold(S, st);
+    double *ug = sm, *ugx = ug + P, *sc = ugx + P;
+    const double ca = S.cos_a[i], sa = S.sin_a[i], hd = S.h_dot[i];
+    const double *gam = S.gamma_airfoil + (size_t)itev * S.af_stride;
+    __syncthreads();
+    for (int j = tid; j < P; j += nth) {
+        double u1 = exact ? exact_combine_row(S.pb_u, nrows, j, fold) : fast_combine_row(S.pb_u, nrows, j, fold);
+        double w1 = exact ? exact_combine_row(S.pb_w, nrows, j, fold) : fast_combine_row(S.pb_w, nrows, j, fold);
+        double u = u1 * ca - w1 * sa;
+        ug[j] = u * gam[j];
+        ugx[j] = u * gam[j] * S.x_p[j];
+    }
+    __syncthreads();
+    if (tid == 0) sc[0] = trapz_seq([&](int j) { return ug[j]; }, S.x_p, P);
+    if (tid == 32) sc[1] = trapz_seq([&](int j) { return ugx[j]; }, S.x_p, P);
+    __syncthreads();
+    if (tid == 0) {
+        const double *F = S.fourier + (size_t)(i % S.fourier_rows) * 2 * S.Nc, *Fd = F + S.Nc;
+        const double rho = S.rho, chord = S.chord, Uinf = S.Uinf;
+        double A0 = F[0], A1 = F[1], A2 = F[2], A0d = Fd[0], A1d = Fd[1], A2d = Fd[2], A3d = Fd[3];
+        double vrel = Uinf * ca + hd * sa;
+        double Fn = rho * PI_D * chord * Uinf *
+                        (vrel * (A0 + 0.5 * A1) + chord * (3.0 / 4 * A0d + 1.0 / 4 * A1d + 1.0 / 8 * A2d)) +
+                    rho * sc[0];
+        double Fs = rho * PI_D * chord * (Uinf * Uinf) * (A0 * A0);
+        double Lf = Fn * ca + Fs * sa;
+        double Df = Fn * sa - Fs * ca;
+        double Mo = S.piv * Fn -
+                    rho * PI_D * (chord * chord) * Uinf *
+                        (vrel * (1.0 / 4 * A0 + 1.0 / 4 * A1 - 1.0 / 8 * A2) +
+                         chord * (7.0 / 16 * A0d + 3.0 / 16 * A1d + 1.0 / 16 * A2d - 1.0 / 64 * A3d)) -
+                    rho * sc[1];
+        S.Fn[i] = Fn; S.Fs[i] = Fs; S.L[i] = Lf; S.D[i] = Df; S.T[i] = -Df; S.M[i] = Mo;
+        S.counters[1] = itev;
+        S.counters[2] = st.ilev;
+    }
+}
+
+// convection, LUDVM.py:1095-1127: x += dt*(u_wake + u_foil) for TEV[:nT], LEV[:nL], FREE, in place
+__device__ __forceinline__ void phase_finish_update(const SimDev &S, const Step &st, long t0, long nthreads)
+{
+    const int P = S.P, i = st.i, nv = S.nv;
+    const int nT = st.itev + 1, nL = st.ilev + 1;
     SrcView W = wake_view(S, nT, nL);
     const int nrows = P + W.n;
     const bool exact = S.mode == LUDVM_EXACT_F64;
-    const int fold = exact ? sim_depth(W.n, nrows, S.target_warps) : sim_chunks(W.n, nrows, S.target_warps);
-
-    if (blockIdx.x == 0) {  // loads, LUDVM.py:1035-1090
-        double *ug = sm, *ugx = ug + P, *sc = ugx + P;
-        const double ca = S.cos_a[i], sa = S.sin_a[i], hd = S.h_dot[i];
-        const double *gam = S.gamma_airfoil + (size_t)itev * P;
-        for (int j = tid; j < P; j += nth) {
-            double u1 = exact ? exact_combine_row(S.pb_u, nrows, j, fold) : fast_combine_row(S.pb_u, nrows, j, fold);
-            double w1 = exact ? exact_combine_row(S.pb_w, nrows, j, fold) : fast_combine_row(S.pb_w, nrows, j, fold);
-            double u = u1 * ca - w1 * sa;
-            ug[j] = u * gam[j];
-            ugx[j] = u * gam[j] * S.x_p[j];
-        }
-        __syncthreads();
-        if (tid == 0) sc[0] = trapz_seq([&](int j) { return ug[j]; }, S.x_p, P);
-        if (tid == 32) sc[1] = trapz_seq([&](int j) { return ugx[j]; }, S.x_p, P);
-        __syncthreads();
-        if (tid == 0) {
-            const double *F = S.fourier + (size_t)i * 2 * S.Nc, *Fd = F + S.Nc;
-            const double rho = S.rho, chord = S.chord, Uinf = S.Uinf;
-            double A0 = F[0], A1 = F[1], A2 = F[2], A0d = Fd[0], A1d = Fd[1], A2d = Fd[2], A3d = Fd[3];
-            double vrel = Uinf * ca + hd * sa;
-            double Fn = rho * PI_D * chord * Uinf *
-                            (vrel * (A0 + 0.5 * A1) + chord * (3.0 / 4 * A0d + 1.0 / 4 * A1d + 1.0 / 8 * A2d)) +
-                        rho * sc[0];
-            double Fs = rho * PI_D * chord * (Uinf * Uinf) * (A0 * A0);
-            double Lf = Fn * ca + Fs * sa;
-            double Df = Fn * sa - Fs * ca;
-            double Mo = S.piv * Fn -
-                        rho * PI_D * (chord * chord) * Uinf *
-                            (vrel * (1.0 / 4 * A0 + 1.0 / 4 * A1 - 1.0 / 8 * A2) +
-                             chord * (7.0 / 16 * A0d + 3.0 / 16 * A1d + 1.0 / 16 * A2d - 1.0 / 64 * A3d)) -
-                        rho * sc[1];
-            S.Fn[i] = Fn; S.Fs[i] = Fs; S.L[i] = Lf; S.D[i] = Df; S.T[i] = -Df; S.M[i] = Mo;
-            S.counters[1] = itev;
-            S.counters[2] = ilev;
-        }
-        return;
-    }
-    // convection, LUDVM.py:1095-1127: x += dt*(u_wake + u_foil) for TEV[:nT], LEV[:nL], FREE, in place
+    const int fold = conv_fold(S, st);
     const double dt = S.dt;
-    for (long r = (long)(blockIdx.x - 1) * nth + tid; r < W.n; r += (long)(gridDim.x - 1) * nth) {
+    for (long r = t0; r < W.n; r += nthreads) {
         int row = P + (int)r;
         double uw, ww, uf, wf;
         if (exact) {
@@ -528,30 +700,222 @@ __global__ void __launch_bounds__(256) k_finish(SimDev S, int s)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// graph path: four kernels per step
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_wake_on_foil(SimDev S, int s)
+{
+    Step st;
+    if (!step_begin(S, s, st)) return;
+    phase_wake_on_foil(S, st, st.itev, st.ilev, grid_pool());
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SimDev S, int s)
+{
+    extern __shared__ double sm[];
+    Step st;
+    if (!step_begin(S, s, st)) return;
+    phase_solve(S, st, sm);
+}
+
+__global__ void __launch_bounds__(256) k_conv_partials(SimDev S, int s)
+{
+    Step st;
+    if (!step_begin(S, s, st)) return;
+    phase_conv_partials(S, st, grid_pool());
+}
+
+__global__ void __launch_bounds__(256) k_finish(SimDev S, int s)
+{
+    extern __shared__ double sm[];
+    Step st;
+    if (!step_begin(S, s, st)) return;
+    if (blockIdx.x == 0) {
+        phase_finish_loads(S, st, sm);
+        return;
+    }
+    phase_finish_update(S, st, (long)(blockIdx.x - 1) * blockDim.x + threadIdx.x, (long)(gridDim.x - 1) * blockDim.x);
+}
+
 __global__ void k_advance(SimDev S, int k)
 {
     long long v = S.counters[0] + k;
     S.counters[0] = v > S.nt - 1 ? S.nt - 1 : v;
 }
 
-__global__ void k_fill(double *p, size_t n, double v)
+// ---------------------------------------------------------------------------------------------------
+// CTA path: one persistent CTA per case, all steps
+// ---------------------------------------------------------------------------------------------------
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_sim_cta(const SimDev *cases, int ncases, int *next_case, int nsteps)
 {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < n) p[idx] = v;
+    extern __shared__ double sm[];
+    __shared__ int s_case;
+    __shared__ SimDev s_sim;  // the case descriptor lives in shared memory (a by-value copy would sit in local memory)
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_case = atomicAdd(next_case, 1);
+        __syncthreads();
+        const int c = s_case;
+        if (c >= ncases) return;
+        {
+            const int *src = reinterpret_cast<const int *>(cases + c);
+            int *dst = reinterpret_cast<int *>(&s_sim);
+            for (int w = threadIdx.x; w < (int)(sizeof(SimDev) / sizeof(int)); w += blockDim.x) dst[w] = src[w];
+        }
+        __syncthreads();
+        const SimDev &S = s_sim;
+        const int first = (int)S.counters[0] + 1;
+        const int last = min(S.nt - 1, first + nsteps - 1);
+        const Pool pl = block_pool();
+        for (int i = first; i <= last; i++) {
+            __syncthreads();
+            Step st{i, i - 1, S.ilev_arr[i]};
+            if (S.method == LUDVM_METHOD_FAURE) {
+                phase_wake_on_foil(S, st, st.itev, st.ilev, pl);
+                __syncthreads();
+            }
+            phase_solve(S, st, sm);
+            __syncthreads();
+            phase_conv_partials(S, st, pl);
+            __syncthreads();
+            phase_finish_loads(S, st, sm);
+            phase_finish_update(S, st, threadIdx.x, blockDim.x);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) S.counters[0] = last;
+    }
 }
+
+// Per-case initial state (LUDVM.py:618, :645-654): free vortices, fourier[0,0,:2], LEV_shed = -1, LESPcrit.
+__global__ void __launch_bounds__(256) k_case_init(const SimDev *cases, int ncases)
+{
+    int c = blockIdx.x;
+    if (c >= ncases) return;
+    const SimDev S = cases[c];
+    for (int j = threadIdx.x; j < S.nt; j += blockDim.x) S.lev_shed[j] = -1.0;
+    for (int j = threadIdx.x; j < S.nfree; j += blockDim.x) {
+        S.wg[2 * S.nv + j] = S.free_g[j];
+        S.wx[2 * S.nv + j] = S.free_xz[j];
+        S.wz[2 * S.nv + j] = S.free_xz[S.nfree + j];
+        if (S.store_history) {
+            S.path_free[j] = S.free_xz[j];
+            S.path_free[S.nfree + j] = S.free_xz[S.nfree + j];
+        }
+    }
+    if (threadIdx.x == 0) {
+        S.fourier[0] = S.a0_init;
+        S.fourier[1] = S.a1_init;
+        *S.lespcrit_cur = S.lespcrit0;
+    }
+}
+
+// Sweep results: out[c][f][nt] with f in LUDVM_SW_* order (the three circulation rows hold nt-1 values + a 0).
+__global__ void __launch_bounds__(256) k_sweep_gather(const SimDev *cases, int ncases, double *out)
+{
+    int c = blockIdx.x;
+    if (c >= ncases) return;
+    const SimDev S = cases[c];
+    const double *src[LUDVM_SWEEP_FIELDS] = {S.Fn, S.Fs, S.L, S.D, S.T, S.M, S.lesp, S.lesp_prev, S.lev_shed,
+                                             S.wg, S.wg + S.nv, S.g_bound};
+    double *o = out + (size_t)c * LUDVM_SWEEP_FIELDS * S.nt;
+    for (int f = 0; f < LUDVM_SWEEP_FIELDS; f++) {
+        int n = f < 9 ? S.nt : S.nt - 1;
+        for (int j = threadIdx.x; j < S.nt; j += blockDim.x) o[(size_t)f * S.nt + j] = j < n ? src[f][j] : 0.0;
+    }
+}
+
+// Bump allocator over one device arena; with base == nullptr it only measures.
+struct Arena {
+    char *base = nullptr;
+    size_t off = 0;
+    template <typename T>
+    T *take(size_t n)
+    {
+        off = (off + 255) & ~(size_t)255;
+        T *p = base ? (T *)(base + off) : nullptr;
+        off += std::max<size_t>(n, 1) * sizeof(T);
+        return p;
+    }
+};
+
+struct DevTables {  // device copies of one ludvm_sim_tables
+    const double *cos_a, *sin_a, *alpha_dot, *h_dot, *gp, *le, *te;
+    const double *detadx_p, *eta_p, *x_p, *theta_p, *dtheta, *cos_tp, *sin_tp, *cosn, *sinn, *free_g, *free_xz;
+};
+
+static int check_params(const ludvm_sim_params *p, const ludvm_sim_tables *t)
+{
+    ARG_CHECK(p->nt >= 2 && p->nt < (1 << 24) && p->P >= 2 && p->P <= 2048 && p->Nc >= 4 && p->Nc <= 512);
+    ARG_CHECK(p->nfree >= 1 && p->nfree < (1 << 28));
+    ARG_CHECK(p->mode == LUDVM_EXACT_F64 || p->mode == LUDVM_FAST_F64);
+    ARG_CHECK(p->method == LUDVM_METHOD_FAURE || p->method == LUDVM_METHOD_RAMESH);
+    ARG_CHECK(t->cos_a && t->sin_a && t->alpha_dot && t->h_dot && t->gp && t->le && t->te && t->detadx_p && t->eta_p &&
+              t->x_p && t->theta_p && t->dtheta && t->cos_tp && t->sin_tp && t->cosn && t->sinn && t->free_g &&
+              t->free_xz);
+    return LUDVM_OK;
+}
+
+// Fill the scalar fields and carve the per-case state out of the arena.  `compact` keeps only what a parameter
+// sweep reads back (no [nv,P] bound-vortex histories, two Fourier rows, no vortex path history).
+static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t, Arena &a, int target_warps,
+                        int sum_nodes, bool compact)
+{
+    const size_t nt = p.nt, P = p.P, Nc = p.Nc, nf = p.nfree, nv = nt - 1, nstate = 2 * nv + nf;
+    D.nt = (int)nt; D.P = (int)P; D.Nc = (int)Nc; D.nfree = (int)nf; D.nv = (int)nv;
+    D.method = p.method; D.mode = p.mode; D.store_history = compact ? 0 : p.store_history;
+    D.target_warps = target_warps; D.sum_nodes = sum_nodes;
+    D.af_stride = compact ? 0 : (int)P;
+    D.fourier_rows = compact ? 2 : (int)nt;
+    D.dt = p.dt; D.Uinf = p.Uinf; D.chord = p.chord; D.rho = p.rho; D.piv = p.piv; D.vc4 = p.vc4; D.ic = p.ic;
+    D.sum_free = p.sum_free; D.maxerror = p.maxerror; D.epsilon = p.epsilon; D.maxiter = (int)p.maxiter;
+    D.lespcrit0 = p.lespcrit; D.a0_init = p.a0_init; D.a1_init = p.a1_init;
+    D.cos_a = t.cos_a; D.sin_a = t.sin_a; D.alpha_dot = t.alpha_dot; D.h_dot = t.h_dot; D.gp = t.gp; D.le = t.le;
+    D.te = t.te; D.detadx_p = t.detadx_p; D.eta_p = t.eta_p; D.x_p = t.x_p; D.theta_p = t.theta_p;
+    D.dtheta = t.dtheta; D.cos_tp = t.cos_tp; D.sin_tp = t.sin_tp; D.cosn = t.cosn; D.sinn = t.sinn;
+    D.free_g = t.free_g; D.free_xz = t.free_xz;
+    D.wx = a.take<double>(nstate); D.wz = a.take<double>(nstate); D.wg = a.take<double>(nstate);
+    D.g_bound = a.take<double>(nv);
+    const size_t afrows = compact ? 1 : nv;
+    D.g_airfoil = a.take<double>(afrows * P);
+    D.gamma_airfoil = a.take<double>(afrows * P);
+    D.Gamma_airfoil = a.take<double>(afrows * P);
+    D.fourier = a.take<double>((size_t)D.fourier_rows * 2 * Nc);
+    D.lesp = a.take<double>(nt); D.lesp_prev = a.take<double>(nt); D.lev_shed = a.take<double>(nt);
+    D.Fn = a.take<double>(nt); D.Fs = a.take<double>(nt); D.L = a.take<double>(nt); D.D = a.take<double>(nt);
+    D.T = a.take<double>(nt); D.M = a.take<double>(nt);
+    if (D.store_history) {
+        D.path_tev = a.take<double>(nt * 2 * nv);
+        D.path_lev = a.take<double>(nt * 2 * nv);
+        D.path_free = a.take<double>(nt * 2 * nf);
+    } else {
+        D.path_tev = D.path_lev = D.path_free = nullptr;
+    }
+    D.counters = a.take<long long>(4);
+    D.ilev_arr = a.take<int>(nt + 2);
+    D.lespcrit_cur = a.take<double>(1);
+    const size_t quadsP = (P + 3) / 4;
+    const size_t pa = std::min<size_t>((size_t)1 << SIM_DMAX, std::max<size_t>(1, 2 * (size_t)target_warps / quadsP)) * P + P;
+    D.pa_u = a.take<double>(pa); D.pa_w = a.take<double>(pa);
+    const size_t rows_max = P + nstate + 2;
+    const size_t pb = std::max(rows_max, (size_t)16 * target_warps + rows_max);
+    D.pb_u = a.take<double>(pb); D.pb_w = a.take<double>(pb);
+    D.foil_u = a.take<double>(nstate + 8); D.foil_w = a.take<double>(nstate + 8);
+}
+
+static size_t solve_smem_bytes(const SimDev &D) { return (size_t)(7 * D.P + D.Nc + 32 + D.sum_nodes) * sizeof(double); }
 
 }  // namespace ludvm
 
 using namespace ludvm;
 
-// ---------------------------------------------------------------------------------------------------
-// host object
-// ---------------------------------------------------------------------------------------------------
 struct ludvm_sim {
     ludvm_ctx *ctx = nullptr;
     ludvm_sim_params p{};
     SimDev d{};
     std::vector<void *> allocs;
+    SimDev *d_case = nullptr;  // device copy of `d` (CTA path)
+    int *d_next = nullptr;
     long steps_enqueued = 0;
     int K = 50;
     std::map<int, cudaGraphExec_t> graphs;  // (bracket, length) -> instantiated graph
@@ -562,28 +926,43 @@ struct ludvm_sim {
 
 namespace ludvm {
 
-static int dev_alloc(ludvm_sim *s, size_t n_doubles, double **out, bool zero = true)
+static int dev_malloc(std::vector<void *> &allocs, size_t bytes, void **out)
 {
     void *p = nullptr;
-    size_t bytes = std::max<size_t>(n_doubles, 1) * sizeof(double);
-    cudaError_t e = cudaMalloc(&p, bytes);
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 256));
     if (e != cudaSuccess) {
         cudaGetLastError();
         return set_error(LUDVM_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
     }
-    s->allocs.push_back(p);
-    if (zero) CUDA_TRY(cudaMemsetAsync(p, 0, bytes, s->ctx->stream));
-    *out = (double *)p;
+    allocs.push_back(p);
+    *out = p;
     return LUDVM_OK;
 }
 
-static int upload(ludvm_sim *s, const double *host, size_t n, const double **out)
+// Upload one host table set into its own arena; returns device pointers.
+static int upload_tables(ludvm_ctx *ctx, std::vector<void *> &allocs, const ludvm_sim_params &p,
+                         const ludvm_sim_tables &t, DevTables *out)
 {
-    double *d;
-    int rc = dev_alloc(s, n, &d, false);
+    const size_t nt = p.nt, P = p.P, Nc = p.Nc, nf = p.nfree;
+    struct Item { const double *h; size_t n; const double **d; };
+    Item items[] = {{t.cos_a, nt, &out->cos_a}, {t.sin_a, nt, &out->sin_a}, {t.alpha_dot, nt, &out->alpha_dot},
+                    {t.h_dot, nt, &out->h_dot}, {t.gp, nt * 2 * P, &out->gp}, {t.le, nt * 2, &out->le},
+                    {t.te, nt * 2, &out->te}, {t.detadx_p, P, &out->detadx_p}, {t.eta_p, P, &out->eta_p},
+                    {t.x_p, P, &out->x_p}, {t.theta_p, P, &out->theta_p}, {t.dtheta, P, &out->dtheta},
+                    {t.cos_tp, P, &out->cos_tp}, {t.sin_tp, P, &out->sin_tp}, {t.cosn, Nc * P, &out->cosn},
+                    {t.sinn, Nc * P, &out->sinn}, {t.free_g, nf, &out->free_g}, {t.free_xz, 2 * nf, &out->free_xz}};
+    Arena a;
+    for (auto &it : items) a.take<double>(it.n);
+    void *base;
+    int rc = dev_malloc(allocs, a.off + 256, &base);
     if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(d, host, n * sizeof(double), cudaMemcpyHostToDevice, s->ctx->stream));
-    *out = d;
+    Arena b;
+    b.base = (char *)base;
+    for (auto &it : items) {
+        double *d = b.take<double>(it.n);
+        CUDA_TRY(cudaMemcpyAsync(d, it.h, it.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        *it.d = d;
+    }
     return LUDVM_OK;
 }
 
@@ -638,113 +1017,60 @@ static int build_graph(ludvm_sim *s, int bracket, int ksteps, cudaGraphExec_t *o
     return LUDVM_OK;
 }
 
+static int set_smem_limits(size_t solve_smem, size_t finish_smem)
+{
+    if (solve_smem > 200 * 1024) return set_error(LUDVM_E_UNSUPPORTED, "Npoints too large for the solve kernel");
+    if (solve_smem > 48 * 1024) {
+        CUDA_TRY(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<CTA_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<RAMESH_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+    }
+    if (finish_smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)finish_smem));
+    return LUDVM_OK;
+}
+
 }  // namespace ludvm
 
 LUDVM_API int ludvm_sim_create(ludvm_ctx *ctx, const ludvm_sim_params *p, const ludvm_sim_tables *t, ludvm_sim **out)
 {
     ARG_CHECK(ctx && p && t && out);
     *out = nullptr;
-    ARG_CHECK(p->nt >= 2 && p->nt < (1 << 24) && p->P >= 2 && p->P <= 4096 && p->Nc >= 4 && p->Nc <= 512);
-    ARG_CHECK(p->nfree >= 1 && p->nfree < (1 << 28));
-    ARG_CHECK(p->mode == LUDVM_EXACT_F64 || p->mode == LUDVM_FAST_F64);
-    if (p->method != LUDVM_METHOD_FAURE)
-        return set_error(LUDVM_E_UNSUPPORTED, "only method='Faure' runs on the device in this build");
-    ARG_CHECK(t->cos_a && t->sin_a && t->alpha_dot && t->h_dot && t->gp && t->le && t->te && t->detadx_p && t->eta_p &&
-              t->x_p && t->theta_p && t->dtheta && t->cos_tp && t->sin_tp && t->cosn && t->sinn && t->free_g &&
-              t->free_xz);
+    int rc = check_params(p, t);
+    if (rc) return rc;
     DeviceGuard g(ctx->device);
     ludvm_sim *s = new ludvm_sim();
     s->ctx = ctx;
     s->p = *p;
     s->K = p->steps_per_graph > 0 ? p->steps_per_graph : 50;
-    SimDev &D = s->d;
-    const size_t nt = p->nt, P = p->P, Nc = p->Nc, nf = p->nfree, nv = nt - 1;
-    D.nt = (int)nt; D.P = (int)P; D.Nc = (int)Nc; D.nfree = (int)nf; D.nv = (int)nv;
-    D.method = p->method; D.mode = p->mode; D.store_history = p->store_history;
-    D.target_warps = ctx->sm_count * 48;
-    D.dt = p->dt; D.Uinf = p->Uinf; D.chord = p->chord; D.rho = p->rho; D.piv = p->piv; D.vc4 = p->vc4;
-    D.ic = p->ic; D.sum_free = p->sum_free; D.maxerror = p->maxerror; D.epsilon = p->epsilon; D.maxiter = (int)p->maxiter;
-    int rc = LUDVM_OK;
 #define TRY(x) do { if ((rc = (x)) != LUDVM_OK) { ludvm_sim_destroy(s); return rc; } } while (0)
-    TRY(upload(s, t->cos_a, nt, &D.cos_a));
-    TRY(upload(s, t->sin_a, nt, &D.sin_a));
-    TRY(upload(s, t->alpha_dot, nt, &D.alpha_dot));
-    TRY(upload(s, t->h_dot, nt, &D.h_dot));
-    TRY(upload(s, t->gp, nt * 2 * P, &D.gp));
-    TRY(upload(s, t->le, nt * 2, &D.le));
-    TRY(upload(s, t->te, nt * 2, &D.te));
-    TRY(upload(s, t->detadx_p, P, &D.detadx_p));
-    TRY(upload(s, t->eta_p, P, &D.eta_p));
-    TRY(upload(s, t->x_p, P, &D.x_p));
-    TRY(upload(s, t->theta_p, P, &D.theta_p));
-    TRY(upload(s, t->dtheta, P, &D.dtheta));
-    TRY(upload(s, t->cos_tp, P, &D.cos_tp));
-    TRY(upload(s, t->sin_tp, P, &D.sin_tp));
-    TRY(upload(s, t->cosn, Nc * P, &D.cosn));
-    TRY(upload(s, t->sinn, Nc * P, &D.sinn));
-    const size_t nstate = 2 * nv + nf;
-    TRY(dev_alloc(s, nstate, &D.wx));
-    TRY(dev_alloc(s, nstate, &D.wz));
-    TRY(dev_alloc(s, nstate, &D.wg));
-    CUDA_TRY(cudaMemcpyAsync(D.wg + 2 * nv, t->free_g, nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(D.wx + 2 * nv, t->free_xz, nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(cudaMemcpyAsync(D.wz + 2 * nv, t->free_xz + nf, nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    TRY(dev_alloc(s, nv, &D.g_bound));
-    TRY(dev_alloc(s, nv * P, &D.g_airfoil));
-    TRY(dev_alloc(s, nv * P, &D.gamma_airfoil));
-    TRY(dev_alloc(s, nv * P, &D.Gamma_airfoil));
-    TRY(dev_alloc(s, nt * 2 * Nc, &D.fourier));
-    TRY(dev_alloc(s, nt, &D.lesp));
-    TRY(dev_alloc(s, nt, &D.lesp_prev));
-    TRY(dev_alloc(s, nt, &D.lev_shed));
-    TRY(dev_alloc(s, nt, &D.Fn));
-    TRY(dev_alloc(s, nt, &D.Fs));
-    TRY(dev_alloc(s, nt, &D.L));
-    TRY(dev_alloc(s, nt, &D.D));
-    TRY(dev_alloc(s, nt, &D.T));
-    TRY(dev_alloc(s, nt, &D.M));
-    k_fill<<<ceil_div((long)nt, 256), 256, 0, ctx->stream>>>(D.lev_shed, nt, -1.0);  // LUDVM.py:654
+#define CU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { ludvm_sim_destroy(s); return set_error(LUDVM_E_CUDA, "%s failed: %s", #x, cudaGetErrorString(e__)); } } while (0)
+    DevTables dt{};
+    TRY(upload_tables(ctx, s->allocs, *p, *t, &dt));
+    const bool cta = p->method == LUDVM_METHOD_RAMESH;  // Newton loops: the whole step runs in one CTA
+    const int target = cta ? 2 * (RAMESH_THREADS / 32) : ctx->sm_count * 48;
+    const int sum_nodes = cta ? 1024 : 4096;
+    Arena measure;
+    layout_case(s->d, *p, dt, measure, target, sum_nodes, false);
+    void *base;
+    TRY(dev_malloc(s->allocs, measure.off + 256, &base));
+    CU(cudaMemsetAsync(base, 0, measure.off + 256, ctx->stream));
+    Arena real;
+    real.base = (char *)base;
+    layout_case(s->d, *p, dt, real, target, sum_nodes, false);
+    void *dc;
+    TRY(dev_malloc(s->allocs, sizeof(SimDev) + 512, &dc));
+    s->d_case = (SimDev *)dc;
+    s->d_next = (int *)((char *)dc + ((sizeof(SimDev) + 255) & ~(size_t)255));
+    CU(cudaMemcpyAsync(s->d_case, &s->d, sizeof(SimDev), cudaMemcpyHostToDevice, ctx->stream));
+    k_case_init<<<1, 256, 0, ctx->stream>>>(s->d_case, 1);
     ctx->launches++;
-    double f0[2] = {p->a0_init, p->a1_init};
-    CUDA_TRY(cudaMemcpyAsync(D.fourier, f0, sizeof(f0), cudaMemcpyHostToDevice, ctx->stream));  // LUDVM.py:647
-    if (p->store_history) {
-        TRY(dev_alloc(s, nt * 2 * nv, &D.path_tev));
-        TRY(dev_alloc(s, nt * 2 * nv, &D.path_lev));
-        TRY(dev_alloc(s, nt * 2 * nf, &D.path_free));
-        // row 0 of path['FREE'] holds the initial positions (LUDVM.py:618)
-        CUDA_TRY(cudaMemcpyAsync(D.path_free, t->free_xz, 2 * nf * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    }
-    double *tmp;
-    TRY(dev_alloc(s, 8, &tmp));
-    D.counters = (long long *)tmp;
-    TRY(dev_alloc(s, (nt + 2) / 2 + 2, &tmp));
-    D.ilev_arr = (int *)tmp;
-    TRY(dev_alloc(s, 1, &D.lespcrit_cur));
-    CUDA_TRY(cudaMemcpyAsync(D.lespcrit_cur, &p->lespcrit, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    // scratch: phase-C partials and loads+convection partials
-    TRY(dev_alloc(s, ((size_t)1 << SIM_DMAX) * P, &D.pa_u, false));
-    TRY(dev_alloc(s, ((size_t)1 << SIM_DMAX) * P, &D.pa_w, false));
-    const size_t rows_max = P + nstate + 2;
-    // rows * 2^d <= 4*quads * 2*target/quads = 8*target when split; rows when not
-    size_t pb = std::max(rows_max, (size_t)16 * D.target_warps + rows_max);
-    TRY(dev_alloc(s, pb, &D.pb_u, false));
-    TRY(dev_alloc(s, pb, &D.pb_w, false));
-    TRY(dev_alloc(s, nstate + 8, &D.foil_u, false));
-    TRY(dev_alloc(s, nstate + 8, &D.foil_w, false));
+    s->solve_smem = solve_smem_bytes(s->d);
+    s->finish_smem = (2 * (size_t)p->P + 8) * sizeof(double);
+    TRY(set_smem_limits(s->solve_smem, s->finish_smem));
+    CU(cudaStreamSynchronize(ctx->stream));  // the host tables may be freed by the caller after return
 #undef TRY
-    s->solve_smem = (7 * P + Nc + 32 + SUM_NODES_MAX) * sizeof(double);
-    s->finish_smem = (2 * P + 8) * sizeof(double);
-    if (s->solve_smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->solve_smem);
-        if (e != cudaSuccess) {
-            ludvm_sim_destroy(s);
-            return set_error(LUDVM_E_CUDA, "k_solve needs %zu bytes of shared memory: %s", s->solve_smem,
-                             cudaGetErrorString(e));
-        }
-    }
-    if (s->finish_smem > 48 * 1024)
-        CUDA_TRY(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->finish_smem));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));  // the host tables may be freed by the caller after return
+#undef CU
     *out = s;
     return LUDVM_OK;
 }
@@ -755,6 +1081,15 @@ LUDVM_API int ludvm_sim_run(ludvm_sim *s, long nsteps)
     DeviceGuard g(s->ctx->device);
     long total = s->p.nt - 1;
     long todo = std::min(nsteps, total - s->steps_enqueued);
+    if (todo <= 0) return LUDVM_OK;
+    if (s->p.method == LUDVM_METHOD_RAMESH) {  // CTA path
+        CUDA_TRY(cudaMemsetAsync(s->d_next, 0, sizeof(int), s->ctx->stream));
+        k_sim_cta<RAMESH_THREADS><<<1, RAMESH_THREADS, s->solve_smem, s->ctx->stream>>>(s->d_case, 1, s->d_next, (int)todo);
+        CUDA_TRY(cudaGetLastError());
+        s->ctx->launches++;
+        s->steps_enqueued += todo;
+        return LUDVM_OK;
+    }
     // graphs of K unrolled steps (a shorter one for a tail), cached per (wake-size bracket, length)
     while (todo > 0) {
         int k = (int)std::min<long>(s->K, todo);
@@ -811,7 +1146,8 @@ static int field_info(ludvm_sim *s, int field, const void **ptr, size_t *bytes)
     case LUDVM_F_T: *ptr = D.T; *bytes = nt * d8; break;
     case LUDVM_F_M: *ptr = D.M; *bytes = nt * d8; break;
     case LUDVM_F_COUNTERS: *ptr = D.counters; *bytes = 4 * sizeof(long long); break;
-    case LUDVM_F_CUR_TEV: case LUDVM_F_CUR_LEV: case LUDVM_F_CUR_FREE: *ptr = nullptr; *bytes = 2 * (field == LUDVM_F_CUR_FREE ? nf : nv) * d8; break;
+    case LUDVM_F_CUR_TEV: case LUDVM_F_CUR_LEV: case LUDVM_F_CUR_FREE:
+        *ptr = nullptr; *bytes = 2 * (field == LUDVM_F_CUR_FREE ? nf : nv) * d8; break;
     default: return set_error(LUDVM_E_ARG, "unknown field %d", field);
     }
     return LUDVM_OK;
@@ -857,5 +1193,75 @@ LUDVM_API int ludvm_sim_destroy(ludvm_sim *s)
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
     for (void *p : s->allocs) cudaFree(p);
     delete s;
+    return LUDVM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// batched parameter sweep (BASELINE.json configs[3]): ncases independent simulations, one CTA per case
+// ---------------------------------------------------------------------------------------------------
+LUDVM_API int ludvm_sweep_run(ludvm_ctx *ctx, long ncases, const ludvm_sim_params *params,
+                              const ludvm_sim_tables *tables, double *out, size_t out_doubles_per_case)
+{
+    ARG_CHECK(ctx && params && tables && out && ncases > 0 && ncases < (1 << 24));
+    int rc;
+    const ludvm_sim_params &p0 = params[0];
+    for (long c = 0; c < ncases; c++) {
+        if ((rc = check_params(&params[c], &tables[c]))) return rc;
+        ARG_CHECK(params[c].nt == p0.nt && params[c].P == p0.P && params[c].Nc == p0.Nc && params[c].nfree == p0.nfree);
+    }
+    const size_t nt = p0.nt;
+    ARG_CHECK(out_doubles_per_case == (size_t)LUDVM_SWEEP_FIELDS * nt);
+    DeviceGuard g(ctx->device);
+    std::vector<void *> allocs;
+    auto cleanup = [&]() { for (void *p : allocs) cudaFree(p); };
+#define TRY(x) do { if ((rc = (x)) != LUDVM_OK) { cleanup(); return rc; } } while (0)
+#define CU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { cleanup(); return set_error(LUDVM_E_CUDA, "%s failed: %s", #x, cudaGetErrorString(e__)); } } while (0)
+    // table sets shared by several cases (same host pointers) are uploaded once
+    std::map<const double *, DevTables> uploaded;
+    std::vector<SimDev> host_cases((size_t)ncases);
+    std::vector<DevTables> dts((size_t)ncases);
+    const int target = 2 * (CTA_THREADS / 32), sum_nodes = 256;
+    Arena measure;
+    for (long c = 0; c < ncases; c++) {
+        auto it = uploaded.find(tables[c].gp);
+        if (it == uploaded.end()) {
+            DevTables dt{};
+            TRY(upload_tables(ctx, allocs, params[c], tables[c], &dt));
+            it = uploaded.emplace(tables[c].gp, dt).first;
+        }
+        dts[c] = it->second;
+        layout_case(host_cases[c], params[c], dts[c], measure, target, sum_nodes, true);
+    }
+    void *base;
+    TRY(dev_malloc(allocs, measure.off + 256, &base));
+    CU(cudaMemsetAsync(base, 0, measure.off + 256, ctx->stream));
+    Arena real;
+    real.base = (char *)base;
+    for (long c = 0; c < ncases; c++) layout_case(host_cases[c], params[c], dts[c], real, target, sum_nodes, true);
+    void *dcases, *dnext;
+    TRY(dev_malloc(allocs, sizeof(SimDev) * (size_t)ncases + 256, &dcases));
+    TRY(dev_malloc(allocs, 256, &dnext));
+    CU(cudaMemcpyAsync(dcases, host_cases.data(), sizeof(SimDev) * (size_t)ncases, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemsetAsync(dnext, 0, sizeof(int), ctx->stream));
+    k_case_init<<<(unsigned)ncases, 256, 0, ctx->stream>>>((const SimDev *)dcases, (int)ncases);
+    size_t smem = solve_smem_bytes(host_cases[0]);
+    TRY(set_smem_limits(smem, 0));
+    int per_sm = 1;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_cta<CTA_THREADS>, CTA_THREADS, smem));
+    int grid = (int)std::min<long>(ncases, (long)ctx->sm_count * std::max(per_sm, 1));
+    k_sim_cta<CTA_THREADS><<<grid, CTA_THREADS, smem, ctx->stream>>>((const SimDev *)dcases, (int)ncases, (int *)dnext, (int)nt);
+    ctx->launches += 2;
+    CU(cudaGetLastError());
+    void *dout;
+    const size_t out_bytes = sizeof(double) * (size_t)ncases * out_doubles_per_case;
+    TRY(dev_malloc(allocs, out_bytes, &dout));
+    k_sweep_gather<<<(unsigned)ncases, 256, 0, ctx->stream>>>((const SimDev *)dcases, (int)ncases, (double *)dout);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+#undef CU
+#undef TRY
+    cleanup();
     return LUDVM_OK;
 }

@@ -268,8 +268,6 @@ class LUDVM:
                                       "length-Npoints and length-(Npoints-1) arrays); not provided")
         tb = tables if tables is not None else self.step_tables()
         self._tables = tb
-        if tb['method'] != 0:
-            raise NotImplementedError("method='Ramesh' (LUDVM.py:683-739, :807-909) is not on the device yet")
         nt, P, Nc, nf = tb['nt'], tb['P'], tb['Nc'], tb['nfree']
         nv = nt - 1
         L = load()

@@ -1,0 +1,145 @@
+"""Run the five BASELINE.json configurations on one B200 with parity checks against the CPU oracle and write one
+JSON report (profiles/rNN_configs.json).  Usage: python scripts/run_configs.py [--only 1,2,3,4,5] [--out file]"""
+import argparse, json, os, sys, time
+import numpy as np
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from ludvm_b200 import LUDVM, _lib, ops, sweep
+from oracle import ludvm_oracle as oracle
+
+README = dict(t0=0, tf=20, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012")
+ap = argparse.ArgumentParser()
+ap.add_argument("--only", default="1,2,3,4,5")
+ap.add_argument("--out", default="gpurun_out/configs.json")
+ap.add_argument("--hires-steps", type=int, default=20000)
+ap.add_argument("--hires-parity-steps", type=int, default=1500)
+args = ap.parse_args()
+only = set(int(x) for x in args.only.split(","))
+ctx = _lib.Context(0, torch.cuda.current_stream().cuda_stream)
+rep = {"gpu": torch.cuda.get_device_name(0), "dfma_per_s": ctx.fp64_fma_rate(200.0), "host_cores": os.cpu_count()}
+biteq = lambda a, b: bool(np.array_equal(np.asarray(a, dtype=np.float64).view(np.uint64), np.asarray(b, dtype=np.float64).view(np.uint64)))
+
+
+def dump():
+    os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+    json.dump(rep, open(args.out, "w"), indent=1)
+
+
+if 1 in only:   # README case
+    r = {}
+    for mode in ("exact", "fast"):
+        s = LUDVM(**README, verbose=False, run=False, mode=mode, ctx=ctx, steps_per_graph=400)
+        s.time_loop(); s.compute_coefficients()
+        best = min(_t for _t in [(lambda t0: (s.time_loop(), s.compute_coefficients(), time.perf_counter() - t0)[2])(time.perf_counter()) for _ in range(3)])
+        r[mode + "_steps_per_s"] = 400 / best
+        if mode == "exact":
+            ex = s
+    t0 = time.perf_counter(); o = oracle.OracleLUDVM(**README); r["cpu_oracle_1core_steps_per_s"] = 400 / (time.perf_counter() - t0)
+    r["exact_bit_equal_to_oracle"] = all(biteq(getattr(ex, k), getattr(o, k)) for k in ("Cl", "Cd", "Cm", "LESP")) and biteq(ex.path["TEV"], o.path["TEV"])
+    r["reference_numpy_steps_per_s_dev_container"] = 60.0
+    rep["config1_readme"] = r; dump(); print("config1", r, flush=True)
+
+if 2 in only:   # high-resolution run, dt=2e-3, tf=40
+    kw = dict(README, dt=2e-3, tf=40)
+    r = {}
+    nsteps = args.hires_steps
+    s = LUDVM(**kw, verbose=False, run=False, mode="fast", ctx=ctx, store_history=False)
+    tb = s.step_tables()
+    t0 = time.perf_counter(); s.time_loop(tables=tb, nsteps=nsteps); dt = time.perf_counter() - t0
+    nlev = int((s.LEV_shed[1:nsteps + 1] != -1).sum())
+    ilev_hist = np.concatenate([[0], np.cumsum(s.LEV_shed[1:nsteps + 1] != -1)])[:nsteps]
+    nw = np.arange(1, nsteps + 1) + ilev_hist + 1 + 1.0
+    pairs = float(np.sum((80 + nw) * nw + 80 * nw + 80 * (nw - 2)))
+    r.update(mode="fast", steps=nsteps, seconds=dt, steps_per_s=nsteps / dt, tev=nsteps, lev=nlev,
+             pair_interactions=pairs, pairs_per_s=pairs / dt, Cl_last=float(s.L[nsteps]))
+    s.close()
+    # exact-mode prefix parity against the oracle
+    npre = min(args.hires_parity_steps, nsteps)
+    se = LUDVM(**kw, verbose=False, run=False, mode="exact", ctx=ctx, store_history=False)
+    t0 = time.perf_counter(); se.time_loop(tables=tb, nsteps=npre); r["exact_prefix_seconds"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); o = oracle.OracleLUDVM(**kw, nsteps=npre); r["cpu_oracle_prefix_seconds"] = time.perf_counter() - t0
+    r["prefix_steps"] = npre
+    r["exact_prefix_bit_equal_to_oracle"] = all(biteq(getattr(se, k)[:npre + 1], getattr(o, k)[:npre + 1]) for k in ("L", "D", "M", "LESP", "LEV_shed"))
+    r["fast_vs_oracle_prefix_max_rel_L"] = float(np.max(np.abs(s.L[:npre + 1] - o.L[:npre + 1])) / np.max(np.abs(o.L[:npre + 1])))
+    se.close()
+    rep["config2_hires"] = r; dump(); print("config2", r, flush=True)
+
+if 3 in only:   # synthetic 1M all-pairs (the bench workload), exact + fast + fp32 single step timings
+    n = 1 << 20
+    rng = np.random.default_rng(20260101)
+    xh, zh, gh = rng.uniform(-20, 0, n), rng.uniform(-4, 4, n), rng.standard_normal(n) * 1e-2
+    g, x, z = (torch.tensor(a, device="cuda") for a in (gh, xh, zh))
+    xo, zo, uo, wo = (torch.empty_like(x) for _ in range(4))
+    r = {}
+    for mode in ("fast", "fp32", "exact"):
+        reps = 1 if mode == "exact" else 2
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); ops.selfconv_step(ctx, mode, g, x, z, 0.065 ** 4, 0.05, xo, zo, u_out=uo, w_out=wo); e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        r[mode] = {"ms": ms, "pairs_per_s": n * float(n) / (ms * 1e-3), "frac_of_dfma_slots_13": n * float(n) * 13 / (ms * 1e-3) / rep["dfma_per_s"]}
+        if mode == "fast":
+            uf, wf = uo.cpu().numpy(), wo.cpu().numpy()
+        if mode == "fp32":
+            u32 = uo.cpu().numpy()
+        if mode == "exact":
+            ue = uo.cpu().numpy()
+    rows = np.random.default_rng(7).choice(n, 4096, replace=False)
+    ur, wr = oracle.induced_velocity(gh, xh, zh, xh[rows], zh[rows], 0.065)
+    r["parity_rows"] = 4096
+    r["fast_max_abs_err_over_max_abs_u"] = float(np.max(np.abs(uf[rows] - ur)) / np.max(np.abs(ur)))
+    r["exact_bit_equal_rows"] = biteq(ue[rows], ur)
+    r["fp32_max_abs_err_over_max_abs_u"] = float(np.max(np.abs(u32[rows] - ur)) / np.max(np.abs(ur)))
+    rep["config3_allpairs_1M"] = r; dump(); print("config3", r, flush=True)
+
+if 4 in only:   # 4096-case sweep
+    cases = sweep.lespcrit_k_grid(np.linspace(0.1, 0.4, 64), np.linspace(0.1, 1.0, 64), **README)
+    r = {}
+    for mode in ("exact", "fast"):
+        t0 = time.perf_counter(); res = sweep.run_sweep(cases, mode=mode, ctx=ctx); dt = time.perf_counter() - t0
+        r[mode] = {"seconds_e2e": dt, "case_steps_per_s_e2e": len(cases) * 400 / dt, "timing": res["timing"],
+                   "case_steps_per_s_device_call": len(cases) * 400 / res["timing"]["ludvm_sweep_run_s"]}
+        if mode == "exact":
+            rex = res
+    idx = np.random.default_rng(3).choice(len(cases), 16, replace=False)
+    t0 = time.perf_counter()
+    ok = True
+    for a in idx:
+        o = oracle.OracleLUDVM(**cases[a])
+        ok &= all(biteq(rex[k][a], getattr(o, k)) for k in ("Cl", "Cd", "Cm", "LESP", "LEV_shed"))
+    r["cpu_oracle_1core_case_steps_per_s"] = 16 * 400 / (time.perf_counter() - t0)
+    r["exact_16_sampled_cases_bit_equal_to_oracle"] = bool(ok)
+    r["cases"] = len(cases)
+    rep["config4_sweep"] = r; dump(); print("config4", r, flush=True)
+
+if 5 in only:   # flow-field 4096x4096 grid, 200k vortices
+    rng = np.random.default_rng(20260102)
+    nsrc = 200000
+    xh, zh, gh = rng.uniform(-20, 0, nsrc), rng.uniform(-4, 4, nsrc), rng.standard_normal(nsrc) * 1e-2
+    x1, z1 = np.arange(-20.48, 0, 0.005), np.arange(-10.24, 10.24, 0.005)
+    r = {"nx": len(x1), "nz": len(z1), "sources": nsrc}
+    g, xs, zs, X1, Z1 = (torch.tensor(a, device="cuda") for a in (gh, xh, zh, x1, z1))
+    u = torch.empty((len(x1), len(z1)), dtype=torch.float64, device="cuda"); w = torch.empty_like(u); ome = torch.empty_like(u)
+    L = _lib.load()
+    for rep_i in range(2):
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        _lib.check(L.ludvm_flowfield_velocity(ctx.handle, _lib.FAST_F64, g.data_ptr(), xs.data_ptr(), zs.data_ptr(), nsrc, None, None, None, 0,
+                                              0.065 ** 4, X1.data_ptr(), len(x1), Z1.data_ptr(), len(z1), 0, len(x1), u.data_ptr(), w.data_ptr(), _lib.PTR_DEVICE))
+        e1.record()
+        _lib.check(L.ludvm_flowfield_vorticity(ctx.handle, X1.data_ptr(), len(x1), Z1.data_ptr(), len(z1), u.data_ptr(), w.data_ptr(), 1, ome.data_ptr(), _lib.PTR_DEVICE))
+        e2.record(); torch.cuda.synchronize()
+    pairs = float(len(x1)) * len(z1) * nsrc
+    r.update(velocity_ms=e0.elapsed_time(e1), vorticity_ms=e1.elapsed_time(e2), pairs=pairs, pairs_per_s=pairs / (e0.elapsed_time(e1) * 1e-3))
+    r["frac_of_dfma_slots_13"] = r["pairs_per_s"] * 13 / rep["dfma_per_s"]
+    pick = np.random.default_rng(11).choice(len(x1) * len(z1), 4096, replace=False)
+    ii, jj = pick // len(z1), pick % len(z1)
+    ur, wr = oracle.induced_velocity(gh, xh, zh, x1[ii], z1[jj], 0.065)
+    uh = u.cpu().numpy()
+    r["fast_max_abs_err_over_max_abs_u_4096pts"] = float(np.max(np.abs(uh[ii, jj] - ur)) / np.max(np.abs(ur)))
+    blk_u, blk_w = uh[:64, :64], w[:64, :64].cpu().numpy()
+    X, Z = np.meshgrid(x1[:64], z1[:64], indexing="ij")
+    ob = oracle.vorticity(X, Z, blk_u[None], blk_w[None])[0]
+    r["vorticity_corner_block_62x62_bit_equal"] = biteq(ome[:63, :63].cpu().numpy()[:62, :62], ob[:62, :62])
+    rep["config5_flowfield"] = r; dump(); print("config5", r, flush=True)
+dump()
