@@ -36,6 +36,8 @@ namespace ludvm {
 #define CTA_THREADS 256
 #define RAMESH_THREADS 1024
 #define PI_D 3.141592653589793
+#define SIM_TILED_MIN_WAKE 8192   // fast mode: wakes at least this large use the tiled convection kernel
+#define SIM_TILED_CHUNKS_MAX 16
 
 struct SimDev {
     int nt, P, Nc, nfree, nv, method, mode, store_history;
@@ -604,18 +606,19 @@ __device__ __forceinline__ void phase_conv_partials(const SimDev &S, const Step 
 // ---------------------------------------------------------------------------------------------------
 // phase 4: loads (one CTA) and convection update + history (thread pool)
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int conv_fold(const SimDev &S, const Step &st)
+__device__ __forceinline__ int conv_fold(const SimDev &S, const Step &st, int tiled_chunks)
 {
+    if (tiled_chunks > 0) return tiled_chunks;
     int nw = st.itev + 1 + st.ilev + 1 + S.nfree;
     return S.mode == LUDVM_EXACT_F64 ? sim_depth(nw, S.P + nw, S.target_warps) : sim_chunks(nw, S.P + nw, S.target_warps);
 }
 
-__device__ void phase_finish_loads(const SimDev &S, const Step &st, double *sm)  // LUDVM.py:1035-1090
+__device__ void phase_finish_loads(const SimDev &S, const Step &st, double *sm, int tiled_chunks)  // LUDVM.py:1035-1090
 {
     const int P = S.P, i = st.i, itev = st.itev, tid = threadIdx.x, nth = blockDim.x;
     const int nrows = P + st.itev + 1 + st.ilev + 1 + S.nfree;
     const bool exact = S.mode == LUDVM_EXACT_F64;
-    const int fold = conv_fold(S, st);
+    const int fold = conv_fold(S, st, tiled_chunks);
     double *ug = sm, *ugx = ug + P, *sc = ugx + P;
     const double ca = S.cos_a[i], sa = S.sin_a[i], hd = S.h_dot[i];
     const double *gam = S.gamma_airfoil + (size_t)itev * S.af_stride;
@@ -654,14 +657,15 @@ __device__ void phase_finish_loads(const SimDev &S, const Step &st, double *sm) 
 }
 
 // convection, LUDVM.py:1095-1127: x += dt*(u_wake + u_foil) for TEV[:nT], LEV[:nL], FREE, in place
-__device__ __forceinline__ void phase_finish_update(const SimDev &S, const Step &st, long t0, long nthreads)
+__device__ __forceinline__ void phase_finish_update(const SimDev &S, const Step &st, long t0, long nthreads,
+                                                    int tiled_chunks)
 {
     const int P = S.P, i = st.i, nv = S.nv;
     const int nT = st.itev + 1, nL = st.ilev + 1;
     SrcView W = wake_view(S, nT, nL);
     const int nrows = P + W.n;
     const bool exact = S.mode == LUDVM_EXACT_F64;
-    const int fold = conv_fold(S, st);
+    const int fold = conv_fold(S, st, tiled_chunks);
     const double dt = S.dt;
     for (long r = t0; r < W.n; r += nthreads) {
         int row = P + (int)r;
@@ -725,16 +729,45 @@ __global__ void __launch_bounds__(256) k_conv_partials(SimDev S, int s)
     phase_conv_partials(S, st, grid_pool());
 }
 
-__global__ void __launch_bounds__(256) k_finish(SimDev S, int s)
+// Large wakes in fast mode: the O(N^2) part goes through the shared-memory tiled kernel (13 FP64 slots/pair at
+// ~94% of the DFMA rate) instead of the lane-group tasks.  grid = (row blocks, chunks + 1): y < chunks evaluates the
+// wake on (gamma points ++ wake) for one source chunk; y == chunks evaluates the P bound vortices on the wake.
+template <int R>
+__global__ void __launch_bounds__(FT_THREADS, 2) k_conv_partials_tiled(SimDev S, int s, int chunks)
+{
+    __shared__ double sx[FT_TILE], sz[FT_TILE], sg[FT_TILE], sv[FT_TILE];
+    Step st;
+    if (!step_begin(S, s, st)) return;
+    const int P = S.P;
+    SrcView W = wake_view(S, st.itev + 1, st.ilev + 1);
+    const double *gx = S.gp + ((size_t)st.i * 2 + 0) * P, *gz = S.gp + ((size_t)st.i * 2 + 1) * P;
+    const int nrows = P + W.n;
+    if ((int)blockIdx.y < chunks) {
+        if ((long)blockIdx.x * (FT_THREADS * R) >= nrows) return;
+        TgtGammaWake TA{gx, gz, P, W};
+        int chunk_len = ((W.n + chunks - 1) / chunks + FT_TILE - 1) / FT_TILE * FT_TILE;
+        int c0 = blockIdx.y * chunk_len, c1 = min(W.n, c0 + chunk_len);
+        size_t po = (size_t)blockIdx.y * nrows;
+        fast_tiled_block<R>(W, TA, nrows, blockIdx.x, c0, c1, S.pb_u + po, S.pb_w + po, sx, sz, sg, sv);
+    } else {
+        if ((long)blockIdx.x * (FT_THREADS * R) >= W.n) return;
+        SrcView Fo = make_src(S.g_airfoil + (size_t)st.itev * S.af_stride, 1, gx, gz, nullptr, S.vc4, P);
+        TgtWake TW{W};
+        fast_tiled_block<R>(Fo, TW, W.n, blockIdx.x, 0, P, S.foil_u, S.foil_w, sx, sz, sg, sv);
+    }
+}
+
+__global__ void __launch_bounds__(256) k_finish(SimDev S, int s, int tiled_chunks)
 {
     extern __shared__ double sm[];
     Step st;
     if (!step_begin(S, s, st)) return;
     if (blockIdx.x == 0) {
-        phase_finish_loads(S, st, sm);
+        phase_finish_loads(S, st, sm, tiled_chunks);
         return;
     }
-    phase_finish_update(S, st, (long)(blockIdx.x - 1) * blockDim.x + threadIdx.x, (long)(gridDim.x - 1) * blockDim.x);
+    phase_finish_update(S, st, (long)(blockIdx.x - 1) * blockDim.x + threadIdx.x, (long)(gridDim.x - 1) * blockDim.x,
+                        tiled_chunks);
 }
 
 __global__ void k_advance(SimDev S, int k)
@@ -779,8 +812,8 @@ __global__ void __launch_bounds__(THREADS) k_sim_cta(const SimDev *cases, int nc
             __syncthreads();
             phase_conv_partials(S, st, pl);
             __syncthreads();
-            phase_finish_loads(S, st, sm);
-            phase_finish_update(S, st, threadIdx.x, blockDim.x);
+            phase_finish_loads(S, st, sm, 0);
+            phase_finish_update(S, st, threadIdx.x, blockDim.x, 0);
         }
         __syncthreads();
         if (threadIdx.x == 0) S.counters[0] = last;
@@ -898,7 +931,8 @@ static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t
     const size_t pa = std::min<size_t>((size_t)1 << SIM_DMAX, std::max<size_t>(1, 2 * (size_t)target_warps / quadsP)) * P + P;
     D.pa_u = a.take<double>(pa); D.pa_w = a.take<double>(pa);
     const size_t rows_max = P + nstate + 2;
-    const size_t pb = std::max(rows_max, (size_t)16 * target_warps + rows_max);
+    size_t pb = std::max(rows_max, (size_t)16 * target_warps + rows_max);
+    if (!compact && p.mode != LUDVM_EXACT_F64) pb = std::max(pb, (size_t)SIM_TILED_CHUNKS_MAX * rows_max);
     D.pb_u = a.take<double>(pb); D.pb_w = a.take<double>(pb);
     D.foil_u = a.take<double>(nstate + 8); D.foil_w = a.take<double>(nstate + 8);
 }
@@ -1002,11 +1036,25 @@ static int build_graph(ludvm_sim *s, int bracket, int ksteps, cudaGraphExec_t *o
     if (!s->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
     cudaStream_t cs = s->cap_stream;
     CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    const bool tiled = D.mode != LUDVM_EXACT_F64 && nw >= SIM_TILED_MIN_WAKE;
+    int R = 1, tchunks = 0;
+    dim3 gt(1, 1);
+    if (tiled) {
+        const long rows_up = D.P + nw;
+        R = rows_up >= 131072 ? 4 : (rows_up >= 32768 ? 2 : 1);
+        const long row_blocks = (rows_up + FT_THREADS * R - 1) / (FT_THREADS * R);
+        tchunks = (int)std::max<long>(1, std::min<long>(std::min<long>(SIM_TILED_CHUNKS_MAX, nw / (2 * FT_TILE)),
+                                                        ((long)sm * 2 * 6 + row_blocks - 1) / row_blocks));
+        gt = dim3((unsigned)row_blocks, (unsigned)tchunks + 1);
+    }
     for (int k = 0; k < ksteps; k++) {
         k_wake_on_foil<<<g1, 256, 0, cs>>>(D, k);
         k_solve<<<1, SOLVE_THREADS, s->solve_smem, cs>>>(D, k);
-        k_conv_partials<<<g3, 256, 0, cs>>>(D, k);
-        k_finish<<<g4, 256, s->finish_smem, cs>>>(D, k);
+        if (!tiled) k_conv_partials<<<g3, 256, 0, cs>>>(D, k);
+        else if (R == 4) k_conv_partials_tiled<4><<<gt, FT_THREADS, 0, cs>>>(D, k, tchunks);
+        else if (R == 2) k_conv_partials_tiled<2><<<gt, FT_THREADS, 0, cs>>>(D, k, tchunks);
+        else k_conv_partials_tiled<1><<<gt, FT_THREADS, 0, cs>>>(D, k, tchunks);
+        k_finish<<<g4, 256, s->finish_smem, cs>>>(D, k, tchunks);
     }
     k_advance<<<1, 1, 0, cs>>>(D, ksteps);
     cudaError_t e = cudaStreamEndCapture(cs, &graph);

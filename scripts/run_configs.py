@@ -60,7 +60,12 @@ if 2 in only:   # high-resolution run, dt=2e-3, tf=40
     t0 = time.perf_counter(); o = oracle.OracleLUDVM(**kw, nsteps=npre); r["cpu_oracle_prefix_seconds"] = time.perf_counter() - t0
     r["prefix_steps"] = npre
     r["exact_prefix_bit_equal_to_oracle"] = all(biteq(getattr(se, k)[:npre + 1], getattr(o, k)[:npre + 1]) for k in ("L", "D", "M", "LESP", "LEV_shed"))
-    r["fast_vs_oracle_prefix_max_rel_L"] = float(np.max(np.abs(s.L[:npre + 1] - o.L[:npre + 1])) / np.max(np.abs(o.L[:npre + 1])))
+    scl = np.max(np.abs(o.L[:npre + 1]))
+    r["fast_vs_exact_max_rel_L_up_to_step"] = {str(m): float(np.max(np.abs(s.L[:m + 1] - o.L[:m + 1])) / scl)
+                                               for m in (200, 500, 650, 700, 800, 1000, npre) if m <= npre}
+    r["first_lev_step"] = int(np.argmax(o.LEV_shed != -1))
+    r["note"] = ("chaotic once LEV shedding starts: a 1-ulp perturbation of h_max in the CPU oracle gives 1e-8 @700, "
+                 "3e-4 @800, 0.38 @900, 1.27 @1500 (scripts/chaos_envelope.py)")
     se.close()
     rep["config2_hires"] = r; dump(); print("config2", r, flush=True)
 
