@@ -10,8 +10,14 @@ __all__ = ["Context", "LudvmError", "ops", "LUDVM"]
 
 
 def __getattr__(name):
-    if name in ("LUDVM", "generate_free_vortices", "generate_free_single_vortex", "generate_flowfield_vortices",
-                "generate_flowfield_turbulence"):
+    if name == "LUDVM":
         from . import ludvm as _m
-        return getattr(_m, name)
+        return _m.LUDVM
+    if name in ("generate_free_vortices", "generate_free_single_vortex", "generate_flowfield_vortices",
+                "generate_flowfield_turbulence"):
+        from . import freevort as _f
+        return getattr(_f, name)
+    if name in ("sweep", "sharded", "freevort"):
+        import importlib
+        return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -39,6 +39,16 @@ k_fast_tiled(SrcView S, Tgt T, int nrows, int chunk_len, double *pu, double *pw_
 
 template <int R, class Tgt>
 __global__ void __launch_bounds__(FT_THREADS, 2)
+k_fast_tiled_tma(SrcView S, Tgt T, int nrows, int chunk_len, double *pu, double *pw_)
+{
+    __shared__ __align__(128) TmaTiles tiles;
+    int c0 = blockIdx.y * chunk_len, c1 = min(S.n, c0 + chunk_len);
+    size_t po = (size_t)blockIdx.y * nrows;
+    fast_tiled_block_tma<R>(S, T, nrows, blockIdx.x, c0, c1, pu + po, pw_ + po, tiles);
+}
+
+template <int R, class Tgt>
+__global__ void __launch_bounds__(FT_THREADS, 2)
 k_fast32_tiled(SrcView S, Tgt T, int nrows, int chunk_len, double *pu, double *pw_)
 {
     __shared__ float4 ssrc[FT_TILE];
@@ -161,7 +171,13 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
         if ((rc = scratch_reserve(ctx, slot, bytes, &a))) return rc;
         if ((rc = scratch_reserve(ctx, slot + 1, bytes, &b))) return rc;
         dim3 grid(row_blocks, (unsigned)chunks);
+        // one contiguous, 16-byte aligned source segment with a scalar core: TMA-staged tiles
+        const bool tma = !f32 && S.vc4 == nullptr && S.gstride == 1 && S.n0 == S.n &&
+                         (((uintptr_t)S.x | (uintptr_t)S.z | (uintptr_t)S.g) & 15) == 0 && !getenv("LUDVM_NO_TMA");
         if (f32) k_fast32_tiled<4><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
+        else if (tma && R == 4) k_fast_tiled_tma<4><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
+        else if (tma && R == 2) k_fast_tiled_tma<2><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
+        else if (tma) k_fast_tiled_tma<1><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
         else if (R == 4) k_fast_tiled<4><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
         else if (R == 2) k_fast_tiled<2><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
         else k_fast_tiled<1><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);

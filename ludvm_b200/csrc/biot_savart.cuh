@@ -290,6 +290,116 @@ __device__ __forceinline__ void fast_tiled_block(const SrcView &S, const Tgt &T,
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// fast tiled, TMA-staged: for one contiguous source segment with a scalar core the x / z / Gamma tiles are brought
+// into shared memory by the copy engine (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP), double-buffered so the
+// load of tile k+1 overlaps the FP64 work on tile k and only one __syncthreads per tile remains.  1/(2 pi) is folded
+// into the row result.  Requires 16-byte aligned source pointers; a ragged last tile is loaded by the threads.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct TmaTiles {  // [stage][x | z | g][FT_TILE]
+    double buf[2][3][FT_TILE];
+    uint64_t full[2];
+};
+
+template <int R, class Tgt>
+__device__ __forceinline__ void fast_tiled_block_tma(const SrcView &S, const Tgt &T, int nrows, int row_block, int c0,
+                                                     int c1, double *__restrict__ pu, double *__restrict__ pw_,
+                                                     TmaTiles &sm)
+{
+    double tx[R], tz[R], au[R], aw[R];
+    int base = row_block * (FT_THREADS * R) + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        int row = min(base + r * FT_THREADS, nrows - 1);
+        T.get(row, tx[r], tz[r]);
+        au[r] = 0.0;
+        aw[r] = 0.0;
+    }
+    const double vc4 = S.vc4s;
+    const int ntiles = (c1 - c0 + FT_TILE - 1) / FT_TILE;
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.full[0], 1);
+        mbar_init(&sm.full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    // producer: thread 0 hands whole tiles to the copy engine; a ragged tile is filled by all threads instead
+    auto issue = [&](int k) {
+        int t0 = c0 + k * FT_TILE, cnt = min(FT_TILE, c1 - t0), st = k & 1;
+        if (cnt == FT_TILE) {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&sm.full[st], 3 * FT_TILE * sizeof(double));
+                bulk_g2s(sm.buf[st][0], S.x + t0, FT_TILE * sizeof(double), &sm.full[st]);
+                bulk_g2s(sm.buf[st][1], S.z + t0, FT_TILE * sizeof(double), &sm.full[st]);
+                bulk_g2s(sm.buf[st][2], S.g + t0, FT_TILE * sizeof(double), &sm.full[st]);
+            }
+        } else {
+            for (int j = threadIdx.x; j < cnt; j += FT_THREADS) {
+                sm.buf[st][0][j] = S.x[t0 + j];
+                sm.buf[st][1][j] = S.z[t0 + j];
+                sm.buf[st][2][j] = S.g[t0 + j];
+            }
+            __threadfence_block();
+            if (threadIdx.x == 0) mbar_arrive(&sm.full[st]);
+        }
+    };
+    if (ntiles > 0) issue(0);
+    for (int k = 0; k < ntiles; k++) {
+        if (k + 1 < ntiles) issue(k + 1);  // stage (k+1)&1 was released by the __syncthreads of iteration k-1
+        const int st = k & 1, cnt = min(FT_TILE, c1 - (c0 + k * FT_TILE));
+        if (cnt != FT_TILE) __syncthreads();  // thread-filled tile: make every thread's stores visible
+        mbar_wait(&sm.full[st], (k >> 1) & 1);
+        const double *sx = sm.buf[st][0], *sz = sm.buf[st][1], *sg = sm.buf[st][2];
+#pragma unroll 4
+        for (int j = 0; j < cnt; j++) {
+            double x = sx[j], z = sz[j], g = sg[j];
+#pragma unroll
+            for (int r = 0; r < R; r++) pair_fast(tx[r], tz[r], x, z, g, vc4, au[r], aw[r]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        int row = base + r * FT_THREADS;
+        if (row < nrows) {
+            pu[row] = au[r] * LUDVM_INV_TWO_PI;
+            pw_[row] = aw[r] * LUDVM_INV_TWO_PI;
+        }
+    }
+}
+
 // fp32 pair arithmetic; R rows per thread.
 template <int R, class Tgt>
 __device__ __forceinline__ void fast32_tiled_block(const SrcView &S, const Tgt &T, int nrows, int row_block, int c0,
