@@ -188,8 +188,11 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    transport = {}
+
     def timed_steps(mode, steps, warmup):
-        sc = ShardedSelfConvection(g, x.clone(), z.clone(), VCORE, DT, mode=mode, ctx=ctx)
+        sc = ShardedSelfConvection(g, x.clone(), z.clone(), VCORE, DT, mode=mode, ctx=ctx, transport=args.transport)
+        transport["used"] = sc.transport
         for _ in range(warmup):
             sc.step()
         barrier()
@@ -199,7 +202,7 @@ def run_ours(args):
             flush.fill_(1)                                   # evict L2 between timed iterations
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            sc.step()                                        # kernel(s) on this stream + NCCL all-gather if G > 1
+            sc.step()                                        # kernel(s) + fused peer-store all-gather (or NCCL) if G > 1
             e1.record()
             e1.synchronize()
             times.append(e0.elapsed_time(e1))
@@ -254,10 +257,12 @@ def run_ours(args):
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": "configs[2]: synthetic all-pairs self-convection of N=%d Vatistas vortices, "
-                               "target rows sharded over %d GPU(s), NCCL all-gather of positions per step" % (n, world),
+                               "target rows sharded over %d GPU(s), positions all-gathered each step (%s)"
+                               % (n, world, {"p2p": "fused into the kernel epilogue as NVLink peer stores + symmetric-memory barrier",
+                                             "nccl": "NCCL all_gather_into_tensor", "none": "single GPU: no exchange"}[transport["used"]]),
                    "n_vortices": n, "pairs_per_step": float(n) * n, "mode": "fast_f64 (FMA + MUFU.RSQ64H rsqrt)",
                    "l2": "256 MiB buffer written between timed iterations (inputs are 24 MiB < L2)",
-                   "parallelism": "row-shard x%d" % world},
+                   "parallelism": "row-shard x%d" % world, "transport": transport["used"]},
         "clocks": clocks,
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -320,6 +325,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=1 << 20)
+    ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-step-s", type=float, default=4.0)
     args = ap.parse_args()

@@ -89,6 +89,17 @@ int ludvm_selfconv_step(ludvm_ctx *ctx, int mode, const double *gamma, const dou
                         double *x_out, double *z_out, double *u_out, double *w_out);
 
 /*
+ * Same step with the all-gather fused into the kernel epilogue: instead of writing the shard's rows locally for a
+ * later NCCL all-gather, the Euler-update kernel stores them straight into the next-position buffers of all
+ * `npeers` ranks (peer-mapped device pointers, e.g. from torch.distributed._symmetric_memory; include this rank's
+ * own buffer) over NVLink/NVSwitch.  The caller separates consecutive steps with a cross-rank barrier.
+ */
+#define LUDVM_MAX_PEERS 16
+int ludvm_selfconv_step_p2p(ludvm_ctx *ctx, int mode, const double *gamma, const double *x, const double *z,
+                            const double *vc4_per_source, double vc4, long n, long row0, long nrows, double dt,
+                            int npeers, double *const *x_out_peers, double *const *z_out_peers);
+
+/*
  * Flow-field grid evaluation -- replaces the velocity part of LUDVM.flowfield (LUDVM.py:1193-1220) for one
  * snapshot: targets are the 'ij' mesh of x1[nx] x z1[nz] (np.arange values passed by the caller), rows
  * [row0, row0+nrows) of the x index.  Up to two source sets are summed the way the reference does

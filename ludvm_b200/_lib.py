@@ -57,6 +57,8 @@ SIGNATURES = {
                                          c_vp, c_vp, C.c_long, c_vp, c_vp, C.c_int]),
     "ludvm_selfconv_step": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_long, C.c_long,
                                       C.c_long, C.c_double, c_vp, c_vp, c_vp, c_vp]),
+    "ludvm_selfconv_step_p2p": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_long, C.c_long,
+                                          C.c_long, C.c_double, C.c_int, C.POINTER(c_vp), C.POINTER(c_vp)]),
     "ludvm_flowfield_velocity": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, C.c_long, c_vp, c_vp, c_vp, C.c_long,
                                            C.c_double, c_vp, C.c_long, c_vp, C.c_long, C.c_long, C.c_long,
                                            c_vp, c_vp, C.c_int]),

@@ -69,6 +69,10 @@ struct CombineArgs {
     const double *x, *z;     // Euler: inputs (already offset to the shard's first row)
     double *xo, *zo;         // Euler: outputs (nullable)
     double dt;
+    // fused all-gather: the updated rows are also stored into every peer's buffers (NVLink peer stores),
+    // already offset to the shard's first row
+    int npeers;
+    double *xo_peer[LUDVM_MAX_PEERS], *zo_peer[LUDVM_MAX_PEERS];
 };
 
 __global__ void __launch_bounds__(256) k_combine(CombineArgs a)
@@ -95,9 +99,17 @@ __global__ void __launch_bounds__(256) k_combine(CombineArgs a)
         a.u[row] = u;
         a.w[row] = w;
     }
-    if (a.xo) {
-        a.xo[row] = __dadd_rn(a.x[row], __dmul_rn(a.dt, u));
-        a.zo[row] = __dadd_rn(a.z[row], __dmul_rn(a.dt, w));
+    if (a.xo || a.npeers) {
+        double xn = __dadd_rn(a.x[row], __dmul_rn(a.dt, u));
+        double zn = __dadd_rn(a.z[row], __dmul_rn(a.dt, w));
+        if (a.xo) {
+            a.xo[row] = xn;
+            a.zo[row] = zn;
+        }
+        for (int p = 0; p < a.npeers; p++) {  // st.global on mapped peer pointers: the all-gather, fused
+            a.xo_peer[p][row] = xn;
+            a.zo_peer[p][row] = zn;
+        }
     }
 }
 
@@ -322,6 +334,36 @@ LUDVM_API int ludvm_selfconv_step(ludvm_ctx *ctx, int mode, const double *gamma,
     a.xo = x_out + row0;
     a.zo = z_out + row0;
     a.dt = dt;
+    return launch_combine(ctx, a);
+}
+
+LUDVM_API int ludvm_selfconv_step_p2p(ludvm_ctx *ctx, int mode, const double *gamma, const double *x, const double *z,
+                                      const double *vc4_per_source, double vc4, long n, long row0, long nrows,
+                                      double dt, int npeers, double *const *x_out_peers, double *const *z_out_peers)
+{
+    ARG_CHECK(ctx != nullptr);
+    int rc = check_mode(mode);
+    if (rc) return rc;
+    ARG_CHECK(n > 0 && n < (1L << 30) && row0 >= 0 && nrows >= 0 && row0 + nrows <= n);
+    ARG_CHECK(gamma && x && z && x_out_peers && z_out_peers && npeers >= 1 && npeers <= LUDVM_MAX_PEERS);
+    if (nrows == 0) return LUDVM_OK;
+    DeviceGuard g(ctx->device);
+    SrcView S = make_src(gamma, 1, x, z, vc4_per_source, vc4, (int)n);
+    TgtArray T{x + row0, z + row0};
+    CombineArgs a{};
+    if ((rc = launch_partials(ctx, mode, S, T, nrows, 0, (double **)&a.pu, (double **)&a.pw, &a.nfold))) return rc;
+    CUDA_TRY(cudaGetLastError());
+    a.exact = (mode == LUDVM_EXACT_F64);
+    a.nrows = (int)nrows;
+    a.x = x + row0;
+    a.z = z + row0;
+    a.dt = dt;
+    a.npeers = npeers;
+    for (int p = 0; p < npeers; p++) {
+        ARG_CHECK(x_out_peers[p] && z_out_peers[p]);
+        a.xo_peer[p] = x_out_peers[p] + row0;
+        a.zo_peer[p] = z_out_peers[p] + row0;
+    }
     return launch_combine(ctx, a);
 }
 

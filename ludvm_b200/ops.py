@@ -43,6 +43,18 @@ def selfconv_step(ctx, mode, g, x, z, vc4, dt, x_out, z_out, row0=0, nrows=None,
                                      ptr(w_out)))
 
 
+def selfconv_step_p2p(ctx, mode, g, x, z, vc4, dt, x_out_peer_ptrs, z_out_peer_ptrs, row0, nrows):
+    """Self-convection step whose epilogue stores the shard's updated rows into every peer's buffers (raw peer-mapped
+    device pointers, this rank included) -- the all-gather fused into the kernel over NVLink."""
+    import ctypes as C
+    n = x.numel()
+    npeers = len(x_out_peer_ptrs)
+    xs = (_lib.c_vp * npeers)(*[int(p) for p in x_out_peer_ptrs])
+    zs = (_lib.c_vp * npeers)(*[int(p) for p in z_out_peer_ptrs])
+    check(load().ludvm_selfconv_step_p2p(ctx.handle, _mode(mode), ptr(g), ptr(x), ptr(z), None, float(vc4), n, int(row0),
+                                         int(nrows), float(dt), npeers, xs, zs))
+
+
 def flowfield_velocity(ga, xa, za, gb, xb, zb, vc4, x1, z1, row0=0, nrows=None, mode="exact", ctx=None):
     """Velocity of up to two source sets on the 'ij' mesh x1 x z1 (LUDVM.py:1193-1220), host buffers."""
     ctx = ctx or _lib.default_context()

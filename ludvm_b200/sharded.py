@@ -2,9 +2,17 @@
 (BASELINE.json configs[2]; the convection phase LUDVM.py:1095-1127 for a free cloud).
 
 Every rank holds the full source state (32 B/vortex), evaluates the rows [rank*N/G, (rank+1)*N/G) against all N
-sources with the CUDA kernel behind `ludvm_selfconv_step`, and the updated positions are all-gathered (16
-B/vortex/step).  Row sums do not depend on the shard, so the G-rank result is bitwise equal to the 1-rank one.
-The per-row kernel is injectable so the sharding/assembly logic can be exercised on CPU tensors with gloo."""
+sources with the CUDA kernel behind `ludvm_selfconv_step`, and every rank must end the step with all N updated
+positions (16 B/vortex/step).  Two transports:
+
+  transport="p2p"   the Euler-update kernel stores its rows straight into the next-position buffers of ALL ranks
+                    (peer-mapped symmetric memory, NVLink/NVSwitch stores) -- compute and all-gather in one kernel,
+                    no NCCL call in the step; consecutive steps are separated by a symmetric-memory barrier.
+  transport="nccl"  the kernel writes its rows locally, then one NCCL all-gather per coordinate.
+
+Row sums do not depend on the shard, so the G-rank result is bitwise equal to the 1-rank one.  The per-row kernel is
+injectable so the sharding/assembly logic can be exercised on CPU tensors with gloo.
+"""
 import torch
 import torch.distributed as dist
 
@@ -20,23 +28,73 @@ def shard_bounds(n, world, rank):
 
 
 class ShardedSelfConvection:
-    def __init__(self, g, x, z, v_core, dt, mode="fast", ctx=None, group=None, kernel=None):
+    def __init__(self, g, x, z, v_core, dt, mode="fast", ctx=None, group=None, kernel=None, transport="auto"):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
-        self.g, self.x, self.z = g, x, z
+        self.g = g
         self.n = x.numel()
         self.vc4, self.dt, self.mode, self.ctx = float(v_core) ** 4, float(dt), mode, ctx
         self.row0, self.nrows = shard_bounds(self.n, self.world, self.rank)
-        self._xs, self._zs = torch.empty_like(x), torch.empty_like(z)   # shard rows land here
-        self._xn, self._zn = torch.empty_like(x), torch.empty_like(z)   # gathered next state
         self._kernel = kernel or self._cuda_kernel
+        self.transport = "none"
+        self._hdl = None
+        if self.world > 1:
+            want = transport
+            if want == "auto":
+                want = "p2p" if (kernel is None and x.is_cuda) else "nccl"
+            if want == "p2p":
+                try:
+                    self._init_p2p(x, z)
+                    self.transport = "p2p"
+                except Exception as e:  # symmetric memory unavailable on this system: use the collective instead
+                    if transport == "p2p":
+                        raise
+                    self.transport_note = "p2p unavailable (%s)" % e
+                    want = "nccl"
+            if want == "nccl":
+                self.transport = "nccl"
+        if self.transport != "p2p":
+            self.x, self.z = x, z
+            self._xs, self._zs = torch.empty_like(x), torch.empty_like(z)   # shard rows land here
+            self._xn, self._zn = torch.empty_like(x), torch.empty_like(z)   # gathered next state
 
+    # -- p2p transport ---------------------------------------------------------------------------------------
+    def _init_p2p(self, x, z):
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = self.group if self.group is not None else dist.group.WORLD
+        n = self.n
+        self._bufs, self._hdls = [], []
+        for _ in range(2):                      # double buffer: [x | z] per buffer, symmetric across ranks
+            t = symm_mem.empty(2 * n, dtype=torch.float64, device=x.device)
+            h = symm_mem.rendezvous(t, grp)
+            self._bufs.append(t)
+            self._hdls.append(h)
+        self._bufs[0][:n].copy_(x)
+        self._bufs[0][n:].copy_(z)
+        self._cur = 0
+        self._hdls[0].barrier()
+        self.x, self.z = self._bufs[0][:n], self._bufs[0][n:]
+
+    def _step_p2p(self):
+        n, cur, nxt = self.n, self._cur, 1 - self._cur
+        xin, zin = self._bufs[cur][:n], self._bufs[cur][n:]
+        peers = [int(p) for p in self._hdls[nxt].buffer_ptrs]
+        ops.selfconv_step_p2p(self.ctx, self.mode, self.g, xin, zin, self.vc4, self.dt,
+                              peers, [p + 8 * n for p in peers], self.row0, self.nrows)
+        self._hdls[nxt].barrier()               # every rank's stores have landed; nobody still reads `nxt`'s old data
+        self._cur = nxt
+        self.x, self.z = self._bufs[nxt][:n], self._bufs[nxt][n:]
+        return self.x, self.z
+
+    # -- nccl / single-rank ----------------------------------------------------------------------------------
     def _cuda_kernel(self, g, x, z, vc4, dt, row0, nrows, x_out, z_out):
         ops.selfconv_step(self.ctx, self.mode, g, x, z, vc4, dt, x_out, z_out, row0=row0, nrows=nrows)
 
     def step(self):
         """One forward-Euler step of the whole cloud; returns the new (x, z) (full length on every rank)."""
+        if self.transport == "p2p":
+            return self._step_p2p()
         if self.world == 1:
             self._kernel(self.g, self.x, self.z, self.vc4, self.dt, 0, self.n, self._xn, self._zn)
         else:

@@ -15,10 +15,12 @@ rank, world = dist.get_rank(), dist.get_world_size()
 ctx = _lib.Context(local, torch.cuda.current_stream().cuda_stream)
 rng = np.random.default_rng(20260101)
 ok = True
-for n, mode, steps in ((65536, "fast", 3), (16384, "exact", 2), (65536, "fp32", 2)):
+for n, mode, steps, transport in ((65536, "fast", 3, "p2p"), (65536, "fast", 3, "nccl"), (16384, "exact", 2, "p2p"),
+                                  (65536, "fp32", 2, "nccl")):
     x_h, z_h, g_h = rng.uniform(-20, 0, n), rng.uniform(-4, 4, n), rng.standard_normal(n) * 1e-2
     g, x, z = (torch.tensor(a, device=dev) for a in (g_h, x_h, z_h))
-    sc = ShardedSelfConvection(g, x.clone(), z.clone(), 0.065, 0.05, mode=mode, ctx=ctx)
+    sc = ShardedSelfConvection(g, x.clone(), z.clone(), 0.065, 0.05, mode=mode, ctx=ctx,
+                               transport=transport if world > 1 else "auto")
     for _ in range(steps):
         xs, zs = sc.step()
     # single-rank evaluation of the same steps on this GPU
@@ -31,7 +33,8 @@ for n, mode, steps in ((65536, "fast", 3), (16384, "exact", 2), (65536, "fp32", 
     torch.cuda.synchronize()
     same = bool(torch.equal(xs, xa) and torch.equal(zs, za))
     ok &= same
-    print("rank %d/%d n=%d mode=%s steps=%d bitwise_equal_to_single_rank=%s" % (rank, world, n, mode, steps, same), flush=True)
+    print("rank %d/%d n=%d mode=%s steps=%d transport=%s bitwise_equal_to_single_rank=%s"
+          % (rank, world, n, mode, steps, sc.transport, same), flush=True)
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 dist.barrier()
