@@ -143,7 +143,8 @@ typedef struct {
     const double *detadx_p, *eta_p, *x_p, *theta_p; /* airfoil[...] panel tables [P] LUDVM.py:345-347 */
     const double *dtheta;      /* theta[1:] - theta[:-1]  [P]             LUDVM.py:995 */
     const double *cos_tp, *sin_tp; /* np.cos/np.sin(theta_panel) [P]      LUDVM.py:756, :1002 */
-    const double *cosn, *sinn; /* np.cos(n*theta_panel), np.sin(n*theta_panel) [Nc,P] LUDVM.py:771, :1000 */
+    const double *cosn, *sinn; /* np.cos(n*theta_panel), np.sin(n*theta_panel) [Nc,P] LUDVM.py:771, :1000;
+                                  row 0 of cosn is cos(0) = 1.0 exactly and is used as the unit weight of A0 */
     const double *free_g;      /* circulation_freevort [nfree]            LUDVM.py:622 */
     const double *free_xz;     /* xy_freevort [2,nfree]                   LUDVM.py:618 */
 } ludvm_sim_tables;            /* host pointers */
@@ -153,6 +154,10 @@ int ludvm_sim_create(ludvm_ctx *ctx, const ludvm_sim_params *p, const ludvm_sim_
 int ludvm_sim_run(ludvm_sim *sim, long nsteps);
 /* Steps completed so far (synchronises). */
 int ludvm_sim_steps_done(ludvm_sim *sim, long *out);
+/* Diagnostic twin of ludvm_sim_run (method Faure): advances `nsteps` steps launching the step's kernels one by one
+ * with CUDA events around each.  ms_out[0..3] = summed milliseconds of wake-on-foil, solve, convection partials,
+ * finish; ms_out[4] = their total.  Synchronises. */
+int ludvm_sim_profile_steps(ludvm_sim *sim, long nsteps, double *ms_out);
 
 enum {
     LUDVM_F_PATH_TEV = 0,  /* [nt,2,nt-1]  needs store_history  LUDVM.py:615 */
@@ -183,7 +188,7 @@ int ludvm_sim_destroy(ludvm_sim *sim);
 /*
  * Batched parameter sweep (BASELINE.json configs[3]: e.g. 4096 cases LESPcrit x reduced frequency): `ncases`
  * independent time loops, one persistent CTA per case, all steps in one launch, no collective.  All cases must
- * share nt, P, Nc, nfree; table sets shared by several cases (identical host pointers) are uploaded once.
+ * share nt, P, Nc, nfree and method; table sets shared by several cases (identical host pointers) are uploaded once.
  * out is a host buffer [ncases][LUDVM_SWEEP_FIELDS][nt] (out_doubles_per_case = LUDVM_SWEEP_FIELDS * nt) with rows
  * Fn, Fs, L, D, T, M, LESP, LESP_prev, LEV_shed, circulation TEV, LEV, bound (the last three hold nt-1 values).
  * To split a sweep over GPUs call it once per device with that device's slice of the cases.

@@ -38,11 +38,19 @@ namespace ludvm {
 #define PI_D 3.141592653589793
 #define SIM_TILED_MIN_WAKE 8192   // fast mode: wakes at least this large use the tiled convection kernel
 #define SIM_TILED_CHUNKS_MAX 16
+#define FINISH_STAGE 4096         // doubles of staging in the loads block of k_finish
+
+#ifdef LUDVM_TRACE
+__device__ long long g_trace[64];
+#define TRACE(k) do { if (threadIdx.x == 0) g_trace[k] = clock64(); } while (0)
+#else
+#define TRACE(k) do { } while (0)
+#endif
 
 struct SimDev {
     int nt, P, Nc, nfree, nv, method, mode, store_history;
     int target_warps;   // parallelism target used to pick split depths (same value in every phase of a case)
-    int sum_nodes;      // block_np_sum: tree nodes held in shared memory (power of two)
+    int sum_nodes;      // doubles of shared-memory staging (block_np_sum tree nodes, block_fold / block_trapz batches)
     int af_stride;      // row stride of the [nv,P] bound-vortex arrays (P, or 0 in compact sweep mode)
     int fourier_rows;   // nt, or 2 in compact sweep mode (row i lives at i % fourier_rows)
     double dt, Uinf, chord, rho, piv, vc4, ic, sum_free, maxerror, epsilon, lespcrit0, a0_init, a1_init;
@@ -64,6 +72,7 @@ struct SimDev {
     double *pa_u, *pa_w;  // wake-on-foil partials        [2^d1][P]
     double *pb_u, *pb_w;  // loads+convection partials    [2^d2][P + Nw2]
     double *foil_u, *foil_w;  // bound vortices on the wake [Nw2]
+    double *pre_sums;         // graph path: np.sum(Gamma_TEV[:itev]), np.sum(Gamma_LEV[:ilev]) of the current step
 };
 
 __host__ __device__ __forceinline__ int ilog2_ceil_i(int v)
@@ -87,6 +96,15 @@ __host__ __device__ __forceinline__ int sim_chunks(int n, int nrows, int target_
     int c = max(1, target_warps / max(1, quads));
     c = min(c, (n + 63) / 64);
     return min(max(c, 1), 1 << SIM_DMAX);
+}
+
+// Phase 1 has only P target rows: its partials per row are capped (2^6 tree nodes / 64 chunks) so that the fold at
+// the head of the solve kernel -- the step's critical path -- stays short; 64 x P/4 warp tasks still cover every SM.
+#define SIM_WOF_MAX_DEPTH 6
+__host__ __device__ __forceinline__ int wof_fold(int mode, int n, int P, int target_warps)
+{
+    return mode == LUDVM_EXACT_F64 ? min(sim_depth(n, P, target_warps), SIM_WOF_MAX_DEPTH)
+                                   : min(sim_chunks(n, P, target_warps), 1 << SIM_WOF_MAX_DEPTH);
 }
 
 struct Step {
@@ -178,81 +196,149 @@ __device__ __forceinline__ void phase_wake_on_foil(const SimDev &S, const Step &
     SrcView W = wake_view(S, nT, nL);
     TgtGamma T{S.gp + ((size_t)st.i * 2 + 0) * S.P, S.gp + ((size_t)st.i * 2 + 1) * S.P};
     long nquads = (S.P + 3) >> 2;
+    const int fold = wof_fold(S.mode, W.n, S.P, S.target_warps);
     if (S.mode == LUDVM_EXACT_F64) {
-        int d = sim_depth(W.n, S.P, S.target_warps);
-        for (long t = pl.wid; t < (nquads << d); t += pl.nwarps)
-            exact_rows_warp_task(W, T, S.P, d, t, pl.lane, S.pa_u, S.pa_w);
+        for (long t = pl.wid; t < (nquads << fold); t += pl.nwarps)
+            exact_rows_warp_task(W, T, S.P, fold, t, pl.lane, S.pa_u, S.pa_w);
     } else {
-        int c = sim_chunks(W.n, S.P, S.target_warps);
-        for (long t = pl.wid; t < nquads * c; t += pl.nwarps)
-            fast_rows_warp_task(W, T, S.P, c, t, pl.lane, S.pa_u, S.pa_w);
+        for (long t = pl.wid; t < nquads * fold; t += pl.nwarps)
+            fast_rows_warp_task(W, T, S.P, fold, t, pl.lane, S.pa_u, S.pa_w);
     }
 }
 
-// Fold the phase-1 partials into u1, w1 (block-strided).
-__device__ __forceinline__ void fold_wake_on_foil(const SimDev &S, int n1, double *u1, double *w1)
+// np.sum(a[off:off+n]) as numpy's tree, by the calling 8-lane group.
+__device__ __noinline__ double sum_group(const double *a, int off, int n)
 {
-    const int P = S.P;
-    if (S.mode == LUDVM_EXACT_F64) {
-        int d = sim_depth(n1, P, S.target_warps);
-        for (int j = threadIdx.x; j < P; j += blockDim.x) {
-            u1[j] = exact_combine_row(S.pa_u, P, j, d);
-            w1[j] = exact_combine_row(S.pa_w, P, j, d);
+    auto f = [a](int j) { return a[j]; };
+    return pw_group(f, off, n, (int)(threadIdx.x & 7));
+}
+
+// Fold of nn partials of one row, staged contiguously in shared memory, by the calling 8-lane group.
+//   exact: the nn = 2^d node partials are the leaves of a perfect binary tree in index order; each lane folds a
+//          contiguous subtree with the recursion's stack, an xor-butterfly closes the top levels, and numpy's
+//          additive identity finishes (np.sum = 0.0 + pairwise).
+//   fast:  nn chunk partials, any order.
+__device__ __noinline__ double fold_group(const double *v, int nn, bool exact)
+{
+    const unsigned gm = group8_mask();
+    const int lane8 = threadIdx.x & 7;
+    if (exact) {
+        const int per = max(1, nn >> 3), first = lane8 * per;
+        double r = 0.0;
+        if (first < nn) {
+            double st[PW_MAX_STACK];
+            int sp = 0;
+            for (int i = 0; i < per; i++) {
+                double x = v[first + i];
+                for (int k = i; k & 1; k >>= 1) x = __dadd_rn(st[--sp], x);
+                st[sp++] = x;
+            }
+            r = st[0];
         }
-    } else {
-        int c = sim_chunks(n1, P, S.target_warps);
-        for (int j = threadIdx.x; j < P; j += blockDim.x) {
-            u1[j] = fast_combine_row(S.pa_u, P, j, c);
-            w1[j] = fast_combine_row(S.pa_w, P, j, c);
+        for (int s = 1; s < 8 && s < nn; s <<= 1) r = __dadd_rn(r, __shfl_xor_sync(gm, r, s));
+        return __dadd_rn(0.0, r);
+    }
+    double s = 0.0;
+    for (int c = lane8; c < nn; c += 8) s += v[c];
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(gm, s, o);
+    return s;
+}
+
+// Block-wide fold of the partial sums of rows [0, nr) of two components (u, w): the partials [fold][nrows] are first
+// staged into shared memory by all threads (coalesced, every load in flight at once), then one 8-lane group per
+// (component, row) folds its row in the prescribed order.  `nfold` is the tree depth (exact) or the chunk count (fast).
+// Ends with a block barrier.
+__device__ __noinline__ void block_fold(const double *pu, const double *pw, int nrows, int nr, int nfold, bool exact,
+                                        double *stage, int cap, double *out_u, double *out_w)
+{
+    const int tid = threadIdx.x, nth = blockDim.x, lane8 = tid & 7, grp = tid >> 3, ngrp = nth >> 3;
+    const int nn = exact ? 1 << nfold : nfold, ld = nn | 1;  // odd row pitch: no bank conflicts while staging
+    const int per = max(1, cap / ld);
+    for (int t0 = 0; t0 < 2 * nr; t0 += per) {
+        const int tend = min(t0 + per, 2 * nr), nb = tend - t0;   // see the note in block_trapz
+        __syncthreads();
+        for (int idx = tid; idx < nb * nn; idx += nth) {
+            int f = idx / nb, tl = idx - f * nb, t = t0 + tl, c = t >= nr, r = t - c * nr;
+            stage[tl * ld + f] = (c ? pw : pu)[(size_t)f * nrows + r];
+        }
+        __syncthreads();
+        for (int tl = grp; tl < nb; tl += ngrp) {
+            double v = fold_group(stage + tl * ld, nn, exact);
+            if (lane8 == 0) {
+                int t = t0 + tl, c = t >= nr, r = t - c * nr;
+                (c ? out_w : out_u)[r] = v;
+            }
         }
     }
+    __syncthreads();
+}
+
+// Block-wide np.trapz of nq integrands at once:
+//   out[q] = np.trapz(a_q * b_q, x),  a_q = a0 + (q & amask) * astride,  b_q = b0 + (q >> bshift) * bstride,
+// dx[j] = x[j+1] - x[j] (the same subtraction, tabulated).  A plain np.trapz(a, x) passes a table of ones for b
+// (a * 1.0 is exact).  All threads evaluate the terms d*(y[1:]+y[:-1])/2.0 into shared memory (coalesced operand
+// loads, everything in flight at once); then one 8-lane group per integrand adds them in numpy's pairwise order.
+// The solve phase runs once per step on one CTA, so what matters is its latency: few dependent round trips and a
+// small code footprint (one out-of-line copy serves every integral of the step).  Ends with a block barrier.
+__device__ __noinline__ void block_trapz(const double *a0, int amask, int astride, const double *b0, int bshift,
+                                         int bstride, const double *dx, int P, int nq, double *stage, int cap,
+                                         double *out)
+{
+    const int n = P - 1, tid = threadIdx.x, nth = blockDim.x, lane8 = tid & 7, grp = tid >> 3, ngrp = nth >> 3;
+    const int rows = max(1, cap / P);
+    for (int q0 = 0; q0 < nq; q0 += rows) {
+        // batch [q0, qend): written as min(q0 + rows, nq) - q0, NOT min(rows, nq - q0) -- when ptxas (12.9) clones this
+        // function for a call site with a literal nq it folds `nq - q0` into VIADDMNMX(q0 + (-nq), rows), i.e. the
+        // wrong sign, and the batch comes out empty (observed in k_finish: both load integrals stayed 0)
+        const int qend = min(q0 + rows, nq), nb = qend - q0;
+        __syncthreads();
+        for (int idx = tid; idx < nb * n; idx += nth) {
+            int q = idx / n, j = idx - q * n, qq = q0 + q;
+            const double *a = a0 + (qq & amask) * astride, *b = b0 + (size_t)(qq >> bshift) * bstride;
+            stage[q * P + j] = dx[j] * (a[j + 1] * b[j + 1] + a[j] * b[j]) / 2.0;
+        }
+        __syncthreads();
+        for (int q = grp; q < nb; q += ngrp) {
+            double v = 0.0 + sum_group(stage + q * P, 0, n);
+            if (lane8 == 0) out[q0 + q] = v;
+
+        }
+    }
+    __syncthreads();
 }
 
 // ---------------------------------------------------------------------------------------------------
 // phase 2 helpers
 // ---------------------------------------------------------------------------------------------------
 
-// np.sum(a[:n]) by the whole block: tree nodes at depth d are summed by one thread each, thread 0 folds them.
-__device__ double block_np_sum(const double *a, int n, double *s_nodes, int max_nodes, double *s_out)
+// np.sum(a[:n]) by the whole block: the tree nodes at depth d are summed by 8-lane groups, the top of the tree is
+// folded level by level in shared memory.  Returns the sum on every thread.  Starts with a block barrier (so stores
+// to `a` and to shared memory made before the call are visible inside and after it).
+__device__ __noinline__ double block_np_sum(const double *a, int n, double *s_nodes, int max_nodes)
 {
     __syncthreads();
+    const int lane8 = threadIdx.x & 7, grp = threadIdx.x >> 3, ngrp = blockDim.x >> 3;
     int d = pw_max_depth(n);
     while ((1 << d) > max_nodes) d--;
-    int nn = 1 << d;
-    auto f = [a](int j) { return a[j]; };
-    for (int b = threadIdx.x; b < nn; b += blockDim.x) {
+    const int nn = 1 << d;
+    for (int b = grp; b < nn; b += ngrp) {
         int off, len;
         pw_node(n, d, b, off, len);
-        s_nodes[b] = pw_seq(f, off, len);
+        double v = sum_group(a, off, len);
+        if (lane8 == 0) s_nodes[b] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double stck[PW_MAX_STACK];
-        int sp = 0;
-        for (int i = 0; i < nn; i++) {
-            double v = s_nodes[i];
-            for (int k = i; k & 1; k >>= 1) v = __dadd_rn(stck[--sp], v);
-            stck[sp++] = v;
-        }
-        *s_out = 0.0 + stck[0];
+    for (int stride = 1; stride < nn; stride <<= 1) {  // left + right, in place at the left child's slot
+        for (int i = threadIdx.x * 2 * stride; i < nn; i += blockDim.x * 2 * stride)
+            s_nodes[i] = __dadd_rn(s_nodes[i], s_nodes[i + stride]);
+        __syncthreads();
     }
-    __syncthreads();
-    return *s_out;
-}
-
-// np.trapz(y, x) over P points by one thread.
-template <class Y>
-__device__ double trapz_seq(Y y, const double *x, int P)
-{
-    auto term = [&](int j) {
-        double d = x[j + 1] - x[j];
-        return d * (y(j + 1) + y(j)) / 2.0;
-    };
-    return 0.0 + pw_seq(term, 0, P - 1);
+    return 0.0 + s_nodes[0];
 }
 
 // unit-strength influence of a vortex at (xv, zv) on panel j (LUDVM.py:749-754): T = detadx*ut - un
-__device__ __forceinline__ double unit_T(const SimDev &S, double xa, double za, double xv, double zv, double ca,
+__device__ __noinline__ double unit_T(const SimDev &S, double xa, double za, double xv, double zv, double ca,
                                          double sa, double detadx)
 {
     double tu, tw;
@@ -280,80 +366,108 @@ __device__ __forceinline__ void solve2x2(double a00, double a01, double a10, dou
     x0 = fma(-a01, x1, b0) / a00;
 }
 
-// A0 = -1/pi*trapz(W/Uinf), An = 2/pi*trapz(W/Uinf*cos(n theta))  (LUDVM.py:694-695, :769-771)
-__device__ __forceinline__ double fourier_coeff(const SimDev &S, const double *W, int n)
-{
-    const double Uinf = S.Uinf;
-    if (n == 0) return (-1 / PI_D) * trapz_seq([&](int j) { return W[j] / Uinf; }, S.theta_p, S.P);
-    const double *cn = S.cosn + (size_t)n * S.P;
-    return (2 / PI_D) * trapz_seq([&](int j) { return W[j] / Uinf * cn[j]; }, S.theta_p, S.P);
-}
-
 struct Kin {  // per-step kinematics
     double ca, sa, ad, hd;
     const double *xa, *za;
 };
 
-// airfoil_downwash epilogue (LUDVM.py:587-593): global (u1,w1) at the gamma points -> normal downwash W
-__device__ __forceinline__ void downwash_from_uw(const SimDev &S, const Kin &k, const double *u1, const double *w1,
-                                                 double *W)
+// airfoil_downwash epilogue (LUDVM.py:587-593): global (u1,w1) at gamma point j -> normal downwash W_j
+__device__ __noinline__ double downwash_at(const SimDev &S, const Kin &k, const double *u1, const double *w1, int j)
 {
     double s1 = S.Uinf * k.ca + k.hd * k.sa, us = S.Uinf * k.sa, hc = k.hd * k.ca;
-    for (int j = threadIdx.x; j < S.P; j += blockDim.x) {
-        double u = u1[j] * k.ca - w1[j] * k.sa;
-        double w = u1[j] * k.sa + w1[j] * k.ca;
-        W[j] = S.detadx_p[j] * (s1 + u - k.ad * S.eta_p[j]) - us - k.ad * (S.x_p[j] - S.piv) + hc - w;
-    }
+    double u = u1[j] * k.ca - w1[j] * k.sa;
+    double w = u1[j] * k.sa + w1[j] * k.ca;
+    return S.detadx_p[j] * (s1 + u - k.ad * S.eta_p[j]) - us - k.ad * (S.x_p[j] - S.piv) + hc - w;
 }
 
-// Whole-block airfoil_downwash of the wake TEV[:nT] ++ LEV[:nL] ++ FREE (used by the Ramesh iterations).
-__device__ void cta_downwash(const SimDev &S, const Step &st, const Kin &k, int nT, int nL, double *u1, double *w1,
-                             double *W)
+struct SolveSmem {  // carve-up of the solve phase's dynamic shared memory
+    double *u1, *w1, *T1, *T2, *T3, *W, *dG, *Wu, *dth, *cm1, *ones, *A, *sc, *nodes;
+    __device__ __forceinline__ SolveSmem(double *sm, int P, int Nc)
+    {
+        u1 = sm; w1 = u1 + P; T1 = w1 + P; T2 = T1 + P; T3 = T2 + P; W = T3 + P; dG = W + P; Wu = dG + P;
+        dth = Wu + P; cm1 = dth + P; ones = cm1 + P; A = ones + P; sc = A + Nc; nodes = sc + 32;
+    }
+};
+#define SOLVE_SMEM_DOUBLES(P, Nc, sum_nodes) (11 * (P) + (Nc) + 32 + (sum_nodes))
+
+// Fold the phase-1 partials into u1, w1 (block-wide; ends with a barrier).
+__device__ __forceinline__ void fold_wake_on_foil(const SimDev &S, int n1, const SolveSmem &m)
+{
+    block_fold(S.pa_u, S.pa_w, S.P, S.P, wof_fold(S.mode, n1, S.P, S.target_warps), S.mode == LUDVM_EXACT_F64, m.nodes,
+               S.sum_nodes, m.u1, m.w1);
+}
+
+// Fourier coefficients n0 .. n0+nq-1 of the downwash into A[]: A0 = -1/pi*trapz(W/Uinf), An = 2/pi*trapz(W/Uinf*
+// cos(n theta)) (LUDVM.py:694-695, :769-771).  Wu[j] = W[j] / Uinf (tabulated: the same division); row 0 of the
+// cos(n theta) table is cos(0) = 1.0 exactly, so A0's integrand W/Uinf * 1.0 needs no special case.  Block-wide.
+__device__ __forceinline__ void block_fourier(const SimDev &S, const SolveSmem &m, int n0, int nq, double *A)
+{
+    block_trapz(m.Wu, 0, 0, S.cosn + (size_t)n0 * S.P, 0, S.P, m.dth, S.P, nq, m.nodes, S.sum_nodes, A + n0);
+    for (int n = n0 + threadIdx.x; n < n0 + nq; n += blockDim.x) A[n] = (n == 0 ? (-1 / PI_D) : (2 / PI_D)) * A[n];
+    __syncthreads();
+}
+
+// Whole-block airfoil_downwash of the wake TEV[:nT] ++ LEV[:nL] ++ FREE (used by the Ramesh iterations):
+// fills W and Wu = W / Uinf.
+__device__ __noinline__ void cta_downwash(const SimDev &S, const Step &st, const Kin &k, int nT, int nL, const SolveSmem &m)
 {
     __syncthreads();  // circulation guesses written by thread 0 are visible
     phase_wake_on_foil(S, st, nT, nL, block_pool());
-    __syncthreads();
-    fold_wake_on_foil(S, nT + nL + S.nfree, u1, w1);
-    __syncthreads();
-    downwash_from_uw(S, k, u1, w1, W);
+    fold_wake_on_foil(S, nT + nL + S.nfree, m);
+    for (int j = threadIdx.x; j < S.P; j += blockDim.x) {
+        double w = downwash_at(S, k, m.u1, m.w1, j);
+        m.W[j] = w;
+        m.Wu[j] = w / S.Uinf;
+    }
     __syncthreads();
 }
 
-// Kelvin residual of the Newton loops (LUDVM.py:697-699, :825-827); A0 on thread 0, A1 on thread 32.
-__device__ double cta_kelvin_f(const SimDev &S, const Step &st, const double *W, double *sc, double *nodes)
+// Kelvin residual of the Newton loops (LUDVM.py:697-699, :825-827).  Leaves A0 in sc[20], A1 in sc[21], the bound
+// circulation in sc[24]; returns the residual on every thread.
+__device__ __noinline__ double cta_kelvin_f(const SimDev &S, const Step &st, const SolveSmem &m)
 {
-    if (threadIdx.x == 0) sc[20] = fourier_coeff(S, W, 0);
-    if (threadIdx.x == 32) sc[21] = fourier_coeff(S, W, 1);
-    double sT = block_np_sum(S.wg, st.itev + 1, nodes, S.sum_nodes, &sc[22]);
-    double sL = block_np_sum(S.wg + S.nv, st.ilev + 1, nodes, S.sum_nodes, &sc[23]);
-    if (threadIdx.x == 0) {
-        double cb = S.Uinf * S.chord * PI_D * (sc[20] + sc[21] / 2);
-        sc[24] = cb;
-        sc[25] = cb + sT + sL + S.sum_free - S.ic;
-    }
+    block_fourier(S, m, 0, 2, m.sc + 20);
+    double sT = block_np_sum(S.wg, st.itev + 1, m.nodes, S.sum_nodes);
+    double sL = block_np_sum(S.wg + S.nv, st.ilev + 1, m.nodes, S.sum_nodes);
+    double cb = S.Uinf * S.chord * PI_D * (m.sc[20] + m.sc[21] / 2);
+    double f = cb + sT + sL + S.sum_free - S.ic;
+    if (threadIdx.x == 0) m.sc[24] = cb;
     __syncthreads();
-    return sc[25];
+    return f;
 }
 
 // ---------------------------------------------------------------------------------------------------
 // phase 2: the scalar phases (one CTA).  Faure expects the phase-1 partials of TEV[:itev] ++ LEV[:ilev] ++ FREE.
+// Every reduction over the panels (np.trapz, np.sum) is evaluated by an 8-lane group in numpy's own order, so the
+// 30 Fourier coefficients, the I/J integrals and the row folds all run side by side; scalars that every thread
+// needs are recomputed by every thread from shared operands (identical arithmetic) instead of being broadcast
+// through another barrier.
 // ---------------------------------------------------------------------------------------------------
-__device__ void phase_solve(const SimDev &S, const Step &st, double *sm)
+template <int METHOD>
+__device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const double *pre_sums)
 {
     const int P = S.P, Nc = S.Nc, tid = threadIdx.x, nth = blockDim.x;
+    const int lane8 = tid & 7, grp = tid >> 3, ngrp = nth >> 3;
     const int i = st.i, itev = st.itev, ilev = st.ilev, nv = S.nv;
-    double *u1 = sm, *w1 = u1 + P, *T1 = w1 + P, *T2 = T1 + P, *T3 = T2 + P, *W = T3 + P, *dG = W + P;
-    double *A = dG + P, *sc = A + Nc, *nodes = sc + 32;
-    // sc[]: 0 xt, 1 zt, 2 sT, 3 sL, 4 I1, 5 I2, 6 I3, 7 J1, 8 J2, 9 J3, 10 gtev, 11 glev, 12 shed, 13 xl, 14 zl,
+    const SolveSmem m(sm, P, Nc);
+    double *const T1 = m.T1, *const T2 = m.T2, *const T3 = m.T3, *const W = m.W, *const Wu = m.Wu, *const dG = m.dG;
+    double *const A = m.A, *const sc = m.sc;
+    // sc[]: 0 xt, 1 zt, 4 I1, 5 I2, 6 trapz(T1), 7 trapz(T2), 8 I3, 9 trapz(T3), 10 gtev, 11 glev, 13 xl, 14 zl,
     //       15 lespcrit, 16 bound, 20.. Newton scratch
     Kin k{S.cos_a[i], S.sin_a[i], S.alpha_dot[i], S.h_dot[i], S.gp + ((size_t)i * 2 + 0) * P,
           S.gp + ((size_t)i * 2 + 1) * P};
     const double ca = k.ca, sa = k.sa;
     const double Uinf = S.Uinf, chord = S.chord, dt = S.dt;
-    const bool ramesh = S.method == LUDVM_METHOD_RAMESH;
+    constexpr bool ramesh = METHOD == LUDVM_METHOD_RAMESH;
     double *F = S.fourier + (size_t)(i % S.fourier_rows) * 2 * Nc;
     const double *Fprev = S.fourier + (size_t)((i - 1) % S.fourier_rows) * 2 * Nc;
 
+    TRACE(0);
+    for (int j = tid; j < P; j += nth) {
+        m.dth[j] = (j + 1 < P) ? S.theta_p[j + 1] - S.theta_p[j] : 0.0;
+        m.cm1[j] = S.cos_tp[j] - 1;
+        m.ones[j] = 1.0;
+    }
     // TEV placement (LUDVM.py:672-681)
     if (tid == 0) {
         double xt, zt;
@@ -376,31 +490,45 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm)
             S.wz[nv + ilev] = 0.0;
         }
     }
+    double sT = 0.0, sL = 0.0;  // np.sum(circulation['TEV'][:itev]), np.sum(circulation['LEV'][:ilev])
     if (!ramesh) {
         // Faure closed form (LUDVM.py:741-773)
-        fold_wake_on_foil(S, itev + ilev + S.nfree, u1, w1);
-        double sT = block_np_sum(S.wg, itev, nodes, S.sum_nodes, &sc[2]);       // LUDVM.py:758-759
-        double sL = block_np_sum(S.wg + nv, ilev, nodes, S.sum_nodes, &sc[3]);
-        downwash_from_uw(S, k, u1, w1, T1);
-        for (int j = tid; j < P; j += nth) T2[j] = unit_T(S, k.xa[j], k.za[j], sc[0], sc[1], ca, sa, S.detadx_p[j]);
-        __syncthreads();
-        if (tid == 0) sc[4] = trapz_seq([&](int j) { return T1[j] * (S.cos_tp[j] - 1); }, S.theta_p, P);
-        if (tid == 32) sc[5] = trapz_seq([&](int j) { return T2[j] * (S.cos_tp[j] - 1); }, S.theta_p, P);
-        __syncthreads();
+        TRACE(1);
+        fold_wake_on_foil(S, itev + ilev + S.nfree, m);
+        TRACE(2);
+        if (pre_sums) {   // evaluated beside phase 1 (graph path): identical arithmetic, off the critical path
+            sT = pre_sums[0];
+            sL = pre_sums[1];
+        } else {
+            sT = block_np_sum(S.wg, itev, m.nodes, S.sum_nodes);       // LUDVM.py:758-759
+            TRACE(3);
+            sL = block_np_sum(S.wg + nv, ilev, m.nodes, S.sum_nodes);
+        }
+        TRACE(4);
+        for (int idx = tid; idx < 2 * P; idx += nth) {
+            if (idx < P) T1[idx] = downwash_at(S, k, m.u1, m.w1, idx);
+            else T2[idx - P] = unit_T(S, k.xa[idx - P], k.za[idx - P], sc[0], sc[1], ca, sa, S.detadx_p[idx - P]);
+        }
+        TRACE(5);
+        // I1, I2 (LUDVM.py:756-757) -> sc[4], sc[5] and -- needed only if a LEV is shed, but free here -- the raw
+        // integrals of J1, J2 (LUDVM.py:940-941) -> sc[6], sc[7]   (T2 = T1 + P, ones = cm1 + P in the layout)
+        block_trapz(T1, 1, P, m.cm1, 1, P, m.dth, P, 4, m.nodes, S.sum_nodes, sc + 4);
+        TRACE(6);
+        const double I1 = sc[4], I2 = sc[5];
+        const double gtev = -(I1 + sT + sL + S.sum_free - S.ic) / (1 + I2);  // LUDVM.py:758-760
         if (tid == 0) {
-            double I1 = sc[4], I2 = sc[5];
-            sc[10] = -(I1 + sT + sL + S.sum_free - S.ic) / (1 + I2);  // LUDVM.py:758-760
-            sc[16] = I1 + sc[10] * I2;                                // circulation['bound'], LUDVM.py:762
+            sc[10] = gtev;
+            sc[16] = I1 + gtev * I2;                                          // circulation['bound'], LUDVM.py:762
         }
-        __syncthreads();
-        for (int j = tid; j < P; j += nth) W[j] = T1[j] + sc[10] * T2[j];  // LUDVM.py:767
-        __syncthreads();
-        for (int n = tid; n < Nc; n += nth) {                              // LUDVM.py:769-773
-            double a = fourier_coeff(S, W, n);
-            A[n] = a;
-            F[Nc + n] = (a - Fprev[n]) / dt;
+        for (int j = tid; j < P; j += nth) {                                  // LUDVM.py:767
+            double w = T1[j] + gtev * T2[j];
+            W[j] = w;
+            Wu[j] = w / Uinf;
         }
-        __syncthreads();
+        TRACE(7);
+        block_fourier(S, m, 0, Nc, A);                                        // LUDVM.py:769-773
+        for (int n = tid; n < Nc; n += nth) F[Nc + n] = (A[n] - Fprev[n]) / dt;
+        TRACE(8);
     } else {
         // Ramesh 1-D Newton on the TEV strength (LUDVM.py:683-739)
         if (tid == 0) {
@@ -412,12 +540,11 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm)
         while (fabs(sc[26]) > S.maxerror && niter < S.maxiter) {
             double shed = sc[27];
             if (tid == 0) S.wg[itev] = shed;
-            cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
-            double f = cta_kelvin_f(S, st, W, sc, nodes);
+            cta_downwash(S, st, k, itev + 1, ilev + 1, m);
+            double f = cta_kelvin_f(S, st, m);
             if (tid == 0) S.wg[itev] = shed + S.epsilon;
-            cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
-            double fdelta = cta_kelvin_f(S, st, W, sc, nodes);
-            __syncthreads();
+            cta_downwash(S, st, k, itev + 1, ilev + 1, m);
+            double fdelta = cta_kelvin_f(S, st, m);
             if (tid == 0) {
                 double fprime = (fdelta - f) / S.epsilon;
                 sc[27] = shed - f / fprime;
@@ -427,69 +554,65 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm)
             __syncthreads();
             niter++;
         }
-        cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
-        for (int n = tid; n < Nc; n += nth) {
-            double a = fourier_coeff(S, W, n);
-            A[n] = a;
-            F[Nc + n] = (a - Fprev[n]) / dt;
-        }
-        __syncthreads();
+        cta_downwash(S, st, k, itev + 1, ilev + 1, m);
+        block_fourier(S, m, 0, Nc, A);
+        for (int n = tid; n < Nc; n += nth) F[Nc + n] = (A[n] - Fprev[n]) / dt;
         if (tid == 0) {
             sc[10] = S.wg[itev];
             sc[16] = Uinf * chord * PI_D * (A[0] + A[1] / 2);  // LUDVM.py:734
         }
         __syncthreads();
     }
-    // LESP test (LUDVM.py:775-781)
-    if (tid == 0) {
-        S.lesp_prev[itev] = A[0];
-        sc[12] = (fabs(A[0]) >= fabs(sc[15])) ? 1.0 : 0.0;
-    }
-    __syncthreads();
-    const bool shed = sc[12] != 0.0;
+    // LESP test (LUDVM.py:775-781); |.| makes the comparison blind to the sign flip thread 0 applies below
+    if (tid == 0) S.lesp_prev[itev] = A[0];
+    const bool shed = fabs(A[0]) >= fabs(sc[15]);
     if (shed) {
-        if (tid == 0) {  // LEV placement (LUDVM.py:784-805)
-            double lex = S.le[(size_t)i * 2], lez = S.le[(size_t)i * 2 + 1], xl = lex, zl = lez;
-            if (ilev > 0 && S.lev_shed[i - 1] != -1.0) {
-                xl = lex + 1.0 / 3 * (S.wx[nv + ilev - 1] - lex);
-                zl = lez + 1.0 / 3 * (S.wz[nv + ilev - 1] - lez);
-            }
-            sc[13] = xl;
-            sc[14] = zl;
-            sc[15] = (A[0] < 0) ? -fabs(sc[15]) : fabs(sc[15]);
-            S.lev_shed[i] = (double)ilev;
-            if (ramesh) {
-                S.wx[nv + ilev] = xl;
-                S.wz[nv + ilev] = zl;
-            }
+        // LEV placement (LUDVM.py:784-805), evaluated by every thread
+        double lex = S.le[(size_t)i * 2], lez = S.le[(size_t)i * 2 + 1], xl = lex, zl = lez;
+        if (ilev > 0 && S.lev_shed[i - 1] != -1.0) {
+            xl = lex + 1.0 / 3 * (S.wx[nv + ilev - 1] - lex);
+            zl = lez + 1.0 / 3 * (S.wz[nv + ilev - 1] - lez);
         }
-        __syncthreads();
         if (!ramesh) {
             // Faure 2x2 linear system (LUDVM.py:916-961); T1, T2, I1, I2 are unchanged recomputations there
-            for (int j = tid; j < P; j += nth) T3[j] = unit_T(S, k.xa[j], k.za[j], sc[13], sc[14], ca, sa, S.detadx_p[j]);
+            for (int j = tid; j < P; j += nth) T3[j] = unit_T(S, k.xa[j], k.za[j], xl, zl, ca, sa, S.detadx_p[j]);
+            __syncthreads();   // every thread has evaluated `shed` and read lev_shed[i-1]
+            if (tid == 0) {
+                sc[13] = xl;
+                sc[14] = zl;
+                sc[15] = (A[0] < 0) ? -fabs(sc[15]) : fabs(sc[15]);
+                S.lev_shed[i] = (double)ilev;
+            }
+            block_trapz(T3, 0, 0, m.cm1, 0, P, m.dth, P, 2, m.nodes, S.sum_nodes, sc + 8);  // I3, raw J3 -> sc[8], sc[9]
+            // LUDVM.py:945-959, on every thread
+            const double I1 = sc[4], I2 = sc[5], I3 = sc[8];
+            const double J1 = (-1 / PI_D) * sc[6], J2 = (-1 / PI_D) * sc[7], J3 = (-1 / PI_D) * sc[9];
+            const double b1 = -(I1 + sT + sL + S.sum_free - S.ic), b2 = sc[15] - J1;
+            double x0, x1;
+            solve2x2(1 + I2, 1 + I3, J2, J3, b1, b2, x0, x1);
+            for (int j = tid; j < P; j += nth) {
+                double w = T1[j] + x0 * T2[j] + x1 * T3[j];
+                W[j] = w;
+                Wu[j] = w / Uinf;
+            }
             __syncthreads();
-            if (tid == 0) sc[6] = trapz_seq([&](int j) { return T3[j] * (S.cos_tp[j] - 1); }, S.theta_p, P);
-            if (tid == 32) sc[7] = (-1 / PI_D) * trapz_seq([&](int j) { return T1[j]; }, S.theta_p, P);
-            if (tid == 64) sc[8] = (-1 / PI_D) * trapz_seq([&](int j) { return T2[j]; }, S.theta_p, P);
-            if (tid == 96) sc[9] = (-1 / PI_D) * trapz_seq([&](int j) { return T3[j]; }, S.theta_p, P);
-            __syncthreads();
-            if (tid == 0) {  // LUDVM.py:945-959
-                double I1 = sc[4], I2 = sc[5], I3 = sc[6], J1 = sc[7], J2 = sc[8], J3 = sc[9];
-                double b1 = -(I1 + sc[2] + sc[3] + S.sum_free - S.ic), b2 = sc[15] - J1, x0, x1;
-                solve2x2(1 + I2, 1 + I3, J2, J3, b1, b2, x0, x1);
+            if (tid == 0) {
                 sc[10] = x0;
                 sc[11] = x1;
                 sc[16] = I1 + x0 * I2 + x1 * I3;
                 A[0] = J1 + x0 * J2 + x1 * J3;
             }
-            __syncthreads();
-            for (int j = tid; j < P; j += nth) W[j] = T1[j] + sc[10] * T2[j] + sc[11] * T3[j];
-            __syncthreads();
-            for (int n = 1 + tid; n < Nc; n += nth) A[n] = fourier_coeff(S, W, n);  // LUDVM.py:960-961
-            __syncthreads();
+            block_fourier(S, m, 1, Nc - 1, A);  // LUDVM.py:960-961
         } else {
-            // Ramesh 2-D Newton on (LEV, TEV) strengths (LUDVM.py:807-909)
+            __syncthreads();   // every thread has evaluated `shed` and read lev_shed[i-1]
             if (tid == 0) {
+                sc[13] = xl;
+                sc[14] = zl;
+                sc[15] = (A[0] < 0) ? -fabs(sc[15]) : fabs(sc[15]);
+                S.lev_shed[i] = (double)ilev;
+                S.wx[nv + ilev] = xl;
+                S.wz[nv + ilev] = zl;
+                // Ramesh 2-D Newton on (LEV, TEV) strengths (LUDVM.py:807-909)
                 sc[26] = 0.1;          // f1
                 sc[27] = 0.1;          // f2
                 sc[28] = S.wg[itev];   // TEV_shed_gamma
@@ -500,17 +623,17 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm)
             while ((fabs(sc[26]) > S.maxerror || fabs(sc[27]) > S.maxerror) && niter < S.maxiter) {
                 double tg = sc[28], lg = sc[29];
                 if (tid == 0) { S.wg[itev] = tg; S.wg[nv + ilev] = lg; }
-                cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
-                double f1 = cta_kelvin_f(S, st, W, sc, nodes);
+                cta_downwash(S, st, k, itev + 1, ilev + 1, m);
+                double f1 = cta_kelvin_f(S, st, m);
                 double cbound = sc[24], f2 = sc[15] - sc[20];
                 __syncthreads();
                 if (tid == 0) { S.wg[itev] = tg + S.epsilon; S.wg[nv + ilev] = lg; }
-                cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
-                double f1dT = cta_kelvin_f(S, st, W, sc, nodes), f2dT = sc[15] - sc[20];
+                cta_downwash(S, st, k, itev + 1, ilev + 1, m);
+                double f1dT = cta_kelvin_f(S, st, m), f2dT = sc[15] - sc[20];
                 __syncthreads();
                 if (tid == 0) { S.wg[itev] = tg; S.wg[nv + ilev] = lg + S.epsilon; }
-                cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
-                double f1dL = cta_kelvin_f(S, st, W, sc, nodes), f2dL = sc[15] - sc[20];
+                cta_downwash(S, st, k, itev + 1, ilev + 1, m);
+                double f1dL = cta_kelvin_f(S, st, m), f2dL = sc[15] - sc[20];
                 __syncthreads();
                 if (tid == 0) {
                     double eps = S.epsilon, x0, x1;
@@ -526,9 +649,8 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm)
                 __syncthreads();
                 niter++;
             }
-            cta_downwash(S, st, k, itev + 1, ilev + 1, u1, w1, W);
-            for (int n = tid; n < Nc; n += nth) A[n] = fourier_coeff(S, W, n);  // LUDVM.py:902-909
-            __syncthreads();
+            cta_downwash(S, st, k, itev + 1, ilev + 1, m);
+            block_fourier(S, m, 0, Nc, A);  // LUDVM.py:902-909
             if (tid == 0) {
                 sc[10] = S.wg[itev];
                 sc[11] = S.wg[nv + ilev];
@@ -538,6 +660,7 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm)
         }
     }
     // commit the step's circulations and bookkeeping
+    TRACE(9);
     if (tid == 0) {
         S.wg[itev] = sc[10];
         if (shed) {
@@ -558,6 +681,7 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm)
     const size_t arow = (size_t)itev * S.af_stride;
     for (int j = tid; j < P; j += nth) {
         double term2 = 0;
+#pragma unroll 4
         for (int n = 1; n < Nc; n++) term2 = A[n] * S.sinn[(size_t)n * P + j] + term2;
         double term1 = A[0] * (1 + S.cos_tp[j]) / S.sin_tp[j];
         double gamma = 2 * Uinf * (term1 + term2);
@@ -566,10 +690,17 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm)
         S.g_airfoil[arow + j] = dg;
         S.gamma_airfoil[arow + j] = gamma;
     }
-    __syncthreads();
-    for (int j = tid; j < P; j += nth) {
+    TRACE(10);
+}
+
+// Gamma_j = np.sum(dGamma[:j+1]) (LUDVM.py:1008-1010); nothing in the step consumes it, so it runs beside the loads.
+__device__ __forceinline__ void phase_gamma_cumsum(const SimDev &S, const Step &st, int t0, int nthreads)
+{
+    const double *dG = S.g_airfoil + (size_t)st.itev * S.af_stride;
+    double *out = S.Gamma_airfoil + (size_t)st.itev * S.af_stride;
+    for (int j = t0; j < S.P; j += nthreads) {
         auto f = [&](int kk) { return dG[kk]; };
-        S.Gamma_airfoil[arow + j] = 0.0 + pw_seq(f, 0, j + 1);
+        out[j] = 0.0 + pw_seq(f, 0, j + 1);
     }
 }
 
@@ -613,27 +744,27 @@ __device__ __forceinline__ int conv_fold(const SimDev &S, const Step &st, int ti
     return S.mode == LUDVM_EXACT_F64 ? sim_depth(nw, S.P + nw, S.target_warps) : sim_chunks(nw, S.P + nw, S.target_warps);
 }
 
-__device__ void phase_finish_loads(const SimDev &S, const Step &st, double *sm, int tiled_chunks)  // LUDVM.py:1035-1090
+__device__ void phase_finish_loads(const SimDev &S, const Step &st, double *sm, int tiled_chunks, int cap)  // LUDVM.py:1035-1090
 {
     const int P = S.P, i = st.i, itev = st.itev, tid = threadIdx.x, nth = blockDim.x;
     const int nrows = P + st.itev + 1 + st.ilev + 1 + S.nfree;
     const bool exact = S.mode == LUDVM_EXACT_F64;
     const int fold = conv_fold(S, st, tiled_chunks);
-    double *ug = sm, *ugx = ug + P, *sc = ugx + P;
+    double *ug = sm, *ugx = ug + P, *dxp = ugx + P, *ones = dxp + P, *sc = ones + P, *stage = sc + 8;
     const double ca = S.cos_a[i], sa = S.sin_a[i], hd = S.h_dot[i];
     const double *gam = S.gamma_airfoil + (size_t)itev * S.af_stride;
-    __syncthreads();
     for (int j = tid; j < P; j += nth) {
-        double u1 = exact ? exact_combine_row(S.pb_u, nrows, j, fold) : fast_combine_row(S.pb_u, nrows, j, fold);
-        double w1 = exact ? exact_combine_row(S.pb_w, nrows, j, fold) : fast_combine_row(S.pb_w, nrows, j, fold);
+        dxp[j] = (j + 1 < P) ? S.x_p[j + 1] - S.x_p[j] : 0.0;
+        ones[j] = 1.0;
+    }
+    block_fold(S.pb_u, S.pb_w, nrows, P, fold, exact, stage, cap, ug, ugx);  // wake velocity at the gamma points
+    for (int j = tid; j < P; j += nth) {
+        double u1 = ug[j], w1 = ugx[j];
         double u = u1 * ca - w1 * sa;
         ug[j] = u * gam[j];
         ugx[j] = u * gam[j] * S.x_p[j];
     }
-    __syncthreads();
-    if (tid == 0) sc[0] = trapz_seq([&](int j) { return ug[j]; }, S.x_p, P);
-    if (tid == 32) sc[1] = trapz_seq([&](int j) { return ugx[j]; }, S.x_p, P);
-    __syncthreads();
+    block_trapz(ug, 1, P, ones, 0, 0, dxp, P, 2, stage, cap, sc);   // trapz(ug, x_p), trapz(ugx, x_p)
     if (tid == 0) {
         const double *F = S.fourier + (size_t)(i % S.fourier_rows) * 2 * S.Nc, *Fd = F + S.Nc;
         const double rho = S.rho, chord = S.chord, Uinf = S.Uinf;
@@ -711,15 +842,32 @@ __global__ void __launch_bounds__(256) k_wake_on_foil(SimDev S, int s)
 {
     Step st;
     if (!step_begin(S, s, st)) return;
-    phase_wake_on_foil(S, st, st.itev, st.ilev, grid_pool());
+    if (blockIdx.x == gridDim.x - 1) {  // the last block evaluates the two circulation sums of LUDVM.py:758-759
+        __shared__ double s_nodes[1024];
+        double sT = block_np_sum(S.wg, st.itev, s_nodes, 1024);
+        double sL = block_np_sum(S.wg + S.nv, st.ilev, s_nodes, 1024);
+        if (threadIdx.x == 0) {
+            S.pre_sums[0] = sT;
+            S.pre_sums[1] = sL;
+        }
+        return;
+    }
+    Pool pl = grid_pool();
+    pl.nwarps -= blockDim.x >> 5;
+    pl.nth -= blockDim.x;
+    phase_wake_on_foil(S, st, st.itev, st.ilev, pl);
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SimDev S, int s)
 {
     extern __shared__ double sm[];
     Step st;
+    TRACE(20);
     if (!step_begin(S, s, st)) return;
-    phase_solve(S, st, sm);
+    TRACE(21);
+    phase_solve<LUDVM_METHOD_FAURE>(S, st, sm, S.pre_sums);
+    __syncthreads();
+    TRACE(22);
 }
 
 __global__ void __launch_bounds__(256) k_conv_partials(SimDev S, int s)
@@ -763,10 +911,14 @@ __global__ void __launch_bounds__(256) k_finish(SimDev S, int s, int tiled_chunk
     Step st;
     if (!step_begin(S, s, st)) return;
     if (blockIdx.x == 0) {
-        phase_finish_loads(S, st, sm, tiled_chunks);
+        phase_finish_loads(S, st, sm, tiled_chunks, FINISH_STAGE);
         return;
     }
-    phase_finish_update(S, st, (long)(blockIdx.x - 1) * blockDim.x + threadIdx.x, (long)(gridDim.x - 1) * blockDim.x,
+    if (blockIdx.x == 1) {
+        phase_gamma_cumsum(S, st, threadIdx.x, blockDim.x);
+        return;
+    }
+    phase_finish_update(S, st, (long)(blockIdx.x - 2) * blockDim.x + threadIdx.x, (long)(gridDim.x - 2) * blockDim.x,
                         tiled_chunks);
 }
 
@@ -779,7 +931,7 @@ __global__ void k_advance(SimDev S, int k)
 // ---------------------------------------------------------------------------------------------------
 // CTA path: one persistent CTA per case, all steps
 // ---------------------------------------------------------------------------------------------------
-template <int THREADS>
+template <int THREADS, int METHOD>
 __global__ void __launch_bounds__(THREADS) k_sim_cta(const SimDev *cases, int ncases, int *next_case, int nsteps)
 {
     extern __shared__ double sm[];
@@ -804,16 +956,17 @@ __global__ void __launch_bounds__(THREADS) k_sim_cta(const SimDev *cases, int nc
         for (int i = first; i <= last; i++) {
             __syncthreads();
             Step st{i, i - 1, S.ilev_arr[i]};
-            if (S.method == LUDVM_METHOD_FAURE) {
+            if (METHOD == LUDVM_METHOD_FAURE) {
                 phase_wake_on_foil(S, st, st.itev, st.ilev, pl);
                 __syncthreads();
             }
-            phase_solve(S, st, sm);
+            phase_solve<METHOD>(S, st, sm, nullptr);
             __syncthreads();
             phase_conv_partials(S, st, pl);
             __syncthreads();
-            phase_finish_loads(S, st, sm, 0);
+            phase_finish_loads(S, st, sm, 0, S.sum_nodes);
             phase_finish_update(S, st, threadIdx.x, blockDim.x, 0);
+            phase_gamma_cumsum(S, st, threadIdx.x, blockDim.x);
         }
         __syncthreads();
         if (threadIdx.x == 0) S.counters[0] = last;
@@ -935,9 +1088,10 @@ static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t
     if (!compact && p.mode != LUDVM_EXACT_F64) pb = std::max(pb, (size_t)SIM_TILED_CHUNKS_MAX * rows_max);
     D.pb_u = a.take<double>(pb); D.pb_w = a.take<double>(pb);
     D.foil_u = a.take<double>(nstate + 8); D.foil_w = a.take<double>(nstate + 8);
+    D.pre_sums = a.take<double>(2);
 }
 
-static size_t solve_smem_bytes(const SimDev &D) { return (size_t)(7 * D.P + D.Nc + 32 + D.sum_nodes) * sizeof(double); }
+static size_t solve_smem_bytes(const SimDev &D) { return (size_t)SOLVE_SMEM_DOUBLES(D.P, D.Nc, D.sum_nodes) * sizeof(double); }
 
 }  // namespace ludvm
 
@@ -1014,48 +1168,72 @@ static int bracket_of(long n)
     return b;
 }
 
-static int build_graph(ludvm_sim *s, int bracket, int ksteps, cudaGraphExec_t *out)
+// Launch geometry of one step for every wake size up to 2^bracket.
+struct StepPlan {
+    int g1, g3, g4, R, tchunks;
+    bool tiled;
+    dim3 gt;
+};
+
+static StepPlan plan_step(const ludvm_sim *s, int bracket)
 {
-    ludvm_ctx *ctx = s->ctx;
     const SimDev &D = s->d;
     const int nw = (int)std::min<long>(1L << bracket, 2L * D.nv + D.nfree + 2);  // wake-size upper bound
-    const int sm = ctx->sm_count;
+    const int sm = s->ctx->sm_count;
+    StepPlan pl{};
     // worst-case warp-task counts over every wake size n <= nw (split depth is monotone in n, capped by the target)
     const int dcap = std::min(pw_max_depth(nw), SIM_DMAX);
     const long quadsP = (D.P + 3) / 4;
-    long t1 = std::min<long>(quadsP << dcap, std::max<long>(quadsP, 2L * D.target_warps));
-    if (D.mode != LUDVM_EXACT_F64) t1 = quadsP * sim_chunks(nw, D.P, D.target_warps);
-    int g1 = (int)std::max<long>(1, std::min<long>((t1 + 7) / 8, (long)sm * 8));
+    long t1 = D.mode == LUDVM_EXACT_F64 ? quadsP << std::min(dcap, SIM_WOF_MAX_DEPTH)
+                                        : quadsP * wof_fold(D.mode, nw, D.P, D.target_warps);
+    pl.g1 = 1 + (int)std::max<long>(1, std::min<long>((t1 + 7) / 8, (long)sm * 8));  // + 1: the circulation-sum block
     const long quadsA = (D.P + nw + 3) / 4, quadsW = (nw + 3) / 4;
     long t3 = std::min<long>(quadsA << dcap, std::max<long>(quadsA, 2L * D.target_warps)) + quadsW;
     if (D.mode != LUDVM_EXACT_F64) t3 = std::max<long>(quadsA, (long)D.target_warps + quadsA) + quadsW;
-    int g3 = (int)std::max<long>(1, std::min<long>((t3 + 7) / 8, (long)sm * 16));
-    int g4 = 1 + (int)std::max<long>(1, std::min<long>((nw + 255) / 256, (long)sm * 8));
+    pl.g3 = (int)std::max<long>(1, std::min<long>((t3 + 7) / 8, (long)sm * 16));
+    pl.g4 = 2 + (int)std::max<long>(1, std::min<long>((nw + 255) / 256, (long)sm * 8));
+    pl.tiled = D.mode != LUDVM_EXACT_F64 && nw >= SIM_TILED_MIN_WAKE;
+    pl.R = 1;
+    pl.tchunks = 0;
+    pl.gt = dim3(1, 1);
+    if (pl.tiled) {
+        const long rows_up = D.P + nw;
+        pl.R = rows_up >= 131072 ? 4 : (rows_up >= 32768 ? 2 : 1);
+        const long row_blocks = (rows_up + FT_THREADS * pl.R - 1) / (FT_THREADS * pl.R);
+        pl.tchunks = (int)std::max<long>(1, std::min<long>(std::min<long>(SIM_TILED_CHUNKS_MAX, nw / (2 * FT_TILE)),
+                                                           ((long)sm * 2 * 6 + row_blocks - 1) / row_blocks));
+        pl.gt = dim3((unsigned)row_blocks, (unsigned)pl.tchunks + 1);
+    }
+    return pl;
+}
 
+// Enqueue kernel `which` (0..3) of step offset k.
+static void enqueue_step_kernel(const ludvm_sim *s, const StepPlan &pl, int which, int k, cudaStream_t cs)
+{
+    const SimDev &D = s->d;
+    switch (which) {
+    case 0: k_wake_on_foil<<<pl.g1, 256, 0, cs>>>(D, k); break;
+    case 1: k_solve<<<1, SOLVE_THREADS, s->solve_smem, cs>>>(D, k); break;
+    case 2:
+        if (!pl.tiled) k_conv_partials<<<pl.g3, 256, 0, cs>>>(D, k);
+        else if (pl.R == 4) k_conv_partials_tiled<4><<<pl.gt, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
+        else if (pl.R == 2) k_conv_partials_tiled<2><<<pl.gt, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
+        else k_conv_partials_tiled<1><<<pl.gt, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
+        break;
+    default: k_finish<<<pl.g4, 256, s->finish_smem, cs>>>(D, k, pl.tchunks); break;
+    }
+}
+
+static int build_graph(ludvm_sim *s, int bracket, int ksteps, cudaGraphExec_t *out)
+{
+    const SimDev &D = s->d;
+    const StepPlan pl = plan_step(s, bracket);
     cudaGraph_t graph;
     if (!s->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
     cudaStream_t cs = s->cap_stream;
     CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    const bool tiled = D.mode != LUDVM_EXACT_F64 && nw >= SIM_TILED_MIN_WAKE;
-    int R = 1, tchunks = 0;
-    dim3 gt(1, 1);
-    if (tiled) {
-        const long rows_up = D.P + nw;
-        R = rows_up >= 131072 ? 4 : (rows_up >= 32768 ? 2 : 1);
-        const long row_blocks = (rows_up + FT_THREADS * R - 1) / (FT_THREADS * R);
-        tchunks = (int)std::max<long>(1, std::min<long>(std::min<long>(SIM_TILED_CHUNKS_MAX, nw / (2 * FT_TILE)),
-                                                        ((long)sm * 2 * 6 + row_blocks - 1) / row_blocks));
-        gt = dim3((unsigned)row_blocks, (unsigned)tchunks + 1);
-    }
-    for (int k = 0; k < ksteps; k++) {
-        k_wake_on_foil<<<g1, 256, 0, cs>>>(D, k);
-        k_solve<<<1, SOLVE_THREADS, s->solve_smem, cs>>>(D, k);
-        if (!tiled) k_conv_partials<<<g3, 256, 0, cs>>>(D, k);
-        else if (R == 4) k_conv_partials_tiled<4><<<gt, FT_THREADS, 0, cs>>>(D, k, tchunks);
-        else if (R == 2) k_conv_partials_tiled<2><<<gt, FT_THREADS, 0, cs>>>(D, k, tchunks);
-        else k_conv_partials_tiled<1><<<gt, FT_THREADS, 0, cs>>>(D, k, tchunks);
-        k_finish<<<g4, 256, s->finish_smem, cs>>>(D, k, tchunks);
-    }
+    for (int k = 0; k < ksteps; k++)
+        for (int which = 0; which < 4; which++) enqueue_step_kernel(s, pl, which, k, cs);
     k_advance<<<1, 1, 0, cs>>>(D, ksteps);
     cudaError_t e = cudaStreamEndCapture(cs, &graph);
     if (e != cudaSuccess) return set_error(LUDVM_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
@@ -1070,8 +1248,9 @@ static int set_smem_limits(size_t solve_smem, size_t finish_smem)
     if (solve_smem > 200 * 1024) return set_error(LUDVM_E_UNSUPPORTED, "Npoints too large for the solve kernel");
     if (solve_smem > 48 * 1024) {
         CUDA_TRY(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<CTA_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<RAMESH_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<CTA_THREADS, LUDVM_METHOD_FAURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<CTA_THREADS, LUDVM_METHOD_RAMESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<RAMESH_THREADS, LUDVM_METHOD_RAMESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
     }
     if (finish_smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)finish_smem));
@@ -1097,7 +1276,9 @@ LUDVM_API int ludvm_sim_create(ludvm_ctx *ctx, const ludvm_sim_params *p, const 
     TRY(upload_tables(ctx, s->allocs, *p, *t, &dt));
     const bool cta = p->method == LUDVM_METHOD_RAMESH;  // Newton loops: the whole step runs in one CTA
     const int target = cta ? 2 * (RAMESH_THREADS / 32) : ctx->sm_count * 48;
-    const int sum_nodes = cta ? 1024 : 4096;
+    // shared-memory staging area of the block-wide folds / integrals: all Nc Fourier integrands, or 64 partials of
+    // every (row, component), in one batch
+    const int sum_nodes = (int)std::max<long>(cta ? 1024 : 4096, std::max<long>(p->Nc * p->P, cta ? 0 : 2 * p->P * 65));
     Arena measure;
     layout_case(s->d, *p, dt, measure, target, sum_nodes, false);
     void *base;
@@ -1114,7 +1295,7 @@ LUDVM_API int ludvm_sim_create(ludvm_ctx *ctx, const ludvm_sim_params *p, const 
     k_case_init<<<1, 256, 0, ctx->stream>>>(s->d_case, 1);
     ctx->launches++;
     s->solve_smem = solve_smem_bytes(s->d);
-    s->finish_smem = (2 * (size_t)p->P + 8) * sizeof(double);
+    s->finish_smem = (4 * (size_t)p->P + 8 + (size_t)std::max<long>(FINISH_STAGE, 2 * p->P)) * sizeof(double);
     TRY(set_smem_limits(s->solve_smem, s->finish_smem));
     CU(cudaStreamSynchronize(ctx->stream));  // the host tables may be freed by the caller after return
 #undef TRY
@@ -1132,7 +1313,7 @@ LUDVM_API int ludvm_sim_run(ludvm_sim *s, long nsteps)
     if (todo <= 0) return LUDVM_OK;
     if (s->p.method == LUDVM_METHOD_RAMESH) {  // CTA path
         CUDA_TRY(cudaMemsetAsync(s->d_next, 0, sizeof(int), s->ctx->stream));
-        k_sim_cta<RAMESH_THREADS><<<1, RAMESH_THREADS, s->solve_smem, s->ctx->stream>>>(s->d_case, 1, s->d_next, (int)todo);
+        k_sim_cta<RAMESH_THREADS, LUDVM_METHOD_RAMESH><<<1, RAMESH_THREADS, s->solve_smem, s->ctx->stream>>>(s->d_case, 1, s->d_next, (int)todo);
         CUDA_TRY(cudaGetLastError());
         s->ctx->launches++;
         s->steps_enqueued += todo;
@@ -1157,6 +1338,52 @@ LUDVM_API int ludvm_sim_run(ludvm_sim *s, long nsteps)
     }
     return LUDVM_OK;
 }
+
+// Diagnostic twin of ludvm_sim_run for the graph path: the same kernels with the same launch geometry, launched one
+// by one with CUDA events around each, so that the share of each phase in a step can be reported (profiles/).
+LUDVM_API int ludvm_sim_profile_steps(ludvm_sim *s, long nsteps, double *ms_out)
+{
+    ARG_CHECK(s != nullptr && nsteps >= 0 && ms_out != nullptr);
+    if (s->p.method == LUDVM_METHOD_RAMESH)
+        return set_error(LUDVM_E_UNSUPPORTED, "method='Ramesh' runs as one persistent CTA; there are no phases to time");
+    DeviceGuard g(s->ctx->device);
+    for (int q = 0; q < 5; q++) ms_out[q] = 0.0;
+    long total = s->p.nt - 1;
+    long todo = std::min(nsteps, total - s->steps_enqueued);
+    if (todo <= 0) return LUDVM_OK;
+    cudaStream_t st = s->ctx->stream;
+    cudaEvent_t ev[5];
+    for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+    for (long k = 0; k < todo; k++) {
+        const StepPlan pl = plan_step(s, bracket_of(wake_upper(s, s->steps_enqueued)));
+        for (int which = 0; which < 4; which++) {
+            CUDA_TRY(cudaEventRecord(ev[which], st));
+            enqueue_step_kernel(s, pl, which, 0, st);
+        }
+        CUDA_TRY(cudaEventRecord(ev[4], st));
+        k_advance<<<1, 1, 0, st>>>(s->d, 1);
+        CUDA_TRY(cudaEventSynchronize(ev[4]));
+        for (int which = 0; which < 4; which++) {
+            float ms = 0.f;
+            CUDA_TRY(cudaEventElapsedTime(&ms, ev[which], ev[which + 1]));
+            ms_out[which] += ms;
+            ms_out[4] += ms;
+        }
+        s->ctx->launches += 5;
+        s->steps_enqueued += 1;
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (auto &e : ev) cudaEventDestroy(e);
+    CUDA_TRY(cudaGetLastError());
+    return LUDVM_OK;
+}
+
+#ifdef LUDVM_TRACE
+extern "C" __attribute__((visibility("default"))) int ludvm_debug_trace(long long *out)
+{
+    return cudaMemcpyFromSymbol(out, ludvm::g_trace, sizeof(long long) * 64) == cudaSuccess ? 0 : -1;
+}
+#endif
 
 LUDVM_API int ludvm_sim_steps_done(ludvm_sim *s, long *out)
 {
@@ -1255,7 +1482,8 @@ LUDVM_API int ludvm_sweep_run(ludvm_ctx *ctx, long ncases, const ludvm_sim_param
     const ludvm_sim_params &p0 = params[0];
     for (long c = 0; c < ncases; c++) {
         if ((rc = check_params(&params[c], &tables[c]))) return rc;
-        ARG_CHECK(params[c].nt == p0.nt && params[c].P == p0.P && params[c].Nc == p0.Nc && params[c].nfree == p0.nfree);
+        ARG_CHECK(params[c].nt == p0.nt && params[c].P == p0.P && params[c].Nc == p0.Nc && params[c].nfree == p0.nfree &&
+                  params[c].method == p0.method);
     }
     const size_t nt = p0.nt;
     ARG_CHECK(out_doubles_per_case == (size_t)LUDVM_SWEEP_FIELDS * nt);
@@ -1268,7 +1496,7 @@ LUDVM_API int ludvm_sweep_run(ludvm_ctx *ctx, long ncases, const ludvm_sim_param
     std::map<const double *, DevTables> uploaded;
     std::vector<SimDev> host_cases((size_t)ncases);
     std::vector<DevTables> dts((size_t)ncases);
-    const int target = 2 * (CTA_THREADS / 32), sum_nodes = 256;
+    const int target = 2 * (CTA_THREADS / 32), sum_nodes = (int)std::max<long>(256, p0.Nc * p0.P);
     Arena measure;
     for (long c = 0; c < ncases; c++) {
         auto it = uploaded.find(tables[c].gp);
@@ -1295,9 +1523,12 @@ LUDVM_API int ludvm_sweep_run(ludvm_ctx *ctx, long ncases, const ludvm_sim_param
     size_t smem = solve_smem_bytes(host_cases[0]);
     TRY(set_smem_limits(smem, 0));
     int per_sm = 1;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_cta<CTA_THREADS>, CTA_THREADS, smem));
+    const bool ramesh = p0.method == LUDVM_METHOD_RAMESH;
+    if (ramesh) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_cta<CTA_THREADS, LUDVM_METHOD_RAMESH>, CTA_THREADS, smem));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_cta<CTA_THREADS, LUDVM_METHOD_FAURE>, CTA_THREADS, smem));
     int grid = (int)std::min<long>(ncases, (long)ctx->sm_count * std::max(per_sm, 1));
-    k_sim_cta<CTA_THREADS><<<grid, CTA_THREADS, smem, ctx->stream>>>((const SimDev *)dcases, (int)ncases, (int *)dnext, (int)nt);
+    if (ramesh) k_sim_cta<CTA_THREADS, LUDVM_METHOD_RAMESH><<<grid, CTA_THREADS, smem, ctx->stream>>>((const SimDev *)dcases, (int)ncases, (int *)dnext, (int)nt);
+    else k_sim_cta<CTA_THREADS, LUDVM_METHOD_FAURE><<<grid, CTA_THREADS, smem, ctx->stream>>>((const SimDev *)dcases, (int)ncases, (int *)dnext, (int)nt);
     ctx->launches += 2;
     CU(cudaGetLastError());
     void *dout;
