@@ -28,6 +28,7 @@
 #include <map>
 
 #include "biot_savart.cuh"
+#include "block_reduce.cuh"
 
 namespace ludvm {
 
@@ -51,6 +52,7 @@ struct SimDev {
     int nt, P, Nc, nfree, nv, method, mode, store_history;
     int target_warps;   // parallelism target used to pick split depths (same value in every phase of a case)
     int sum_nodes;      // doubles of shared-memory staging (block_np_sum tree nodes, block_fold / block_trapz batches)
+    int sinn_smem;      // 1: the sin(n theta) table [Nc,P] is copied to shared memory at the head of the solve phase
     int af_stride;      // row stride of the [nv,P] bound-vortex arrays (P, or 0 in compact sweep mode)
     int fourier_rows;   // nt, or 2 in compact sweep mode (row i lives at i % fourier_rows)
     double dt, Uinf, chord, rho, piv, vc4, ic, sum_free, maxerror, epsilon, lespcrit0, a0_init, a1_init;
@@ -206,136 +208,9 @@ __device__ __forceinline__ void phase_wake_on_foil(const SimDev &S, const Step &
     }
 }
 
-// np.sum(a[off:off+n]) as numpy's tree, by the calling 8-lane group.
-__device__ __noinline__ double sum_group(const double *a, int off, int n)
-{
-    auto f = [a](int j) { return a[j]; };
-    return pw_group(f, off, n, (int)(threadIdx.x & 7));
-}
-
-// Fold of nn partials of one row, staged contiguously in shared memory, by the calling 8-lane group.
-//   exact: the nn = 2^d node partials are the leaves of a perfect binary tree in index order; each lane folds a
-//          contiguous subtree with the recursion's stack, an xor-butterfly closes the top levels, and numpy's
-//          additive identity finishes (np.sum = 0.0 + pairwise).
-//   fast:  nn chunk partials, any order.
-__device__ __noinline__ double fold_group(const double *v, int nn, bool exact)
-{
-    const unsigned gm = group8_mask();
-    const int lane8 = threadIdx.x & 7;
-    if (exact) {
-        const int per = max(1, nn >> 3), first = lane8 * per;
-        double r = 0.0;
-        if (first < nn) {
-            double st[PW_MAX_STACK];
-            int sp = 0;
-            for (int i = 0; i < per; i++) {
-                double x = v[first + i];
-                for (int k = i; k & 1; k >>= 1) x = __dadd_rn(st[--sp], x);
-                st[sp++] = x;
-            }
-            r = st[0];
-        }
-        for (int s = 1; s < 8 && s < nn; s <<= 1) r = __dadd_rn(r, __shfl_xor_sync(gm, r, s));
-        return __dadd_rn(0.0, r);
-    }
-    double s = 0.0;
-    for (int c = lane8; c < nn; c += 8) s += v[c];
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) s += __shfl_xor_sync(gm, s, o);
-    return s;
-}
-
-// Block-wide fold of the partial sums of rows [0, nr) of two components (u, w): the partials [fold][nrows] are first
-// staged into shared memory by all threads (coalesced, every load in flight at once), then one 8-lane group per
-// (component, row) folds its row in the prescribed order.  `nfold` is the tree depth (exact) or the chunk count (fast).
-// Ends with a block barrier.
-__device__ __noinline__ void block_fold(const double *pu, const double *pw, int nrows, int nr, int nfold, bool exact,
-                                        double *stage, int cap, double *out_u, double *out_w)
-{
-    const int tid = threadIdx.x, nth = blockDim.x, lane8 = tid & 7, grp = tid >> 3, ngrp = nth >> 3;
-    const int nn = exact ? 1 << nfold : nfold, ld = nn | 1;  // odd row pitch: no bank conflicts while staging
-    const int per = max(1, cap / ld);
-    for (int t0 = 0; t0 < 2 * nr; t0 += per) {
-        const int tend = min(t0 + per, 2 * nr), nb = tend - t0;   // see the note in block_trapz
-        __syncthreads();
-        for (int idx = tid; idx < nb * nn; idx += nth) {
-            int f = idx / nb, tl = idx - f * nb, t = t0 + tl, c = t >= nr, r = t - c * nr;
-            stage[tl * ld + f] = (c ? pw : pu)[(size_t)f * nrows + r];
-        }
-        __syncthreads();
-        for (int tl = grp; tl < nb; tl += ngrp) {
-            double v = fold_group(stage + tl * ld, nn, exact);
-            if (lane8 == 0) {
-                int t = t0 + tl, c = t >= nr, r = t - c * nr;
-                (c ? out_w : out_u)[r] = v;
-            }
-        }
-    }
-    __syncthreads();
-}
-
-// Block-wide np.trapz of nq integrands at once:
-//   out[q] = np.trapz(a_q * b_q, x),  a_q = a0 + (q & amask) * astride,  b_q = b0 + (q >> bshift) * bstride,
-// dx[j] = x[j+1] - x[j] (the same subtraction, tabulated).  A plain np.trapz(a, x) passes a table of ones for b
-// (a * 1.0 is exact).  All threads evaluate the terms d*(y[1:]+y[:-1])/2.0 into shared memory (coalesced operand
-// loads, everything in flight at once); then one 8-lane group per integrand adds them in numpy's pairwise order.
-// The solve phase runs once per step on one CTA, so what matters is its latency: few dependent round trips and a
-// small code footprint (one out-of-line copy serves every integral of the step).  Ends with a block barrier.
-__device__ __noinline__ void block_trapz(const double *a0, int amask, int astride, const double *b0, int bshift,
-                                         int bstride, const double *dx, int P, int nq, double *stage, int cap,
-                                         double *out)
-{
-    const int n = P - 1, tid = threadIdx.x, nth = blockDim.x, lane8 = tid & 7, grp = tid >> 3, ngrp = nth >> 3;
-    const int rows = max(1, cap / P);
-    for (int q0 = 0; q0 < nq; q0 += rows) {
-        // batch [q0, qend): written as min(q0 + rows, nq) - q0, NOT min(rows, nq - q0) -- when ptxas (12.9) clones this
-        // function for a call site with a literal nq it folds `nq - q0` into VIADDMNMX(q0 + (-nq), rows), i.e. the
-        // wrong sign, and the batch comes out empty (observed in k_finish: both load integrals stayed 0)
-        const int qend = min(q0 + rows, nq), nb = qend - q0;
-        __syncthreads();
-        for (int idx = tid; idx < nb * n; idx += nth) {
-            int q = idx / n, j = idx - q * n, qq = q0 + q;
-            const double *a = a0 + (qq & amask) * astride, *b = b0 + (size_t)(qq >> bshift) * bstride;
-            stage[q * P + j] = dx[j] * (a[j + 1] * b[j + 1] + a[j] * b[j]) / 2.0;
-        }
-        __syncthreads();
-        for (int q = grp; q < nb; q += ngrp) {
-            double v = 0.0 + sum_group(stage + q * P, 0, n);
-            if (lane8 == 0) out[q0 + q] = v;
-
-        }
-    }
-    __syncthreads();
-}
-
 // ---------------------------------------------------------------------------------------------------
 // phase 2 helpers
 // ---------------------------------------------------------------------------------------------------
-
-// np.sum(a[:n]) by the whole block: the tree nodes at depth d are summed by 8-lane groups, the top of the tree is
-// folded level by level in shared memory.  Returns the sum on every thread.  Starts with a block barrier (so stores
-// to `a` and to shared memory made before the call are visible inside and after it).
-__device__ __noinline__ double block_np_sum(const double *a, int n, double *s_nodes, int max_nodes)
-{
-    __syncthreads();
-    const int lane8 = threadIdx.x & 7, grp = threadIdx.x >> 3, ngrp = blockDim.x >> 3;
-    int d = pw_max_depth(n);
-    while ((1 << d) > max_nodes) d--;
-    const int nn = 1 << d;
-    for (int b = grp; b < nn; b += ngrp) {
-        int off, len;
-        pw_node(n, d, b, off, len);
-        double v = sum_group(a, off, len);
-        if (lane8 == 0) s_nodes[b] = v;
-    }
-    __syncthreads();
-    for (int stride = 1; stride < nn; stride <<= 1) {  // left + right, in place at the left child's slot
-        for (int i = threadIdx.x * 2 * stride; i < nn; i += blockDim.x * 2 * stride)
-            s_nodes[i] = __dadd_rn(s_nodes[i], s_nodes[i + stride]);
-        __syncthreads();
-    }
-    return 0.0 + s_nodes[0];
-}
 
 // unit-strength influence of a vortex at (xv, zv) on panel j (LUDVM.py:749-754): T = detadx*ut - un
 __device__ __noinline__ double unit_T(const SimDev &S, double xa, double za, double xv, double zv, double ca,
@@ -381,14 +256,16 @@ __device__ __noinline__ double downwash_at(const SimDev &S, const Kin &k, const 
 }
 
 struct SolveSmem {  // carve-up of the solve phase's dynamic shared memory
-    double *u1, *w1, *T1, *T2, *T3, *W, *dG, *Wu, *dth, *cm1, *ones, *A, *sc, *nodes;
-    __device__ __forceinline__ SolveSmem(double *sm, int P, int Nc)
+    double *u1, *w1, *T1, *T2, *T3, *W, *dG, *Wu, *dth, *cm1, *ones, *A, *sc, *nodes, *sinn_s;
+    __device__ __forceinline__ SolveSmem(double *sm, int P, int Nc, int sum_nodes)
     {
         u1 = sm; w1 = u1 + P; T1 = w1 + P; T2 = T1 + P; T3 = T2 + P; W = T3 + P; dG = W + P; Wu = dG + P;
         dth = Wu + P; cm1 = dth + P; ones = cm1 + P; A = ones + P; sc = A + Nc; nodes = sc + 32;
+        sinn_s = nodes + sum_nodes;
     }
 };
-#define SOLVE_SMEM_DOUBLES(P, Nc, sum_nodes) (11 * (P) + (Nc) + 32 + (sum_nodes))
+#define SOLVE_SMEM_DOUBLES(P, Nc, sum_nodes, sinn_smem) (11 * (P) + (Nc) + 32 + (sum_nodes) + ((sinn_smem) ? (Nc) * (P) : 0))
+#define SINN_SMEM_MAX 4096   // largest sin(n theta) table (doubles) kept in shared memory
 
 // Fold the phase-1 partials into u1, w1 (block-wide; ends with a barrier).
 __device__ __forceinline__ void fold_wake_on_foil(const SimDev &S, int n1, const SolveSmem &m)
@@ -449,7 +326,7 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
     const int P = S.P, Nc = S.Nc, tid = threadIdx.x, nth = blockDim.x;
     const int lane8 = tid & 7, grp = tid >> 3, ngrp = nth >> 3;
     const int i = st.i, itev = st.itev, ilev = st.ilev, nv = S.nv;
-    const SolveSmem m(sm, P, Nc);
+    const SolveSmem m(sm, P, Nc, S.sum_nodes);
     double *const T1 = m.T1, *const T2 = m.T2, *const T3 = m.T3, *const W = m.W, *const Wu = m.Wu, *const dG = m.dG;
     double *const A = m.A, *const sc = m.sc;
     // sc[]: 0 xt, 1 zt, 4 I1, 5 I2, 6 trapz(T1), 7 trapz(T2), 8 I3, 9 trapz(T3), 10 gtev, 11 glev, 13 xl, 14 zl,
@@ -463,6 +340,23 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
     const double *Fprev = S.fourier + (size_t)((i - 1) % S.fourier_rows) * 2 * Nc;
 
     TRACE(0);
+    // operands of the TEV placement: loads issued first, consumed after the table set-up below
+    double tex = 0.0, tez = 0.0, pxw = 0.0, pzw = 0.0, lc0 = 0.0;
+    if (tid == 0) {
+        const size_t it = itev == 0 ? 0 : (size_t)i;
+        tex = S.te[it * 2];
+        tez = S.te[it * 2 + 1];
+        if (itev > 0) {
+            pxw = S.wx[itev - 1];
+            pzw = S.wz[itev - 1];
+        }
+        lc0 = *S.lespcrit_cur;
+    }
+    if (S.sinn_smem) {  // sin(n theta) [Nc,P] -> shared memory, asynchronously (consumed by the bound-vortex phase)
+        for (int idx = tid; idx < Nc * P; idx += nth)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(m.sinn_s + idx)), "l"(S.sinn + idx));
+        asm volatile("cp.async.commit_group;");
+    }
     for (int j = tid; j < P; j += nth) {
         m.dth[j] = (j + 1 < P) ? S.theta_p[j + 1] - S.theta_p[j] : 0.0;
         m.cm1[j] = S.cos_tp[j] - 1;
@@ -472,18 +366,17 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
     if (tid == 0) {
         double xt, zt;
         if (itev == 0) {
-            xt = S.te[0] + 0.5 * Uinf * dt;
-            zt = S.te[1] + 0.0;
+            xt = tex + 0.5 * Uinf * dt;
+            zt = tez + 0.0;
         } else {
-            double tex = S.te[(size_t)i * 2], tez = S.te[(size_t)i * 2 + 1];
-            xt = tex + 1.0 / 3 * (S.wx[itev - 1] - tex);
-            zt = tez + 1.0 / 3 * (S.wz[itev - 1] - tez);
+            xt = tex + 1.0 / 3 * (pxw - tex);
+            zt = tez + 1.0 / 3 * (pzw - tez);
         }
         sc[0] = xt;
         sc[1] = zt;
         S.wx[itev] = xt;
         S.wz[itev] = zt;
-        sc[15] = *S.lespcrit_cur;
+        sc[15] = lc0;
         sc[11] = 0.0;
         if (ramesh && ilev < nv) {  // row i of path['LEV'] starts with a zero slot
             S.wx[nv + ilev] = 0.0;
@@ -679,10 +572,16 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
     for (int n = tid; n < Nc; n += nth) F[n] = A[n];
     // bound-vortex distribution (LUDVM.py:986-1010)
     const size_t arow = (size_t)itev * S.af_stride;
+    const double *sinn = S.sinn;
+    if (S.sinn_smem) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        sinn = m.sinn_s;
+    }
     for (int j = tid; j < P; j += nth) {
         double term2 = 0;
 #pragma unroll 4
-        for (int n = 1; n < Nc; n++) term2 = A[n] * S.sinn[(size_t)n * P + j] + term2;
+        for (int n = 1; n < Nc; n++) term2 = A[n] * sinn[(size_t)n * P + j] + term2;
         double term1 = A[0] * (1 + S.cos_tp[j]) / S.sin_tp[j];
         double gamma = 2 * Uinf * (term1 + term2);
         double dg = gamma * chord / 2 * S.sin_tp[j] * S.dtheta[j];
@@ -1051,6 +950,7 @@ static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t
     D.nt = (int)nt; D.P = (int)P; D.Nc = (int)Nc; D.nfree = (int)nf; D.nv = (int)nv;
     D.method = p.method; D.mode = p.mode; D.store_history = compact ? 0 : p.store_history;
     D.target_warps = target_warps; D.sum_nodes = sum_nodes;
+    D.sinn_smem = Nc * P <= SINN_SMEM_MAX ? 1 : 0;
     D.af_stride = compact ? 0 : (int)P;
     D.fourier_rows = compact ? 2 : (int)nt;
     D.dt = p.dt; D.Uinf = p.Uinf; D.chord = p.chord; D.rho = p.rho; D.piv = p.piv; D.vc4 = p.vc4; D.ic = p.ic;
@@ -1091,7 +991,7 @@ static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t
     D.pre_sums = a.take<double>(2);
 }
 
-static size_t solve_smem_bytes(const SimDev &D) { return (size_t)SOLVE_SMEM_DOUBLES(D.P, D.Nc, D.sum_nodes) * sizeof(double); }
+static size_t solve_smem_bytes(const SimDev &D) { return (size_t)SOLVE_SMEM_DOUBLES(D.P, D.Nc, D.sum_nodes, D.sinn_smem) * sizeof(double); }
 
 }  // namespace ludvm
 
