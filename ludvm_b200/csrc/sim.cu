@@ -830,8 +830,23 @@ __global__ void k_advance(SimDev S, int k)
 // ---------------------------------------------------------------------------------------------------
 // CTA path: one persistent CTA per case, all steps
 // ---------------------------------------------------------------------------------------------------
+// Out-of-line copies of the O(N^2) phases for the one-CTA driver: their hot loops get a register allocation of their own
+// instead of sharing one with the scalar phases inlined around them.
+__device__ __noinline__ void cta_wake_on_foil(const SimDev &S, const Step &st)
+{
+    phase_wake_on_foil(S, st, st.itev, st.ilev, block_pool());
+}
+__device__ __noinline__ void cta_conv_partials(const SimDev &S, const Step &st)
+{
+    phase_conv_partials(S, st, block_pool());
+}
+__device__ __noinline__ void cta_finish_update(const SimDev &S, const Step &st)
+{
+    phase_finish_update(S, st, threadIdx.x, blockDim.x, 0);
+}
+
 template <int THREADS, int METHOD>
-__global__ void __launch_bounds__(THREADS) k_sim_cta(const SimDev *cases, int ncases, int *next_case, int nsteps)
+__global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1) k_sim_cta(const SimDev *cases, int ncases, int *next_case, int nsteps)
 {
     extern __shared__ double sm[];
     __shared__ int s_case;
@@ -851,22 +866,37 @@ __global__ void __launch_bounds__(THREADS) k_sim_cta(const SimDev *cases, int nc
         const SimDev &S = s_sim;
         const int first = (int)S.counters[0] + 1;
         const int last = min(S.nt - 1, first + nsteps - 1);
-        const Pool pl = block_pool();
+#ifdef LUDVM_TRACE
+#define CTA_T(k) do { __syncthreads(); if (threadIdx.x == 0) { long long t__ = clock64(); acc[k] += t__ - tlast; tlast = t__; } } while (0)
+        long long acc[6] = {0, 0, 0, 0, 0, 0}, tlast = clock64();
+#else
+#define CTA_T(k) do { } while (0)
+#endif
         for (int i = first; i <= last; i++) {
             __syncthreads();
             Step st{i, i - 1, S.ilev_arr[i]};
+            CTA_T(5);
             if (METHOD == LUDVM_METHOD_FAURE) {
-                phase_wake_on_foil(S, st, st.itev, st.ilev, pl);
+                cta_wake_on_foil(S, st);
                 __syncthreads();
             }
+            CTA_T(0);
             phase_solve<METHOD>(S, st, sm, nullptr);
             __syncthreads();
-            phase_conv_partials(S, st, pl);
+            CTA_T(1);
+            cta_conv_partials(S, st);
             __syncthreads();
+            CTA_T(2);
             phase_finish_loads(S, st, sm, 0, S.sum_nodes);
-            phase_finish_update(S, st, threadIdx.x, blockDim.x, 0);
+            CTA_T(3);
+            cta_finish_update(S, st);
             phase_gamma_cumsum(S, st, threadIdx.x, blockDim.x);
+            CTA_T(4);
         }
+#ifdef LUDVM_TRACE
+        if (threadIdx.x == 0)
+            for (int q = 0; q < 6; q++) atomicAdd((unsigned long long *)&g_trace[40 + q], (unsigned long long)acc[q]);
+#endif
         __syncthreads();
         if (threadIdx.x == 0) S.counters[0] = last;
     }
