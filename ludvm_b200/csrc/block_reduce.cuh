@@ -14,6 +14,12 @@ __device__ __noinline__ double sum_group(const double *a, int off, int n)
     auto f = [a](int j) { return a[j]; };
     return pw_group(f, off, n, (int)(threadIdx.x & 7));
 }
+// The same when all four groups of every calling warp sum rows of the same length n (whole-warp shuffles).
+__device__ __noinline__ double sum_group_uniform(const double *a, int n)
+{
+    auto f = [a](int j) { return a[j]; };
+    return pw_group<true>(f, 0, n, (int)(threadIdx.x & 7));
+}
 
 // Fold of nn partials of one row, staged contiguously in shared memory, by the calling 8-lane group.
 //   exact: the nn = 2^d node partials are the leaves of a perfect binary tree in index order; each lane folds a

@@ -39,6 +39,7 @@ namespace ludvm {
 #define PI_D 3.141592653589793
 #define SIM_TILED_MIN_WAKE 8192   // fast mode: wakes at least this large use the tiled convection kernel
 #define SIM_TILED_CHUNKS_MAX 16
+#define SIM_COOP_MAX_WAKE 8192    // wakes up to this size are stepped by the persistent cooperative kernel
 #define FINISH_STAGE 4096         // doubles of staging in the loads block of k_finish
 
 #ifdef LUDVM_TRACE
@@ -241,31 +242,78 @@ __device__ __forceinline__ void solve2x2(double a00, double a01, double a10, dou
     x0 = fma(-a01, x1, b0) / a00;
 }
 
+// Constant per-case tables of the scalar phases, resident in shared memory: panel tables [P] always, the
+// cos(n theta) / sin(n theta) tables [Nc,P] when they fit (S.sinn_smem), else read from global memory.  Staged once
+// per kernel launch (k_solve), once per case (one-CTA driver) or once per launch of the persistent grid.
+struct StepTables {
+    double *dth, *cm1, *ones, *detadx, *eta, *xp, *costp, *sintp, *dtheta, *dxp;  // cm1, ones adjacent (block_trapz operands)
+    const double *cosn, *sinn;
+    __device__ __forceinline__ StepTables(double *sm, const SimDev &S)
+    {
+        const int P = S.P;
+        dth = sm; cm1 = dth + P; ones = cm1 + P; detadx = ones + P; eta = detadx + P; xp = eta + P; costp = xp + P;
+        sintp = costp + P; dtheta = sintp + P; dxp = dtheta + P;
+        cosn = S.sinn_smem ? dxp + P : S.cosn;
+        sinn = S.sinn_smem ? dxp + P + (size_t)S.Nc * P : S.sinn;
+    }
+};
+#define SINN_SMEM_MAX 4096   // largest cos/sin(n theta) table (doubles each) kept in shared memory
+#define TABLE_SMEM_DOUBLES(P, Nc, big) (10 * (P) + ((big) ? 2 * (Nc) * (P) : 0))
+
+// Fill the tables (all threads of the block).  The two large tables travel asynchronously (cp.async); call
+// tables_wait() and a block barrier before reading them.
+__device__ __forceinline__ void stage_tables(const SimDev &S, const StepTables &t)
+{
+    const int P = S.P, tid = threadIdx.x, nth = blockDim.x;
+    if (S.sinn_smem) {
+        const int n = S.Nc * P;
+        double *dc = const_cast<double *>(t.cosn), *ds = const_cast<double *>(t.sinn);
+        for (int idx = tid; idx < n; idx += nth) {
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dc + idx)), "l"(S.cosn + idx));
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(ds + idx)), "l"(S.sinn + idx));
+        }
+        asm volatile("cp.async.commit_group;");
+    }
+    for (int j = tid; j < P; j += nth) {
+        t.dth[j] = (j + 1 < P) ? S.theta_p[j + 1] - S.theta_p[j] : 0.0;   // np.trapz's d = x[1:] - x[:-1]
+        t.cm1[j] = S.cos_tp[j] - 1;
+        t.ones[j] = 1.0;
+        t.detadx[j] = S.detadx_p[j];
+        t.eta[j] = S.eta_p[j];
+        t.xp[j] = S.x_p[j];
+        t.costp[j] = S.cos_tp[j];
+        t.sintp[j] = S.sin_tp[j];
+        t.dtheta[j] = S.dtheta[j];
+        t.dxp[j] = (j + 1 < P) ? S.x_p[j + 1] - S.x_p[j] : 0.0;
+    }
+}
+__device__ __forceinline__ void tables_wait() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 struct Kin {  // per-step kinematics
     double ca, sa, ad, hd;
     const double *xa, *za;
 };
 
 // airfoil_downwash epilogue (LUDVM.py:587-593): global (u1,w1) at gamma point j -> normal downwash W_j
-__device__ __noinline__ double downwash_at(const SimDev &S, const Kin &k, const double *u1, const double *w1, int j)
+__device__ __noinline__ double downwash_at(const SimDev &S, const StepTables &t, const Kin &k, const double *u1,
+                                           const double *w1, int j)
 {
     double s1 = S.Uinf * k.ca + k.hd * k.sa, us = S.Uinf * k.sa, hc = k.hd * k.ca;
     double u = u1[j] * k.ca - w1[j] * k.sa;
     double w = u1[j] * k.sa + w1[j] * k.ca;
-    return S.detadx_p[j] * (s1 + u - k.ad * S.eta_p[j]) - us - k.ad * (S.x_p[j] - S.piv) + hc - w;
+    return t.detadx[j] * (s1 + u - k.ad * t.eta[j]) - us - k.ad * (t.xp[j] - S.piv) + hc - w;
 }
 
-struct SolveSmem {  // carve-up of the solve phase's dynamic shared memory
-    double *u1, *w1, *T1, *T2, *T3, *W, *dG, *Wu, *dth, *cm1, *ones, *A, *sc, *nodes, *sinn_s;
-    __device__ __forceinline__ SolveSmem(double *sm, int P, int Nc, int sum_nodes)
+struct SolveSmem {  // carve-up of the solve phase's scratch shared memory (after the tables)
+    double *u1, *w1, *T1, *T2, *T3, *W, *dG, *Wu, *A, *sc, *nodes;
+    __device__ __forceinline__ SolveSmem(double *sm, int P, int Nc)
     {
         u1 = sm; w1 = u1 + P; T1 = w1 + P; T2 = T1 + P; T3 = T2 + P; W = T3 + P; dG = W + P; Wu = dG + P;
-        dth = Wu + P; cm1 = dth + P; ones = cm1 + P; A = ones + P; sc = A + Nc; nodes = sc + 32;
-        sinn_s = nodes + sum_nodes;
+        A = Wu + P; sc = A + Nc; nodes = sc + 32;
     }
 };
-#define SOLVE_SMEM_DOUBLES(P, Nc, sum_nodes, sinn_smem) (11 * (P) + (Nc) + 32 + (sum_nodes) + ((sinn_smem) ? (Nc) * (P) : 0))
-#define SINN_SMEM_MAX 4096   // largest sin(n theta) table (doubles) kept in shared memory
+#define SOLVE_SCRATCH_DOUBLES(P, Nc, sum_nodes) (8 * (P) + (Nc) + 32 + (sum_nodes))
+#define SOLVE_SMEM_DOUBLES(P, Nc, sum_nodes, big) (TABLE_SMEM_DOUBLES(P, Nc, big) + SOLVE_SCRATCH_DOUBLES(P, Nc, sum_nodes))
 
 // Fold the phase-1 partials into u1, w1 (block-wide; ends with a barrier).
 __device__ __forceinline__ void fold_wake_on_foil(const SimDev &S, int n1, const SolveSmem &m)
@@ -277,22 +325,24 @@ __device__ __forceinline__ void fold_wake_on_foil(const SimDev &S, int n1, const
 // Fourier coefficients n0 .. n0+nq-1 of the downwash into A[]: A0 = -1/pi*trapz(W/Uinf), An = 2/pi*trapz(W/Uinf*
 // cos(n theta)) (LUDVM.py:694-695, :769-771).  Wu[j] = W[j] / Uinf (tabulated: the same division); row 0 of the
 // cos(n theta) table is cos(0) = 1.0 exactly, so A0's integrand W/Uinf * 1.0 needs no special case.  Block-wide.
-__device__ __forceinline__ void block_fourier(const SimDev &S, const SolveSmem &m, int n0, int nq, double *A)
+__device__ __forceinline__ void block_fourier(const SimDev &S, const StepTables &t, const SolveSmem &m, int n0, int nq,
+                                              double *A)
 {
-    block_trapz(m.Wu, 0, 0, S.cosn + (size_t)n0 * S.P, 0, S.P, m.dth, S.P, nq, m.nodes, S.sum_nodes, A + n0);
+    block_trapz(m.Wu, 0, 0, t.cosn + (size_t)n0 * S.P, 0, S.P, t.dth, S.P, nq, m.nodes, S.sum_nodes, A + n0);
     for (int n = n0 + threadIdx.x; n < n0 + nq; n += blockDim.x) A[n] = (n == 0 ? (-1 / PI_D) : (2 / PI_D)) * A[n];
     __syncthreads();
 }
 
 // Whole-block airfoil_downwash of the wake TEV[:nT] ++ LEV[:nL] ++ FREE (used by the Ramesh iterations):
 // fills W and Wu = W / Uinf.
-__device__ __noinline__ void cta_downwash(const SimDev &S, const Step &st, const Kin &k, int nT, int nL, const SolveSmem &m)
+__device__ __noinline__ void cta_downwash(const SimDev &S, const StepTables &t, const Step &st, const Kin &k, int nT, int nL,
+                                          const SolveSmem &m)
 {
     __syncthreads();  // circulation guesses written by thread 0 are visible
     phase_wake_on_foil(S, st, nT, nL, block_pool());
     fold_wake_on_foil(S, nT + nL + S.nfree, m);
     for (int j = threadIdx.x; j < S.P; j += blockDim.x) {
-        double w = downwash_at(S, k, m.u1, m.w1, j);
+        double w = downwash_at(S, t, k, m.u1, m.w1, j);
         m.W[j] = w;
         m.Wu[j] = w / S.Uinf;
     }
@@ -301,9 +351,9 @@ __device__ __noinline__ void cta_downwash(const SimDev &S, const Step &st, const
 
 // Kelvin residual of the Newton loops (LUDVM.py:697-699, :825-827).  Leaves A0 in sc[20], A1 in sc[21], the bound
 // circulation in sc[24]; returns the residual on every thread.
-__device__ __noinline__ double cta_kelvin_f(const SimDev &S, const Step &st, const SolveSmem &m)
+__device__ __noinline__ double cta_kelvin_f(const SimDev &S, const StepTables &t, const Step &st, const SolveSmem &m)
 {
-    block_fourier(S, m, 0, 2, m.sc + 20);
+    block_fourier(S, t, m, 0, 2, m.sc + 20);
     double sT = block_np_sum(S.wg, st.itev + 1, m.nodes, S.sum_nodes);
     double sL = block_np_sum(S.wg + S.nv, st.ilev + 1, m.nodes, S.sum_nodes);
     double cb = S.Uinf * S.chord * PI_D * (m.sc[20] + m.sc[21] / 2);
@@ -320,13 +370,16 @@ __device__ __noinline__ double cta_kelvin_f(const SimDev &S, const Step &st, con
 // needs are recomputed by every thread from shared operands (identical arithmetic) instead of being broadcast
 // through another barrier.
 // ---------------------------------------------------------------------------------------------------
+// `tab` = shared memory of the StepTables (staged here when stage_now, else already resident), `sm` = scratch.
 template <int METHOD>
-__device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const double *pre_sums)
+__device__ void phase_solve(const SimDev &S, const Step &st, double *tab, double *sm, const double *pre_sums,
+                            bool stage_now)
 {
     const int P = S.P, Nc = S.Nc, tid = threadIdx.x, nth = blockDim.x;
     const int lane8 = tid & 7, grp = tid >> 3, ngrp = nth >> 3;
     const int i = st.i, itev = st.itev, ilev = st.ilev, nv = S.nv;
-    const SolveSmem m(sm, P, Nc, S.sum_nodes);
+    const StepTables t(tab, S);
+    const SolveSmem m(sm, P, Nc);
     double *const T1 = m.T1, *const T2 = m.T2, *const T3 = m.T3, *const W = m.W, *const Wu = m.Wu, *const dG = m.dG;
     double *const A = m.A, *const sc = m.sc;
     // sc[]: 0 xt, 1 zt, 4 I1, 5 I2, 6 trapz(T1), 7 trapz(T2), 8 I3, 9 trapz(T3), 10 gtev, 11 glev, 13 xl, 14 zl,
@@ -352,16 +405,7 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
         }
         lc0 = *S.lespcrit_cur;
     }
-    if (S.sinn_smem) {  // sin(n theta) [Nc,P] -> shared memory, asynchronously (consumed by the bound-vortex phase)
-        for (int idx = tid; idx < Nc * P; idx += nth)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(m.sinn_s + idx)), "l"(S.sinn + idx));
-        asm volatile("cp.async.commit_group;");
-    }
-    for (int j = tid; j < P; j += nth) {
-        m.dth[j] = (j + 1 < P) ? S.theta_p[j + 1] - S.theta_p[j] : 0.0;
-        m.cm1[j] = S.cos_tp[j] - 1;
-        m.ones[j] = 1.0;
-    }
+    if (stage_now) stage_tables(S, t);
     // TEV placement (LUDVM.py:672-681)
     if (tid == 0) {
         double xt, zt;
@@ -399,13 +443,14 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
         }
         TRACE(4);
         for (int idx = tid; idx < 2 * P; idx += nth) {
-            if (idx < P) T1[idx] = downwash_at(S, k, m.u1, m.w1, idx);
-            else T2[idx - P] = unit_T(S, k.xa[idx - P], k.za[idx - P], sc[0], sc[1], ca, sa, S.detadx_p[idx - P]);
+            if (idx < P) T1[idx] = downwash_at(S, t, k, m.u1, m.w1, idx);
+            else T2[idx - P] = unit_T(S, k.xa[idx - P], k.za[idx - P], sc[0], sc[1], ca, sa, t.detadx[idx - P]);
         }
         TRACE(5);
         // I1, I2 (LUDVM.py:756-757) -> sc[4], sc[5] and -- needed only if a LEV is shed, but free here -- the raw
         // integrals of J1, J2 (LUDVM.py:940-941) -> sc[6], sc[7]   (T2 = T1 + P, ones = cm1 + P in the layout)
-        block_trapz(T1, 1, P, m.cm1, 1, P, m.dth, P, 4, m.nodes, S.sum_nodes, sc + 4);
+        if (stage_now) tables_wait();   // the barrier inside block_trapz publishes the async copies
+        block_trapz(T1, 1, P, t.cm1, 1, P, t.dth, P, 4, m.nodes, S.sum_nodes, sc + 4);
         TRACE(6);
         const double I1 = sc[4], I2 = sc[5];
         const double gtev = -(I1 + sT + sL + S.sum_free - S.ic) / (1 + I2);  // LUDVM.py:758-760
@@ -419,7 +464,7 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
             Wu[j] = w / Uinf;
         }
         TRACE(7);
-        block_fourier(S, m, 0, Nc, A);                                        // LUDVM.py:769-773
+        block_fourier(S, t, m, 0, Nc, A);                                        // LUDVM.py:769-773
         for (int n = tid; n < Nc; n += nth) F[Nc + n] = (A[n] - Fprev[n]) / dt;
         TRACE(8);
     } else {
@@ -428,16 +473,17 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
             sc[26] = 1.0;   // f
             sc[27] = -1.0;  // shed_vortex_gamma
         }
+        if (stage_now) tables_wait();
         __syncthreads();
         int niter = 1;
         while (fabs(sc[26]) > S.maxerror && niter < S.maxiter) {
             double shed = sc[27];
             if (tid == 0) S.wg[itev] = shed;
-            cta_downwash(S, st, k, itev + 1, ilev + 1, m);
-            double f = cta_kelvin_f(S, st, m);
+            cta_downwash(S, t, st, k, itev + 1, ilev + 1, m);
+            double f = cta_kelvin_f(S, t, st, m);
             if (tid == 0) S.wg[itev] = shed + S.epsilon;
-            cta_downwash(S, st, k, itev + 1, ilev + 1, m);
-            double fdelta = cta_kelvin_f(S, st, m);
+            cta_downwash(S, t, st, k, itev + 1, ilev + 1, m);
+            double fdelta = cta_kelvin_f(S, t, st, m);
             if (tid == 0) {
                 double fprime = (fdelta - f) / S.epsilon;
                 sc[27] = shed - f / fprime;
@@ -447,8 +493,8 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
             __syncthreads();
             niter++;
         }
-        cta_downwash(S, st, k, itev + 1, ilev + 1, m);
-        block_fourier(S, m, 0, Nc, A);
+        cta_downwash(S, t, st, k, itev + 1, ilev + 1, m);
+        block_fourier(S, t, m, 0, Nc, A);
         for (int n = tid; n < Nc; n += nth) F[Nc + n] = (A[n] - Fprev[n]) / dt;
         if (tid == 0) {
             sc[10] = S.wg[itev];
@@ -468,7 +514,7 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
         }
         if (!ramesh) {
             // Faure 2x2 linear system (LUDVM.py:916-961); T1, T2, I1, I2 are unchanged recomputations there
-            for (int j = tid; j < P; j += nth) T3[j] = unit_T(S, k.xa[j], k.za[j], xl, zl, ca, sa, S.detadx_p[j]);
+            for (int j = tid; j < P; j += nth) T3[j] = unit_T(S, k.xa[j], k.za[j], xl, zl, ca, sa, t.detadx[j]);
             __syncthreads();   // every thread has evaluated `shed` and read lev_shed[i-1]
             if (tid == 0) {
                 sc[13] = xl;
@@ -476,7 +522,7 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
                 sc[15] = (A[0] < 0) ? -fabs(sc[15]) : fabs(sc[15]);
                 S.lev_shed[i] = (double)ilev;
             }
-            block_trapz(T3, 0, 0, m.cm1, 0, P, m.dth, P, 2, m.nodes, S.sum_nodes, sc + 8);  // I3, raw J3 -> sc[8], sc[9]
+            block_trapz(T3, 0, 0, t.cm1, 0, P, t.dth, P, 2, m.nodes, S.sum_nodes, sc + 8);  // I3, raw J3 -> sc[8], sc[9]
             // LUDVM.py:945-959, on every thread
             const double I1 = sc[4], I2 = sc[5], I3 = sc[8];
             const double J1 = (-1 / PI_D) * sc[6], J2 = (-1 / PI_D) * sc[7], J3 = (-1 / PI_D) * sc[9];
@@ -495,7 +541,7 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
                 sc[16] = I1 + x0 * I2 + x1 * I3;
                 A[0] = J1 + x0 * J2 + x1 * J3;
             }
-            block_fourier(S, m, 1, Nc - 1, A);  // LUDVM.py:960-961
+            block_fourier(S, t, m, 1, Nc - 1, A);  // LUDVM.py:960-961
         } else {
             __syncthreads();   // every thread has evaluated `shed` and read lev_shed[i-1]
             if (tid == 0) {
@@ -516,17 +562,17 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
             while ((fabs(sc[26]) > S.maxerror || fabs(sc[27]) > S.maxerror) && niter < S.maxiter) {
                 double tg = sc[28], lg = sc[29];
                 if (tid == 0) { S.wg[itev] = tg; S.wg[nv + ilev] = lg; }
-                cta_downwash(S, st, k, itev + 1, ilev + 1, m);
-                double f1 = cta_kelvin_f(S, st, m);
+                cta_downwash(S, t, st, k, itev + 1, ilev + 1, m);
+                double f1 = cta_kelvin_f(S, t, st, m);
                 double cbound = sc[24], f2 = sc[15] - sc[20];
                 __syncthreads();
                 if (tid == 0) { S.wg[itev] = tg + S.epsilon; S.wg[nv + ilev] = lg; }
-                cta_downwash(S, st, k, itev + 1, ilev + 1, m);
-                double f1dT = cta_kelvin_f(S, st, m), f2dT = sc[15] - sc[20];
+                cta_downwash(S, t, st, k, itev + 1, ilev + 1, m);
+                double f1dT = cta_kelvin_f(S, t, st, m), f2dT = sc[15] - sc[20];
                 __syncthreads();
                 if (tid == 0) { S.wg[itev] = tg; S.wg[nv + ilev] = lg + S.epsilon; }
-                cta_downwash(S, st, k, itev + 1, ilev + 1, m);
-                double f1dL = cta_kelvin_f(S, st, m), f2dL = sc[15] - sc[20];
+                cta_downwash(S, t, st, k, itev + 1, ilev + 1, m);
+                double f1dL = cta_kelvin_f(S, t, st, m), f2dL = sc[15] - sc[20];
                 __syncthreads();
                 if (tid == 0) {
                     double eps = S.epsilon, x0, x1;
@@ -542,8 +588,8 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
                 __syncthreads();
                 niter++;
             }
-            cta_downwash(S, st, k, itev + 1, ilev + 1, m);
-            block_fourier(S, m, 0, Nc, A);  // LUDVM.py:902-909
+            cta_downwash(S, t, st, k, itev + 1, ilev + 1, m);
+            block_fourier(S, t, m, 0, Nc, A);  // LUDVM.py:902-909
             if (tid == 0) {
                 sc[10] = S.wg[itev];
                 sc[11] = S.wg[nv + ilev];
@@ -572,19 +618,14 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *sm, const d
     for (int n = tid; n < Nc; n += nth) F[n] = A[n];
     // bound-vortex distribution (LUDVM.py:986-1010)
     const size_t arow = (size_t)itev * S.af_stride;
-    const double *sinn = S.sinn;
-    if (S.sinn_smem) {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        __syncthreads();
-        sinn = m.sinn_s;
-    }
+    const double *sinn = t.sinn;
     for (int j = tid; j < P; j += nth) {
         double term2 = 0;
 #pragma unroll 4
         for (int n = 1; n < Nc; n++) term2 = A[n] * sinn[(size_t)n * P + j] + term2;
-        double term1 = A[0] * (1 + S.cos_tp[j]) / S.sin_tp[j];
+        double term1 = A[0] * (1 + t.costp[j]) / t.sintp[j];
         double gamma = 2 * Uinf * (term1 + term2);
-        double dg = gamma * chord / 2 * S.sin_tp[j] * S.dtheta[j];
+        double dg = gamma * chord / 2 * t.sintp[j] * t.dtheta[j];
         dG[j] = dg;
         S.g_airfoil[arow + j] = dg;
         S.gamma_airfoil[arow + j] = gamma;
@@ -643,25 +684,35 @@ __device__ __forceinline__ int conv_fold(const SimDev &S, const Step &st, int ti
     return S.mode == LUDVM_EXACT_F64 ? sim_depth(nw, S.P + nw, S.target_warps) : sim_chunks(nw, S.P + nw, S.target_warps);
 }
 
-__device__ void phase_finish_loads(const SimDev &S, const Step &st, double *sm, int tiled_chunks, int cap)  // LUDVM.py:1035-1090
+// `tab` = shared memory of resident StepTables, or nullptr: then the three tables needed here are built in `sm`.
+__device__ void phase_finish_loads(const SimDev &S, const Step &st, double *tab, double *sm, int tiled_chunks, int cap)  // LUDVM.py:1035-1090
 {
     const int P = S.P, i = st.i, itev = st.itev, tid = threadIdx.x, nth = blockDim.x;
     const int nrows = P + st.itev + 1 + st.ilev + 1 + S.nfree;
     const bool exact = S.mode == LUDVM_EXACT_F64;
     const int fold = conv_fold(S, st, tiled_chunks);
-    double *ug = sm, *ugx = ug + P, *dxp = ugx + P, *ones = dxp + P, *sc = ones + P, *stage = sc + 8;
+    double *ug = sm, *ugx = ug + P, *sc = ugx + P, *stage = sc + 8;
+    const double *dxp, *ones, *xp;
     const double ca = S.cos_a[i], sa = S.sin_a[i], hd = S.h_dot[i];
     const double *gam = S.gamma_airfoil + (size_t)itev * S.af_stride;
-    for (int j = tid; j < P; j += nth) {
-        dxp[j] = (j + 1 < P) ? S.x_p[j + 1] - S.x_p[j] : 0.0;
-        ones[j] = 1.0;
+    if (tab) {
+        const StepTables t(tab, S);
+        dxp = t.dxp; ones = t.ones; xp = t.xp;
+    } else {
+        double *d = stage + cap, *o = d + P, *x = o + P;
+        for (int j = tid; j < P; j += nth) {
+            d[j] = (j + 1 < P) ? S.x_p[j + 1] - S.x_p[j] : 0.0;
+            o[j] = 1.0;
+            x[j] = S.x_p[j];
+        }
+        dxp = d; ones = o; xp = x;
     }
     block_fold(S.pb_u, S.pb_w, nrows, P, fold, exact, stage, cap, ug, ugx);  // wake velocity at the gamma points
     for (int j = tid; j < P; j += nth) {
         double u1 = ug[j], w1 = ugx[j];
         double u = u1 * ca - w1 * sa;
         ug[j] = u * gam[j];
-        ugx[j] = u * gam[j] * S.x_p[j];
+        ugx[j] = u * gam[j] * xp[j];
     }
     block_trapz(ug, 1, P, ones, 0, 0, dxp, P, 2, stage, cap, sc);   // trapz(ug, x_p), trapz(ugx, x_p)
     if (tid == 0) {
@@ -764,7 +815,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS) k_solve(SimDev S, int s)
     TRACE(20);
     if (!step_begin(S, s, st)) return;
     TRACE(21);
-    phase_solve<LUDVM_METHOD_FAURE>(S, st, sm, S.pre_sums);
+    phase_solve<LUDVM_METHOD_FAURE>(S, st, sm, sm + TABLE_SMEM_DOUBLES(S.P, S.Nc, S.sinn_smem), S.pre_sums, true);
     __syncthreads();
     TRACE(22);
 }
@@ -810,7 +861,7 @@ __global__ void __launch_bounds__(256) k_finish(SimDev S, int s, int tiled_chunk
     Step st;
     if (!step_begin(S, s, st)) return;
     if (blockIdx.x == 0) {
-        phase_finish_loads(S, st, sm, tiled_chunks, FINISH_STAGE);
+        phase_finish_loads(S, st, nullptr, sm, tiled_chunks, FINISH_STAGE);
         return;
     }
     if (blockIdx.x == 1) {
@@ -825,6 +876,111 @@ __global__ void k_advance(SimDev S, int k)
 {
     long long v = S.counters[0] + k;
     S.counters[0] = v > S.nt - 1 ? S.nt - 1 : v;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cooperative path: one persistent grid (one CTA per SM) runs many steps of ONE simulation with grid-wide barriers
+// between the phases.  For small wakes a step is latency-bound: four dependent launches per step cost more than the
+// arithmetic, and every launch starts with cold instruction and data caches.  Here the phases are the same device
+// functions over the same warp pools, the solve CTA stays on its SM (warm caches), and a phase boundary is one
+// arrive + spin on a counter in L2.  Launched with cudaLaunchCooperativeKernel (co-residency guaranteed).
+// ---------------------------------------------------------------------------------------------------
+#define COOP_SPIN_LIMIT (1u << 27)   // ~1 s of polling: a lost CTA turns into an error flag, not a hung GPU
+
+// Two-level grid barrier on monotonically increasing counters (all zeroed by the host before the launch): CTAs arrive
+// on the counter of their group of COOP_GROUP CTAs (distinct L2 lines, so the groups' atomics proceed in parallel);
+// the last arriver of a group arrives on the root counter; the last arriver there publishes the barrier index in a
+// flag word that every CTA polls with plain volatile loads.  A single counter would serialise 148 atomics on one
+// address (~27 cycles each, measured ~2.5-5 us per barrier); this chain is 16 + 10 atomics deep.
+// Memory protocol as in cooperative_groups::grid_group::sync(): block barrier, fence, arrive, poll, fence, block barrier.
+#define COOP_GROUP 16
+#define COOP_BAR_WORDS (16 * 20)   // root, flag and up to 16 group counters, one 128-byte line each
+__device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned long long &k, long long *counters)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        k += 1;
+        const unsigned nb = gridDim.x, g = blockIdx.x / COOP_GROUP, ng = (nb + COOP_GROUP - 1) / COOP_GROUP;
+        const unsigned gsize = min((unsigned)COOP_GROUP, nb - g * COOP_GROUP);
+        unsigned long long *root = bar, *flag = bar + 16, *grp = bar + 32 + 16 * g;
+        __threadfence();
+        if (atomicAdd(grp, 1ULL) + 1 == k * gsize) {
+            __threadfence();
+            if (atomicAdd(root, 1ULL) + 1 == k * ng) {
+                __threadfence();
+                *(volatile unsigned long long *)flag = k;
+            }
+        }
+        unsigned spins = 0;
+        while (*(volatile unsigned long long *)flag < k) {
+            if (++spins > COOP_SPIN_LIMIT) {
+                counters[3] = 1;  // error flag
+                break;
+            }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 1) k_sim_coop(SimDev S, int nsteps, unsigned long long *bar)
+{
+    extern __shared__ double sm[];
+    unsigned long long epoch = 0;
+    const int first = (int)S.counters[0] + 1;
+    const int last = min(S.nt - 1, first + nsteps - 1);
+    const int nb = gridDim.x;
+    double *const tab = sm, *const scr = sm + TABLE_SMEM_DOUBLES(S.P, S.Nc, S.sinn_smem);
+    if (blockIdx.x == 0) {   // the solve / loads CTA keeps the constant tables in shared memory for the whole launch
+        stage_tables(S, StepTables(tab, S));
+        tables_wait();
+    }
+    __syncthreads();
+#ifdef LUDVM_TRACE
+#define COOP_T(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long t__ = clock64(); acc[k] += t__ - tlast; tlast = t__; } } while (0)
+    long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
+#else
+#define COOP_T(k) do { } while (0)
+#endif
+    for (int i = first; i <= last; i++) {
+        Step st{i, i - 1, ((volatile int *)S.ilev_arr)[i]};
+        // phase 1: the wake on the gamma points; the last CTA evaluates the two circulation sums instead
+        if (blockIdx.x == nb - 1) {
+            double sT = block_np_sum(S.wg, st.itev, scr, S.sum_nodes);
+            double sL = block_np_sum(S.wg + S.nv, st.ilev, scr, S.sum_nodes);
+            if (threadIdx.x == 0) {
+                S.pre_sums[0] = sT;
+                S.pre_sums[1] = sL;
+            }
+        } else {
+            Pool pl = grid_pool();
+            pl.nwarps -= blockDim.x >> 5;
+            pl.nth -= blockDim.x;
+            phase_wake_on_foil(S, st, st.itev, st.ilev, pl);
+        }
+        COOP_T(0);
+        grid_barrier(bar, epoch, S.counters);
+        COOP_T(1);
+        if (blockIdx.x == 0) phase_solve<LUDVM_METHOD_FAURE>(S, st, tab, scr, S.pre_sums, false);
+        COOP_T(2);
+        grid_barrier(bar, epoch, S.counters);
+        COOP_T(3);
+        phase_conv_partials(S, st, grid_pool());
+        COOP_T(4);
+        grid_barrier(bar, epoch, S.counters);
+        COOP_T(5);
+        if (blockIdx.x == 0) phase_finish_loads(S, st, tab, scr, 0, S.sum_nodes);
+        else if (blockIdx.x == 1) phase_gamma_cumsum(S, st, threadIdx.x, blockDim.x);
+        else phase_finish_update(S, st, (long)(blockIdx.x - 2) * blockDim.x + threadIdx.x, (long)(nb - 2) * blockDim.x, 0);
+        COOP_T(6);
+        grid_barrier(bar, epoch, S.counters);
+        COOP_T(7);
+    }
+#ifdef LUDVM_TRACE
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int q = 0; q < 8; q++) g_trace[40 + q] = acc[q];
+#endif
+    if (blockIdx.x == 0 && threadIdx.x == 0) S.counters[0] = last;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -864,6 +1020,10 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1) k_sim_cta(con
         }
         __syncthreads();
         const SimDev &S = s_sim;
+        double *const tab = sm, *const scr = sm + TABLE_SMEM_DOUBLES(S.P, S.Nc, S.sinn_smem);
+        stage_tables(S, StepTables(tab, S));   // once per case
+        tables_wait();
+        __syncthreads();
         const int first = (int)S.counters[0] + 1;
         const int last = min(S.nt - 1, first + nsteps - 1);
 #ifdef LUDVM_TRACE
@@ -881,13 +1041,13 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1) k_sim_cta(con
                 __syncthreads();
             }
             CTA_T(0);
-            phase_solve<METHOD>(S, st, sm, nullptr);
+            phase_solve<METHOD>(S, st, tab, scr, nullptr, false);
             __syncthreads();
             CTA_T(1);
             cta_conv_partials(S, st);
             __syncthreads();
             CTA_T(2);
-            phase_finish_loads(S, st, sm, 0, S.sum_nodes);
+            phase_finish_loads(S, st, tab, scr, 0, S.sum_nodes);
             CTA_T(3);
             cta_finish_update(S, st);
             phase_gamma_cumsum(S, st, threadIdx.x, blockDim.x);
@@ -1038,6 +1198,8 @@ struct ludvm_sim {
     int K = 50;
     std::map<int, cudaGraphExec_t> graphs;  // (bracket, length) -> instantiated graph
     size_t solve_smem = 0, finish_smem = 0;
+    unsigned long long *d_bar = nullptr;  // grid-barrier counter of the cooperative path
+    int coop_grid = 0;                    // CTAs of the cooperative kernel (0: path not available on this device)
     cudaStream_t cap_stream = nullptr;  // private stream used only to record graphs (the context's stream may be
                                         // the legacy default stream, which cannot be captured)
 };
@@ -1218,15 +1380,28 @@ LUDVM_API int ludvm_sim_create(ludvm_ctx *ctx, const ludvm_sim_params *p, const 
     real.base = (char *)base;
     layout_case(s->d, *p, dt, real, target, sum_nodes, false);
     void *dc;
-    TRY(dev_malloc(s->allocs, sizeof(SimDev) + 512, &dc));
+    TRY(dev_malloc(s->allocs, sizeof(SimDev) + 1024, &dc));
     s->d_case = (SimDev *)dc;
     s->d_next = (int *)((char *)dc + ((sizeof(SimDev) + 255) & ~(size_t)255));
+    {
+        void *db;
+        TRY(dev_malloc(s->allocs, COOP_BAR_WORDS * sizeof(unsigned long long), &db));
+        s->d_bar = (unsigned long long *)db;
+    }
     CU(cudaMemcpyAsync(s->d_case, &s->d, sizeof(SimDev), cudaMemcpyHostToDevice, ctx->stream));
     k_case_init<<<1, 256, 0, ctx->stream>>>(s->d_case, 1);
     ctx->launches++;
     s->solve_smem = solve_smem_bytes(s->d);
-    s->finish_smem = (4 * (size_t)p->P + 8 + (size_t)std::max<long>(FINISH_STAGE, 2 * p->P)) * sizeof(double);
+    s->finish_smem = (5 * (size_t)p->P + 8 + (size_t)std::max<long>(FINISH_STAGE, 2 * p->P)) * sizeof(double);
     TRY(set_smem_limits(s->solve_smem, s->finish_smem));
+    {   // cooperative path: needs cooperative-launch support and one resident CTA per SM
+        int coop = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+        if (coop && !cta && cudaFuncSetAttribute(k_sim_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->solve_smem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_coop, 256, s->solve_smem) == cudaSuccess && per_sm >= 1)
+            s->coop_grid = ctx->sm_count;
+        cudaGetLastError();
+    }
     CU(cudaStreamSynchronize(ctx->stream));  // the host tables may be freed by the caller after return
 #undef TRY
 #undef CU
@@ -1248,6 +1423,23 @@ LUDVM_API int ludvm_sim_run(ludvm_sim *s, long nsteps)
         s->ctx->launches++;
         s->steps_enqueued += todo;
         return LUDVM_OK;
+    }
+    // small wakes: the persistent cooperative kernel, all of those steps in one launch
+    if (s->coop_grid >= 3 && !getenv("LUDVM_NO_COOP")) {
+        const long last_small = (SIM_COOP_MAX_WAKE - 2 - (long)s->p.nfree) / 2;   // wake after step i <= 2 i + 2 + nfree
+        long k = std::min(todo, last_small - s->steps_enqueued);
+        if (k > 0) {
+            SimDev dc = s->d;
+            dc.target_warps = s->coop_grid * 8;   // one wave of warp tasks over the resident grid
+            int ki = (int)k;
+            unsigned long long *bar = s->d_bar;
+            void *args[] = {&dc, &ki, &bar};
+            CUDA_TRY(cudaMemsetAsync(s->d_bar, 0, COOP_BAR_WORDS * sizeof(unsigned long long), s->ctx->stream));
+            CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_sim_coop, dim3(s->coop_grid), dim3(256), args, s->solve_smem, s->ctx->stream));
+            s->ctx->launches++;
+            s->steps_enqueued += k;
+            todo -= k;
+        }
     }
     // graphs of K unrolled steps (a shorter one for a tail), cached per (wake-size bracket, length)
     while (todo > 0) {

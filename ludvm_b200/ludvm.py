@@ -329,6 +329,8 @@ class LUDVM:
         self.BC = np.zeros([nv, self.Npoints])
         cnt = self._fetch('COUNTERS', 4, np.int64)
         self.steps_done, self.itev, self.ilev = int(cnt[0]), int(cnt[1]), int(cnt[2])
+        if cnt[3] != 0:
+            raise _lib.LudvmError("device time loop reported error flags %d (grid barrier timed out)" % int(cnt[3]))
 
     def compute_coefficients(self):
         """Force and moment coefficients (LUDVM.py:1173-1184)."""

@@ -1,0 +1,19 @@
+"""Device time of the README-size time loop: persistent cooperative kernel vs CUDA-graph replay (LUDVM_NO_COOP=1)."""
+import ctypes as C, json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ludvm_b200 import LUDVM, _lib
+L = _lib.load()
+README = dict(t0=0, tf=20, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012")
+for label, env in (("coop", None), ("graph", "1")):
+    if env: os.environ["LUDVM_NO_COOP"] = env
+    else: os.environ.pop("LUDVM_NO_COOP", None)
+    for mode in ("exact", "fast"):
+        best = 1e9
+        for rep in range(4):
+            s = LUDVM(**README, verbose=False, run=False, mode=mode, store_history=False, steps_per_graph=400)
+            s.time_loop(nsteps=0)
+            s.ctx.synchronize()
+            t = time.perf_counter(); _lib.check(L.ludvm_sim_run(s._sim, 400)); s.ctx.synchronize(); dt = time.perf_counter() - t
+            if rep: best = min(best, dt)
+            s.close()
+        print(json.dumps({"path": label, "mode": mode, "us_per_step": best / 400 * 1e6, "steps_per_s_device": 400 / best}), flush=True)
