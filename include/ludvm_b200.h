@@ -125,7 +125,9 @@ typedef struct {
     int64_t nfree;     /* n_freevort >= 1                      LUDVM.py:268-277 */
     int32_t method;    /* LUDVM_METHOD_*                       LUDVM.py:252     */
     int32_t mode;      /* LUDVM_EXACT_F64 | LUDVM_FAST_F64 */
-    int32_t store_history; /* 1: keep path['TEV'/'LEV'/'FREE'] [nt,2,*] on the device (LUDVM.py:615-617) */
+    int32_t store_history; /* 0: only the current positions exist; 1: keep path['TEV'/'LEV'/'FREE'] [nt,2,*] on the
+                              device (LUDVM.py:615-617); k > 1: strided snapshots -- rows of steps i % k == 0 of
+                              path['TEV'/'LEV'] ([(nt-1)/k + 1, 2, nt-1]; path['FREE'] stays [nt,2,nfree]) */
     int32_t steps_per_graph; /* K unrolled steps per captured graph; <= 0: library default */
     double dt, Uinf, chord, rho, piv, lespcrit;
     double vc4;        /* v_core**4                            LUDVM.py:260, :565 */
@@ -160,8 +162,8 @@ int ludvm_sim_steps_done(ludvm_sim *sim, long *out);
 int ludvm_sim_profile_steps(ludvm_sim *sim, long nsteps, double *ms_out);
 
 enum {
-    LUDVM_F_PATH_TEV = 0,  /* [nt,2,nt-1]  needs store_history  LUDVM.py:615 */
-    LUDVM_F_PATH_LEV = 1,  /* [nt,2,nt-1]                       LUDVM.py:616 */
+    LUDVM_F_PATH_TEV = 0,  /* [(nt-1)/k+1,2,nt-1]  needs store_history = k >= 1  LUDVM.py:615 */
+    LUDVM_F_PATH_LEV = 1,  /* [(nt-1)/k+1,2,nt-1]                                LUDVM.py:616 */
     LUDVM_F_PATH_FREE = 2, /* [nt,2,nfree]                      LUDVM.py:617 */
     LUDVM_F_G_TEV = 3,     /* [nt-1]                            LUDVM.py:620 */
     LUDVM_F_G_LEV = 4,     /* [nt-1]                            LUDVM.py:621 */

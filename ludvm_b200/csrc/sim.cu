@@ -50,7 +50,7 @@ __device__ long long g_trace[64];
 #endif
 
 struct SimDev {
-    int nt, P, Nc, nfree, nv, method, mode, store_history;
+    int nt, P, Nc, nfree, nv, method, mode, store_history;   // store_history = k >= 1: TEV/LEV rows of steps i % k == 0 are kept
     int target_warps;   // parallelism target used to pick split depths (same value in every phase of a case)
     int sum_nodes;      // doubles of shared-memory staging (block_np_sum tree nodes, block_fold / block_trapz batches)
     int sinn_smem;      // 1: the sin(n theta) table [Nc,P] is copied to shared memory at the head of the solve phase
@@ -767,13 +767,17 @@ __device__ __forceinline__ void phase_finish_update(const SimDev &S, const Step 
         double zn = S.wz[p] + dt * (ww + wf);
         S.wx[p] = xn;
         S.wz[p] = zn;
-        if (S.store_history) {
+        if (S.store_history) {   // snapshot row i / k of the strided TEV / LEV history; the FREE history is kept in full
             double *hx, *hz;
+            const bool snap = (i % S.store_history) == 0;
+            const size_t hrow = (size_t)(i / S.store_history);
             if (r < nT) {
-                hx = S.path_tev + ((size_t)i * 2) * nv + r;
+                if (!snap) continue;
+                hx = S.path_tev + (hrow * 2) * nv + r;
                 hz = hx + nv;
             } else if (r < nT + nL) {
-                hx = S.path_lev + ((size_t)i * 2) * nv + (r - nT);
+                if (!snap) continue;
+                hx = S.path_lev + (hrow * 2) * nv + (r - nT);
                 hz = hx + nv;
             } else {
                 hx = S.path_free + ((size_t)i * 2) * S.nfree + (r - nT - nL);
@@ -1138,7 +1142,7 @@ static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t
 {
     const size_t nt = p.nt, P = p.P, Nc = p.Nc, nf = p.nfree, nv = nt - 1, nstate = 2 * nv + nf;
     D.nt = (int)nt; D.P = (int)P; D.Nc = (int)Nc; D.nfree = (int)nf; D.nv = (int)nv;
-    D.method = p.method; D.mode = p.mode; D.store_history = compact ? 0 : p.store_history;
+    D.method = p.method; D.mode = p.mode; D.store_history = compact ? 0 : std::max(0, p.store_history);
     D.target_warps = target_warps; D.sum_nodes = sum_nodes;
     D.sinn_smem = Nc * P <= SINN_SMEM_MAX ? 1 : 0;
     D.af_stride = compact ? 0 : (int)P;
@@ -1161,8 +1165,9 @@ static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t
     D.Fn = a.take<double>(nt); D.Fs = a.take<double>(nt); D.L = a.take<double>(nt); D.D = a.take<double>(nt);
     D.T = a.take<double>(nt); D.M = a.take<double>(nt);
     if (D.store_history) {
-        D.path_tev = a.take<double>(nt * 2 * nv);
-        D.path_lev = a.take<double>(nt * 2 * nv);
+        const size_t hrows = (nt - 1) / D.store_history + 1;
+        D.path_tev = a.take<double>(hrows * 2 * nv);
+        D.path_lev = a.take<double>(hrows * 2 * nv);
         D.path_free = a.take<double>(nt * 2 * nf);
     } else {
         D.path_tev = D.path_lev = D.path_free = nullptr;
@@ -1523,8 +1528,8 @@ static int field_info(ludvm_sim *s, int field, const void **ptr, size_t *bytes)
     const SimDev &D = s->d;
     const size_t nt = D.nt, nv = D.nv, P = D.P, Nc = D.Nc, nf = D.nfree, d8 = sizeof(double);
     switch (field) {
-    case LUDVM_F_PATH_TEV: *ptr = D.path_tev; *bytes = nt * 2 * nv * d8; break;
-    case LUDVM_F_PATH_LEV: *ptr = D.path_lev; *bytes = nt * 2 * nv * d8; break;
+    case LUDVM_F_PATH_TEV: *ptr = D.path_tev; *bytes = ((nt - 1) / std::max(1, D.store_history) + 1) * 2 * nv * d8; break;
+    case LUDVM_F_PATH_LEV: *ptr = D.path_lev; *bytes = ((nt - 1) / std::max(1, D.store_history) + 1) * 2 * nv * d8; break;
     case LUDVM_F_PATH_FREE: *ptr = D.path_free; *bytes = nt * 2 * nf * d8; break;
     case LUDVM_F_G_TEV: *ptr = D.wg; *bytes = nv * d8; break;
     case LUDVM_F_G_LEV: *ptr = D.wg + nv; *bytes = nv * d8; break;

@@ -86,7 +86,11 @@ class LUDVM:
         # device options
         if mode not in ("exact", "fast"):
             raise ValueError("mode must be 'exact' or 'fast'")
-        self.mode, self.device, self.store_history = mode, device, bool(store_history)
+        # store_history: True / 1 = the reference's full [nt,2,nt-1] vortex paths; False / 0 = latest positions only;
+        # k > 1 = strided snapshots (rows of steps i % k == 0), the O(nt^2) history is the memory wall at dt=2e-3, tf=40
+        self.mode, self.device, self.store_history = mode, device, int(store_history)
+        if self.store_history < 0:
+            raise ValueError('store_history must be >= 0')
         self.steps_per_graph = int(steps_per_graph)
         self._ctx = ctx
         self._sim = None
@@ -276,7 +280,7 @@ class LUDVM:
             if name in tb:
                 setattr(p, name, tb[name])
         p.mode = _lib.MODES[self.mode]
-        p.store_history = 1 if self.store_history else 0
+        p.store_history = self.store_history
         p.steps_per_graph = self.steps_per_graph
         t = SimTables()
         keep = []
@@ -315,9 +319,11 @@ class LUDVM:
                             'gamma_airfoil': fz('GAMMA_AIRFOIL', (nv, P)),
                             'Gamma_airfoil': fz('GAMMA_INT_AIRFOIL', (nv, P)), 'IC': self._tables['ic']}
         if self.store_history:
-            self.path['TEV'] = fz('PATH_TEV', (nt, 2, nv))
-            self.path['LEV'] = fz('PATH_LEV', (nt, 2, nv))
+            hrows = (nt - 1) // self.store_history + 1
+            self.path['TEV'] = fz('PATH_TEV', (hrows, 2, nv))
+            self.path['LEV'] = fz('PATH_LEV', (hrows, 2, nv))
             self.path['FREE'] = fz('PATH_FREE', (nt, 2, nf))
+            self.history_steps = np.arange(hrows) * self.store_history   # time index of each TEV/LEV path row
         else:   # only the latest positions exist (the O(nt^2) history is the memory wall at dt=2e-3, tf=40)
             self.path['TEV_last'] = fz('CUR_TEV', (2, nv))
             self.path['LEV_last'] = fz('CUR_LEV', (2, nv))
@@ -363,12 +369,16 @@ class LUDVM:
                                                       self.path['FREE'][0, 1], None, None, None, vc4, x1, z1,
                                                       mode=self.mode, ctx=self.ctx)
             else:             # index conventions of LUDVM.py:1209-1217 kept
+                if (itev - 1) % self.store_history:
+                    raise ValueError("flowfield step %d needs path row %d, which the strided history (every %d steps) "
+                                     "does not hold" % (itev, itev - 1, self.store_history))
+                hrow = (itev - 1) // self.store_history
                 ilev = int(self.LEV_shed[itev])
                 g = ap(ap(self.circulation['TEV'][:itev + 1], self.circulation['LEV'][:ilev + 1]),
                        self.circulation['FREE'])
-                xw = ap(ap(self.path['TEV'][itev - 1, 0, :itev + 1], self.path['LEV'][itev - 1, 0, :ilev + 1]),
+                xw = ap(ap(self.path['TEV'][hrow, 0, :itev + 1], self.path['LEV'][hrow, 0, :ilev + 1]),
                         self.path['FREE'][itev, 0])
-                zw = ap(ap(self.path['TEV'][itev - 1, 1, :itev + 1], self.path['LEV'][itev - 1, 1, :ilev + 1]),
+                zw = ap(ap(self.path['TEV'][hrow, 1, :itev + 1], self.path['LEV'][hrow, 1, :ilev + 1]),
                         self.path['FREE'][itev, 1])
                 gp = self.path['airfoil_gamma_points'][itev - 1]
                 u[ii], w[ii] = ops.flowfield_velocity(g, xw, zw, self.circulation['airfoil'][itev - 1], gp[0], gp[1],

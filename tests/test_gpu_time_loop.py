@@ -125,3 +125,40 @@ def test_no_history_mode():
     assert "TEV" not in s.path
     last = g["path_TEV_rows"][-1]   # row 200 = final positions
     assert biteq(s.path["TEV_last"], last)
+
+
+def test_strided_history_snapshots(oracle):
+    """store_history=k keeps rows i % k == 0 of path['TEV'/'LEV'] (the O(nt^2) history is the
+    memory wall at dt=2e-3, tf=40); the kept rows and flowfield() on them are bit-equal to the full-history run."""
+    from ludvm_b200 import LUDVM
+    kw = dict(t0=0, tf=3, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012")
+    o = oracle.OracleLUDVM(**kw)
+    s = LUDVM(**kw, verbose=False, store_history=5)
+    assert s.path["TEV"].shape == ((s.nt - 1) // 5 + 1, 2, s.nt - 1) and list(s.history_steps[:3]) == [0, 5, 10]
+    for k in ("TEV", "LEV"):
+        assert biteq(s.path[k], o.path[k][::5]), k
+    assert biteq(s.path["FREE"], o.path["FREE"]) and biteq(s.Cl, o.Cl)
+    ff = dict(xmin=-2.0, xmax=0.5, zmin=-1.0, zmax=1.0, dr=0.1, tsteps=[0, 6, 41])
+    s.flowfield(**ff)
+    o.flowfield(**ff)
+    assert biteq(s.u_ff, o.u_ff) and biteq(s.w_ff, o.w_ff) and biteq(s.ome_ff, o.ome_ff)
+    with pytest.raises(ValueError):
+        s.flowfield(**dict(ff, tsteps=[7]))
+
+
+def test_free_vortex_heavy_run(oracle):
+    """a gust of 2000 free vortices ahead of the aerofoil from step 0 goes through the same
+    step path (FREE rows of the convection, LUDVM.py:1120-1127); exact mode stays bit-equal to the oracle."""
+    from ludvm_b200 import LUDVM
+    rng = np.random.default_rng(5)
+    nf = 2000
+    xy = np.stack([rng.uniform(-3.0, -0.5, nf), rng.uniform(-0.5, 0.5, nf)])
+    gam = rng.standard_normal(nf) * 2e-3
+    kw = dict(t0=0, tf=0.6, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012",
+              circulation_freevort=gam, xy_freevort=xy)
+    s, o = LUDVM(**kw, verbose=False), oracle.OracleLUDVM(**kw)
+    for k in ("L", "D", "M", "LESP", "LEV_shed"):
+        assert biteq(getattr(s, k), getattr(o, k)), k
+    assert biteq(s.path["FREE"], o.path["FREE"]) and biteq(s.path["TEV"], o.path["TEV"])
+    f = LUDVM(**kw, verbose=False, mode="fast")
+    assert np.max(np.abs(f.L - o.L)) <= 1e-9 * np.max(np.abs(o.L))
