@@ -162,3 +162,21 @@ def test_free_vortex_heavy_run(oracle):
     assert biteq(s.path["FREE"], o.path["FREE"]) and biteq(s.path["TEV"], o.path["TEV"])
     f = LUDVM(**kw, verbose=False, mode="fast")
     assert np.max(np.abs(f.L - o.L)) <= 1e-9 * np.max(np.abs(o.L))
+
+
+def test_tiled_convection_matches_exact_mode():
+    """Wakes >= 8192 vortices take the shared-memory tiled convection kernel (fast mode, graph path).  9000 free
+    vortices put the wake there from step 0; the fast run must track the exact-mode run to rounding level."""
+    from ludvm_b200 import LUDVM
+    rng = np.random.default_rng(9)
+    nf = 9000
+    xy = np.stack([rng.uniform(-6.0, -0.5, nf), rng.uniform(-1.0, 1.0, nf)])
+    gam = rng.standard_normal(nf) * 1e-3
+    kw = dict(t0=0, tf=0.3, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012",
+              circulation_freevort=gam, xy_freevort=xy)
+    e = LUDVM(**kw, verbose=False, mode="exact")
+    f = LUDVM(**kw, verbose=False, mode="fast")
+    assert np.max(np.abs(f.L - e.L)) <= 1e-10 * np.max(np.abs(e.L))
+    assert np.max(np.abs(f.M - e.M)) <= 1e-10 * np.max(np.abs(e.M))
+    assert np.max(np.abs(f.path["FREE"] - e.path["FREE"])) <= 1e-12
+    assert np.max(np.abs(f.path["TEV"] - e.path["TEV"])) <= 1e-12
