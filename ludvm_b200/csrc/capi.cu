@@ -149,6 +149,14 @@ LUDVM_API int ludvm_ctx_create(int device, void *cuda_stream, ludvm_ctx **out)
         }
         ctx->own_stream = true;
     }
+    {   // keep freed arenas in the device's default memory pool (stream-ordered allocator) instead of returning them
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long keep = ~0ULL;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        cudaGetLastError();
+    }
     *out = ctx;
     return LUDVM_OK;
 }

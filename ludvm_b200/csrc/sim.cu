@@ -25,6 +25,7 @@
 //                    independent cases, no collective) and for method='Ramesh', whose Newton loops have a
 //                    data-dependent trip count.
 #include <algorithm>
+#include <chrono>
 #include <map>
 
 #include "biot_savart.cuh"
@@ -1211,13 +1212,16 @@ struct ludvm_sim {
 
 namespace ludvm {
 
-static int dev_malloc(std::vector<void *> &allocs, size_t bytes, void **out)
+// Device memory comes from the stream-ordered allocator (the context raises the pool's release threshold, so the
+// arenas of successive simulations / sweeps are recycled without driver calls: cudaMalloc + cudaFree of a 4096-case
+// sweep's arenas was measured at 0.2-3 s per call on the pool's boxes, more than the kernel).
+static int dev_malloc(ludvm_ctx *ctx, std::vector<void *> &allocs, size_t bytes, void **out)
 {
     void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, std::max<size_t>(bytes, 256));
+    cudaError_t e = cudaMallocAsync(&p, std::max<size_t>(bytes, 256), ctx->stream);
     if (e != cudaSuccess) {
         cudaGetLastError();
-        return set_error(LUDVM_E_NOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return set_error(LUDVM_E_NOMEM, "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e));
     }
     allocs.push_back(p);
     *out = p;
@@ -1239,7 +1243,7 @@ static int upload_tables(ludvm_ctx *ctx, std::vector<void *> &allocs, const ludv
     Arena a;
     for (auto &it : items) a.take<double>(it.n);
     void *base;
-    int rc = dev_malloc(allocs, a.off + 256, &base);
+    int rc = dev_malloc(ctx, allocs, a.off + 256, &base);
     if (rc) return rc;
     Arena b;
     b.base = (char *)base;
@@ -1379,18 +1383,18 @@ LUDVM_API int ludvm_sim_create(ludvm_ctx *ctx, const ludvm_sim_params *p, const 
     Arena measure;
     layout_case(s->d, *p, dt, measure, target, sum_nodes, false);
     void *base;
-    TRY(dev_malloc(s->allocs, measure.off + 256, &base));
+    TRY(dev_malloc(ctx, s->allocs, measure.off + 256, &base));
     CU(cudaMemsetAsync(base, 0, measure.off + 256, ctx->stream));
     Arena real;
     real.base = (char *)base;
     layout_case(s->d, *p, dt, real, target, sum_nodes, false);
     void *dc;
-    TRY(dev_malloc(s->allocs, sizeof(SimDev) + 1024, &dc));
+    TRY(dev_malloc(ctx, s->allocs, sizeof(SimDev) + 1024, &dc));
     s->d_case = (SimDev *)dc;
     s->d_next = (int *)((char *)dc + ((sizeof(SimDev) + 255) & ~(size_t)255));
     {
         void *db;
-        TRY(dev_malloc(s->allocs, COOP_BAR_WORDS * sizeof(unsigned long long), &db));
+        TRY(dev_malloc(ctx, s->allocs, COOP_BAR_WORDS * sizeof(unsigned long long), &db));
         s->d_bar = (unsigned long long *)db;
     }
     CU(cudaMemcpyAsync(s->d_case, &s->d, sizeof(SimDev), cudaMemcpyHostToDevice, ctx->stream));
@@ -1593,7 +1597,7 @@ LUDVM_API int ludvm_sim_destroy(ludvm_sim *s)
     cudaStreamSynchronize(s->ctx->stream);
     for (auto &kv : s->graphs) cudaGraphExecDestroy(kv.second);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
-    for (void *p : s->allocs) cudaFree(p);
+    for (void *p : s->allocs) cudaFreeAsync(p, s->ctx->stream);
     delete s;
     return LUDVM_OK;
 }
@@ -1616,7 +1620,10 @@ LUDVM_API int ludvm_sweep_run(ludvm_ctx *ctx, long ncases, const ludvm_sim_param
     ARG_CHECK(out_doubles_per_case == (size_t)LUDVM_SWEEP_FIELDS * nt);
     DeviceGuard g(ctx->device);
     std::vector<void *> allocs;
-    auto cleanup = [&]() { for (void *p : allocs) cudaFree(p); };
+    auto cleanup = [&]() { for (void *p : allocs) cudaFreeAsync(p, ctx->stream); };
+    const bool tm = getenv("LUDVM_SWEEP_TIMING") != nullptr;   // stderr breakdown of the call (diagnostic)
+    auto now = [&]() { if (tm) cudaStreamSynchronize(ctx->stream); return std::chrono::steady_clock::now(); };
+    auto t0 = now();
 #define TRY(x) do { if ((rc = (x)) != LUDVM_OK) { cleanup(); return rc; } } while (0)
 #define CU(x) do { cudaError_t e__ = (x); if (e__ != cudaSuccess) { cleanup(); return set_error(LUDVM_E_CUDA, "%s failed: %s", #x, cudaGetErrorString(e__)); } } while (0)
     // table sets shared by several cases (same host pointers) are uploaded once
@@ -1636,17 +1643,18 @@ LUDVM_API int ludvm_sweep_run(ludvm_ctx *ctx, long ncases, const ludvm_sim_param
         layout_case(host_cases[c], params[c], dts[c], measure, target, sum_nodes, true);
     }
     void *base;
-    TRY(dev_malloc(allocs, measure.off + 256, &base));
+    TRY(dev_malloc(ctx, allocs, measure.off + 256, &base));
     CU(cudaMemsetAsync(base, 0, measure.off + 256, ctx->stream));
     Arena real;
     real.base = (char *)base;
     for (long c = 0; c < ncases; c++) layout_case(host_cases[c], params[c], dts[c], real, target, sum_nodes, true);
     void *dcases, *dnext;
-    TRY(dev_malloc(allocs, sizeof(SimDev) * (size_t)ncases + 256, &dcases));
-    TRY(dev_malloc(allocs, 256, &dnext));
+    TRY(dev_malloc(ctx, allocs, sizeof(SimDev) * (size_t)ncases + 256, &dcases));
+    TRY(dev_malloc(ctx, allocs, 256, &dnext));
     CU(cudaMemcpyAsync(dcases, host_cases.data(), sizeof(SimDev) * (size_t)ncases, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemsetAsync(dnext, 0, sizeof(int), ctx->stream));
     k_case_init<<<(unsigned)ncases, 256, 0, ctx->stream>>>((const SimDev *)dcases, (int)ncases);
+    auto t1 = now();
     size_t smem = solve_smem_bytes(host_cases[0]);
     TRY(set_smem_limits(smem, 0));
     int per_sm = 1;
@@ -1658,16 +1666,24 @@ LUDVM_API int ludvm_sweep_run(ludvm_ctx *ctx, long ncases, const ludvm_sim_param
     else k_sim_cta<CTA_THREADS, LUDVM_METHOD_FAURE><<<grid, CTA_THREADS, smem, ctx->stream>>>((const SimDev *)dcases, (int)ncases, (int *)dnext, (int)nt);
     ctx->launches += 2;
     CU(cudaGetLastError());
+    auto t2 = now();
     void *dout;
     const size_t out_bytes = sizeof(double) * (size_t)ncases * out_doubles_per_case;
-    TRY(dev_malloc(allocs, out_bytes, &dout));
+    TRY(dev_malloc(ctx, allocs, out_bytes, &dout));
     k_sweep_gather<<<(unsigned)ncases, 256, 0, ctx->stream>>>((const SimDev *)dcases, (int)ncases, (double *)dout);
     ctx->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(out, dout, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    auto t3 = now();
 #undef CU
 #undef TRY
     cleanup();
+    if (tm) {
+        auto t4 = std::chrono::steady_clock::now();
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "ludvm_sweep_run: upload+alloc+init %.1f ms, kernel %.1f ms, gather+D2H %.1f ms, free %.1f ms (arena %.0f MB)\n",
+                ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4), measure.off / 1048576.0);
+    }
     return LUDVM_OK;
 }
