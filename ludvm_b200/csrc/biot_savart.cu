@@ -57,6 +57,17 @@ k_fast32_tiled(SrcView S, Tgt T, int nrows, int chunk_len, double *pu, double *p
     fast32_tiled_block<R>(S, T, nrows, blockIdx.x, c0, c1, pu + po, pw_ + po, ssrc);
 }
 
+// fp32 with packed fp32x2 arithmetic: 8 rows (4 float2 pairs) per thread; scalar core radius only.
+template <class Tgt>
+__global__ void __launch_bounds__(FT_THREADS, 2)
+k_fast32x2_tiled(SrcView S, Tgt T, int nrows, int chunk_len, double *pu, double *pw_)
+{
+    __shared__ Src32x2 ssrc[FT_TILE];
+    int c0 = blockIdx.y * chunk_len, c1 = min(S.n, c0 + chunk_len);
+    size_t po = (size_t)blockIdx.y * nrows;
+    fast32x2_tiled_block<4>(S, T, nrows, blockIdx.x, c0, c1, pu + po, pw_ + po, ssrc);
+}
+
 // Fold partials.  exact: nfold = tree depth d; fast: nfold = number of chunks.  Optional second partial set
 // (the reference's `u_wake + u_foil`, LUDVM.py:1108, :1219) and optional forward-Euler update (LUDVM.py:1108-1127).
 struct CombineArgs {
@@ -172,7 +183,10 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
         long chunks = std::max(1L, std::min(8L, (long)S.n / (FT_TILE * 2)));
         int chunk_len = (int)(((S.n + chunks - 1) / chunks + FT_TILE - 1) / FT_TILE * FT_TILE);
         chunks = ((long)S.n + chunk_len - 1) / chunk_len;
-        int R = 4;
+        // fp32: the packed fp32x2 kernel (8 rows per thread) when the core radius is a scalar and there are enough rows
+        const bool f32x2 = f32 && S.vc4 == nullptr && (long)ceil_div(nrows, FT_THREADS * 8) * chunks >= (long)sm * 2 &&
+                           !getenv("LUDVM_NO_F32X2");
+        int R = f32x2 ? 8 : 4;
         if (!f32) {
             while (R > 1 && (long)ceil_div(nrows, FT_THREADS * R) * chunks < (long)sm * 2 * 6) R >>= 1;
         }
@@ -186,7 +200,8 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
         // one contiguous, 16-byte aligned source segment with a scalar core: TMA-staged tiles
         const bool tma = !f32 && S.vc4 == nullptr && S.gstride == 1 && S.n0 == S.n &&
                          (((uintptr_t)S.x | (uintptr_t)S.z | (uintptr_t)S.g) & 15) == 0 && !getenv("LUDVM_NO_TMA");
-        if (f32) k_fast32_tiled<4><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
+        if (f32x2) k_fast32x2_tiled<<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
+        else if (f32) k_fast32_tiled<4><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
         else if (tma && R == 4) k_fast_tiled_tma<4><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
         else if (tma && R == 2) k_fast_tiled_tma<2><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
         else if (tma) k_fast_tiled_tma<1><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);

@@ -461,4 +461,86 @@ __device__ __forceinline__ void fast32_tiled_block(const SrcView &S, const Tgt &
     }
 }
 
+// fp32 pair arithmetic with Blackwell's packed fp32x2 instructions (FADD2 / FMUL2 / FFMA2, sm_100+): one thread owns
+// 2*RP target rows as RP float2 pairs, a source is broadcast from shared memory already duplicated into both halves
+// ({-x,-x}, {-z,-z}, {g,g}: one LDS.64 each, no register shuffling), so a pair of interactions costs 8 packed FP32
+// instructions + 2 MUFU.RSQ instead of 16 + 2 issue slots.  The scalar kernel is issue-bound (10 slots per pair at 4
+// issues/clk/SM); packed, the bound becomes the FP32 pipe / MUFU rate (16 pairs/clk/SM).
+// The w accumulator holds +sum(g K dx) and is negated once at the end.
+struct Src32x2 {
+    float2 nx, nz, g;
+};
+
+template <int RP, class Tgt>
+__device__ __forceinline__ void fast32x2_tiled_block(const SrcView &S, const Tgt &T, int nrows, int row_block, int c0,
+                                                     int c1, double *__restrict__ pu, double *__restrict__ pw_,
+                                                     Src32x2 *ssrc)
+{
+    constexpr int R = 2 * RP;
+    float2 tx[RP], tz[RP];
+    double au[R], aw[R];
+    const int base = row_block * (FT_THREADS * R) + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < RP; r++) {
+        double xa, za, xb, zb;
+        T.get(min(base + (2 * r) * FT_THREADS, nrows - 1), xa, za);
+        T.get(min(base + (2 * r + 1) * FT_THREADS, nrows - 1), xb, zb);
+        tx[r] = make_float2((float)xa, (float)xb);
+        tz[r] = make_float2((float)za, (float)zb);
+        au[2 * r] = au[2 * r + 1] = aw[2 * r] = aw[2 * r + 1] = 0.0;
+    }
+    const float vcs = (float)S.vc4s;
+    const float2 vc4 = make_float2(vcs, vcs);
+    for (int t0 = c0; t0 < c1; t0 += FT_TILE) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < FT_TILE; j += FT_THREADS) {
+            int s = t0 + j;
+            bool ok = s < c1;
+            int p = ok ? S.phys(s) : 0;
+            float x = ok ? -(float)S.x[p] : 0.f, z = ok ? -(float)S.z[p] : 0.f;
+            float g = ok ? (float)(S.g[p * S.gstride] * LUDVM_INV_TWO_PI) : 0.f;
+            Src32x2 v;
+            v.nx = make_float2(x, x);
+            v.nz = make_float2(z, z);
+            v.g = make_float2(g, g);
+            ssrc[j] = v;
+        }
+        __syncthreads();
+        float2 fu[RP], fw[RP];
+#pragma unroll
+        for (int r = 0; r < RP; r++) fu[r] = fw[r] = make_float2(0.f, 0.f);
+#pragma unroll 4
+        for (int j = 0; j < FT_TILE; j++) {
+            const Src32x2 v = ssrc[j];
+#pragma unroll
+            for (int r = 0; r < RP; r++) {
+                float2 dx = __fadd2_rn(tx[r], v.nx), dz = __fadd2_rn(tz[r], v.nz);
+                float2 r2 = __ffma2_rn(dz, dz, __fmul2_rn(dx, dx));
+                float2 q = __ffma2_rn(r2, r2, vc4);
+                float2 y;
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y.x) : "f"(q.x));
+                asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y.y) : "f"(q.y));
+                float2 gg = __fmul2_rn(v.g, y);
+                fu[r] = __ffma2_rn(gg, dz, fu[r]);
+                fw[r] = __ffma2_rn(gg, dx, fw[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < RP; r++) {
+            au[2 * r] += (double)fu[r].x;
+            au[2 * r + 1] += (double)fu[r].y;
+            aw[2 * r] -= (double)fw[r].x;
+            aw[2 * r + 1] -= (double)fw[r].y;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        int row = base + r * FT_THREADS;
+        if (row < nrows) {
+            pu[row] = au[r];
+            pw_[row] = aw[r];
+        }
+    }
+}
+
 }  // namespace ludvm
