@@ -67,6 +67,17 @@ if 2 in only:   # high-resolution run, dt=2e-3, tf=40
     r["note"] = ("chaotic once LEV shedding starts: a 1-ulp perturbation of h_max in the CPU oracle gives 1e-8 @700, "
                  "3e-4 @800, 0.38 @900, 1.27 @1500 (scripts/chaos_envelope.py)")
     se.close()
+    # CPU side of SURVEY.md 8(d)-2: prefix runs of the oracle port (one core), cubic fit t(n) = a n + b n^2 + c n^3
+    # (the step is O(N^2) pairs with N ~ n), EXTRAPOLATED to the full run -- nobody waits hours for the CPU.
+    ns, ts = [250, 500, 1000, 2000], []
+    for n_ in ns:
+        t0 = time.perf_counter(); oracle.OracleLUDVM(**kw, nsteps=n_); ts.append(time.perf_counter() - t0)
+    A = np.array([[n_, n_ ** 2, n_ ** 3] for n_ in ns], dtype=float)
+    coef, *_ = np.linalg.lstsq(A, np.array(ts), rcond=None)
+    r["cpu_oracle_1core_prefix_seconds"] = dict(zip(map(str, ns), ts))
+    r["cpu_oracle_1core_EXTRAPOLATED_seconds_for_%d_steps" % nsteps] = float(np.dot([nsteps, nsteps ** 2, nsteps ** 3], coef))
+    r["cpu_note"] = ("extrapolated from the prefix runs by a cubic least-squares fit; the oracle is the scalar C port, the "
+                     "reference's numpy loop is ~37x slower per step at README size (60 vs 2236 steps/s)")
     rep["config2_hires"] = r; dump(); print("config2", r, flush=True)
 
 if 3 in only:   # synthetic 1M all-pairs (the bench workload), exact + fast + fp32 single step timings
