@@ -90,3 +90,13 @@ def test_motion_plunge_fixed_and_cambered_section():
     s.motion_plunge(G=1, T=2)          # the reference raises TypeError here (LUDVM.py:520)
     assert s.alpha_e.shape == (s.nt,) and np.all(np.diff(s.hpiv) <= 1e-15)
     assert s.hpiv[-1] == s.hpiv[np.searchsorted(s.t, 2.0, side="right") - 1]
+
+
+def test_store_history_argument_is_validated_on_the_host():
+    """store_history: True/False/k (strided snapshots); negative values are rejected before any device work."""
+    from ludvm_b200 import LUDVM
+    kw = dict(t0=0, tf=1, dt=5e-2, Npoints=81, Naca="0012", verbose=False, run=False)
+    assert LUDVM(**kw).store_history == 1 and LUDVM(**kw, store_history=False).store_history == 0
+    assert LUDVM(**kw, store_history=7).store_history == 7
+    with pytest.raises(ValueError):
+        LUDVM(**kw, store_history=-2)
