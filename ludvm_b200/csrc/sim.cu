@@ -76,6 +76,7 @@ struct SimDev {
     double *pa_u, *pa_w;  // wake-on-foil partials        [2^d1][P]
     double *pb_u, *pb_w;  // loads+convection partials    [2^d2][P + Nw2]
     double *foil_u, *foil_w;  // bound vortices on the wake [Nw2]
+    double *gp_u, *gp_w;      // overlapped step: wake velocity at the gamma points [P]
     double *pre_sums;         // graph path: np.sum(Gamma_TEV[:itev]), np.sum(Gamma_LEV[:ilev]) of the current step
 };
 
@@ -189,6 +190,48 @@ struct TgtWake {
         int p = W.phys(r);
         xp = W.x[p];
         zp = W.z[p];
+    }
+};
+
+// Positions of the two vortices a step may add, from data known before the solve (LUDVM.py:672-681, :784-800).
+__device__ __forceinline__ void place_tev(const SimDev &S, int i, int itev, double &xt, double &zt)
+{
+    if (itev == 0) {
+        xt = S.te[0] + 0.5 * S.Uinf * S.dt;
+        zt = S.te[1] + 0.0;
+    } else {
+        double tex = S.te[(size_t)i * 2], tez = S.te[(size_t)i * 2 + 1];
+        xt = tex + 1.0 / 3 * (S.wx[itev - 1] - tex);
+        zt = tez + 1.0 / 3 * (S.wz[itev - 1] - tez);
+    }
+}
+__device__ __forceinline__ void place_lev(const SimDev &S, int i, int ilev, double &xl, double &zl)
+{
+    double lex = S.le[(size_t)i * 2], lez = S.le[(size_t)i * 2 + 1];
+    xl = lex;
+    zl = lez;
+    if (ilev > 0 && S.lev_shed[i - 1] != -1.0) {
+        xl = lex + 1.0 / 3 * (S.wx[S.nv + ilev - 1] - lex);
+        zl = lez + 1.0 / 3 * (S.wz[S.nv + ilev - 1] - lez);
+    }
+}
+
+struct TgtWakePlus {  // rows [0, n): the old wake; n: the new TEV; n + 1: the LEV if one is shed; n + 2: the idle LEV slot (origin)
+    SrcView W;
+    double xt, zt, xl, zl;
+    __device__ __forceinline__ void get(int r, double &xp, double &zp) const
+    {
+        if (r < W.n) {
+            int p = W.phys(r);
+            xp = W.x[p];
+            zp = W.z[p];
+        } else if (r == W.n) {
+            xp = xt; zp = zt;
+        } else if (r == W.n + 1) {
+            xp = xl; zp = zl;
+        } else {
+            xp = 0.0; zp = 0.0;
+        }
     }
 };
 
@@ -686,7 +729,9 @@ __device__ __forceinline__ int conv_fold(const SimDev &S, const Step &st, int ti
 }
 
 // `tab` = shared memory of resident StepTables, or nullptr: then the three tables needed here are built in `sm`.
-__device__ void phase_finish_loads(const SimDev &S, const Step &st, double *tab, double *sm, int tiled_chunks, int cap)  // LUDVM.py:1035-1090
+// `ov`: the wake velocity at the gamma points was already assembled in S.gp_u / S.gp_w (overlapped step).
+__device__ void phase_finish_loads(const SimDev &S, const Step &st, double *tab, double *sm, int tiled_chunks, int cap,
+                                   bool ov = false)  // LUDVM.py:1035-1090
 {
     const int P = S.P, i = st.i, itev = st.itev, tid = threadIdx.x, nth = blockDim.x;
     const int nrows = P + st.itev + 1 + st.ilev + 1 + S.nfree;
@@ -708,7 +753,15 @@ __device__ void phase_finish_loads(const SimDev &S, const Step &st, double *tab,
         }
         dxp = d; ones = o; xp = x;
     }
-    block_fold(S.pb_u, S.pb_w, nrows, P, fold, exact, stage, cap, ug, ugx);  // wake velocity at the gamma points
+    if (ov) {
+        for (int j = tid; j < P; j += nth) {
+            ug[j] = S.gp_u[j];
+            ugx[j] = S.gp_w[j];
+        }
+        __syncthreads();
+    } else {
+        block_fold(S.pb_u, S.pb_w, nrows, P, fold, exact, stage, cap, ug, ugx);  // wake velocity at the gamma points
+    }
     for (int j = tid; j < P; j += nth) {
         double u1 = ug[j], w1 = ugx[j];
         double u = u1 * ca - w1 * sa;
@@ -857,6 +910,152 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_conv_partials_tiled(SimDev S,
         SrcView Fo = make_src(S.g_airfoil + (size_t)st.itev * S.af_stride, 1, gx, gz, nullptr, S.vc4, P);
         TgtWake TW{W};
         fast_tiled_block<R>(Fo, TW, W.n, blockIdx.x, 0, P, S.foil_u, S.foil_w, sx, sz, sg, sv);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// overlapped step (fast mode, tiled wakes).  The O(N^2) part of the convection -- the OLD wake TEV[:itev] ++ LEV[:ilev]
+// ++ FREE acting on itself and on the positions the step's two new vortices will take -- does not depend on the
+// circulations solved in this step, so it runs on a second graph branch beside phase 1 + the solve (which keep one
+// CTA busy for tens of microseconds while 147 SMs would idle):
+//   branch A: k_wake_on_foil -> k_solve_small                   branch B: k_conv_old_tiled
+//   join:     k_conv_new  (the two new vortices + the P bound vortices on every wake row; wake velocity at the gamma
+//                          points = phase-1 sums + the two new vortices)  ->  k_finish_ov (loads, Euler update)
+// For the solve CTA to start while the convection grid occupies every SM it must fit into the hole ONE retiring
+// convection CTA leaves (256 threads x <= 70 registers): k_solve_small is the solve compiled for 64 registers (a
+// 128-register solve CTA was measured to start only when the convection kernel drained).
+// Summation order differs from the serial step (fast mode carries no order guarantee); exact mode keeps the serial step.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SOLVE_THREADS, 4) k_solve_small(SimDev S, int s)
+{
+    extern __shared__ double sm[];
+    Step st;
+    if (!step_begin(S, s, st)) return;
+    phase_solve<LUDVM_METHOD_FAURE>(S, st, sm, sm + TABLE_SMEM_DOUBLES(S.P, S.Nc, S.sinn_smem), S.pre_sums, true);
+}
+
+template <int R>
+__global__ void __launch_bounds__(FT_THREADS, 2) k_conv_old_tiled(SimDev S, int s, int chunks)
+{
+    __shared__ double sx[FT_TILE], sz[FT_TILE], sg[FT_TILE], sv[FT_TILE];
+    Step st;
+    if (!step_begin(S, s, st)) return;
+    SrcView W = wake_view(S, st.itev, st.ilev);
+    const int nrows = W.n + 3;   // + the new TEV, the LEV if shed, the idle LEV slot: their rows need no solve either
+    if ((long)blockIdx.x * (FT_THREADS * R) >= nrows) return;
+    TgtWakePlus TW;
+    TW.W = W;
+    place_tev(S, st.i, st.itev, TW.xt, TW.zt);
+    place_lev(S, st.i, st.ilev, TW.xl, TW.zl);
+    int chunk_len = ((W.n + chunks - 1) / chunks + FT_TILE - 1) / FT_TILE * FT_TILE;
+    int c0 = blockIdx.y * chunk_len, c1 = min(W.n, c0 + chunk_len);
+    size_t po = (size_t)blockIdx.y * nrows;
+    fast_tiled_block<R>(W, TW, nrows, blockIdx.x, c0, c1, S.pb_u + po, S.pb_w + po, sx, sz, sg, sv);
+}
+
+// Row of the updated wake TEV[:itev+1] ++ LEV[:ilev+1] ++ FREE -> row of k_conv_old_tiled's partials (nold = rows of
+// the old wake; the step's two additions map to the extra rows, see TgtWakePlus).
+__device__ __forceinline__ int old_row(int r, int itev, int ilev, int nold, bool shed)
+{
+    if (r < itev) return r;
+    if (r == itev) return nold;
+    if (r < itev + 1 + ilev) return r - 1;
+    if (r == itev + 1 + ilev) return shed ? nold + 1 : nold + 2;
+    return r - 2;
+}
+
+__global__ void __launch_bounds__(256) k_conv_new(SimDev S, int s)
+{
+    __shared__ double sx[260], sz[260], sg[260];   // P bound vortices + the two new wake vortices (P <= 256)
+    Step st;
+    if (!step_begin(S, s, st)) return;
+    const int P = S.P, tid = threadIdx.x, itev = st.itev, ilev = st.ilev, nv = S.nv;
+    SrcView W = wake_view(S, itev + 1, ilev + 1);
+    const double *gx = S.gp + ((size_t)st.i * 2 + 0) * P, *gz = S.gp + ((size_t)st.i * 2 + 1) * P;
+    const double *ga = S.g_airfoil + (size_t)itev * S.af_stride;
+    if (blockIdx.x == 0) {   // gamma points: old wake (phase-1 partials) + the two new vortices  (LUDVM.py:1049-1054)
+        const int fold = wof_fold(S.mode, itev + ilev + S.nfree, P, S.target_warps);
+        const double xt = S.wx[itev], zt = S.wz[itev], gt = S.wg[itev] * LUDVM_INV_TWO_PI;
+        const double xl = S.wx[nv + ilev], zl = S.wz[nv + ilev], gl = S.wg[nv + ilev] * LUDVM_INV_TWO_PI;
+        for (int j = tid; j < P; j += blockDim.x) {
+            double u = fast_combine_row(S.pa_u, P, j, fold), w = fast_combine_row(S.pa_w, P, j, fold);
+            pair_fast(gx[j], gz[j], xt, zt, gt, S.vc4, u, w);
+            pair_fast(gx[j], gz[j], xl, zl, gl, S.vc4, u, w);
+            S.gp_u[j] = u;
+            S.gp_w[j] = w;
+        }
+        return;
+    }
+    // every wake row (the two new ones included): the P bound vortices and the two new wake vortices
+    for (int j = tid; j < P + 2; j += blockDim.x) {
+        if (j < P) { sx[j] = gx[j]; sz[j] = gz[j]; sg[j] = ga[j] * LUDVM_INV_TWO_PI; }
+        else {
+            int q = j == P ? itev : nv + ilev;
+            sx[j] = S.wx[q]; sz[j] = S.wz[q]; sg[j] = S.wg[q] * LUDVM_INV_TWO_PI;
+        }
+    }
+    __syncthreads();
+    for (long r = (long)(blockIdx.x - 1) * blockDim.x + tid; r < W.n; r += (long)(gridDim.x - 1) * blockDim.x) {
+        const int p = W.phys((int)r);
+        const double xp = S.wx[p], zp = S.wz[p];
+        double u0 = 0.0, w0 = 0.0, u1 = 0.0, w1 = 0.0;
+        int j = 0;
+        for (; j + 1 < P + 2; j += 2) {
+            pair_fast(xp, zp, sx[j], sz[j], sg[j], S.vc4, u0, w0);
+            pair_fast(xp, zp, sx[j + 1], sz[j + 1], sg[j + 1], S.vc4, u1, w1);
+        }
+        if (j < P + 2) pair_fast(xp, zp, sx[j], sz[j], sg[j], S.vc4, u0, w0);
+        S.foil_u[r] = u0 + u1;
+        S.foil_w[r] = w0 + w1;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_finish_ov(SimDev S, int s, int chunks)
+{
+    extern __shared__ double sm[];
+    Step st;
+    if (!step_begin(S, s, st)) return;
+    if (blockIdx.x == 0) {
+        phase_finish_loads(S, st, nullptr, sm, chunks, FINISH_STAGE, true);
+        return;
+    }
+    if (blockIdx.x == 1) {
+        phase_gamma_cumsum(S, st, threadIdx.x, blockDim.x);
+        return;
+    }
+    // convection (LUDVM.py:1095-1127): old-wake partials + k_conv_new's terms
+    const int i = st.i, nv = S.nv, nT = st.itev + 1, nL = st.ilev + 1;
+    SrcView W = wake_view(S, nT, nL);
+    const int nold = W.n - 2, npart = nold + 3;
+    const bool shed = S.lev_shed[i] != -1.0;
+    const double dt = S.dt;
+    for (long r = (long)(blockIdx.x - 2) * blockDim.x + threadIdx.x; r < W.n; r += (long)(gridDim.x - 2) * blockDim.x) {
+        const int ro = old_row((int)r, st.itev, st.ilev, nold, shed);
+        const double u = S.foil_u[r] + fast_combine_row(S.pb_u, npart, ro, chunks);
+        const double w = S.foil_w[r] + fast_combine_row(S.pb_w, npart, ro, chunks);
+        const int p = W.phys((int)r);
+        const double xn = S.wx[p] + dt * u, zn = S.wz[p] + dt * w;
+        S.wx[p] = xn;
+        S.wz[p] = zn;
+        if (S.store_history) {
+            double *hx, *hz;
+            const bool snap = (i % S.store_history) == 0;
+            const size_t hrow = (size_t)(i / S.store_history);
+            if (r < nT) {
+                if (!snap) continue;
+                hx = S.path_tev + (hrow * 2) * nv + r;
+                hz = hx + nv;
+            } else if (r < nT + nL) {
+                if (!snap) continue;
+                hx = S.path_lev + (hrow * 2) * nv + (r - nT);
+                hz = hx + nv;
+            } else {
+                hx = S.path_free + ((size_t)i * 2) * S.nfree + (r - nT - nL);
+                hz = hx + S.nfree;
+            }
+            *hx = xn;
+            *hz = zn;
+        }
     }
 }
 
@@ -1185,6 +1384,7 @@ static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t
     D.pb_u = a.take<double>(pb); D.pb_w = a.take<double>(pb);
     D.foil_u = a.take<double>(nstate + 8); D.foil_w = a.take<double>(nstate + 8);
     D.pre_sums = a.take<double>(2);
+    D.gp_u = a.take<double>(P); D.gp_w = a.take<double>(P);
 }
 
 static size_t solve_smem_bytes(const SimDev &D) { return (size_t)SOLVE_SMEM_DOUBLES(D.P, D.Nc, D.sum_nodes, D.sinn_smem) * sizeof(double); }
@@ -1206,6 +1406,8 @@ struct ludvm_sim {
     size_t solve_smem = 0, finish_smem = 0;
     unsigned long long *d_bar = nullptr;  // grid-barrier counter of the cooperative path
     int coop_grid = 0;                    // CTAs of the cooperative kernel (0: path not available on this device)
+    cudaStream_t cap_stream2 = nullptr;   // second capture stream: the overlapped step's old-wake convection branch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t cap_stream = nullptr;  // private stream used only to record graphs (the context's stream may be
                                         // the legacy default stream, which cannot be captured)
 };
@@ -1271,8 +1473,9 @@ static int bracket_of(long n)
 
 // Launch geometry of one step for every wake size up to 2^bracket.
 struct StepPlan {
-    int g1, g3, g4, R, tchunks;
-    bool tiled;
+    int g1, g3, g4, g5, R, tchunks;
+    bool tiled, ov;
+    dim3 gto;
     dim3 gt;
 };
 
@@ -1294,6 +1497,8 @@ static StepPlan plan_step(const ludvm_sim *s, int bracket)
     pl.g3 = (int)std::max<long>(1, std::min<long>((t3 + 7) / 8, (long)sm * 16));
     pl.g4 = 2 + (int)std::max<long>(1, std::min<long>((nw + 255) / 256, (long)sm * 8));
     pl.tiled = D.mode != LUDVM_EXACT_F64 && nw >= SIM_TILED_MIN_WAKE;
+    pl.ov = false;
+    pl.g5 = 1;
     pl.R = 1;
     pl.tchunks = 0;
     pl.gt = dim3(1, 1);
@@ -1304,24 +1509,40 @@ static StepPlan plan_step(const ludvm_sim *s, int bracket)
         pl.tchunks = (int)std::max<long>(1, std::min<long>(std::min<long>(SIM_TILED_CHUNKS_MAX, nw / (2 * FT_TILE)),
                                                            ((long)sm * 2 * 6 + row_blocks - 1) / row_blocks));
         pl.gt = dim3((unsigned)row_blocks, (unsigned)pl.tchunks + 1);
+        // overlapped step: old-wake convection on a second graph branch beside phase 1 + solve
+        pl.ov = D.P <= 256 && !getenv("LUDVM_NO_OVERLAP");
+        pl.gto = dim3((unsigned)((nw + 3 + FT_THREADS * pl.R - 1) / (FT_THREADS * pl.R)), (unsigned)pl.tchunks);
+        pl.g5 = 1 + (int)std::max<long>(1, std::min<long>((nw + 255) / 256, (long)sm * 8));
     }
     return pl;
 }
 
-// Enqueue kernel `which` (0..3) of step offset k.
+// Enqueue kernel `which` of step offset k: 0 wake-on-foil, 1 solve, 2 convection partials, 3 finish; for the overlapped
+// step 2 = old-wake convection (independent of 0 and 1), 4 = the new-vortex / bound-vortex terms, 3 = finish.
 static void enqueue_step_kernel(const ludvm_sim *s, const StepPlan &pl, int which, int k, cudaStream_t cs)
 {
     const SimDev &D = s->d;
     switch (which) {
     case 0: k_wake_on_foil<<<pl.g1, 256, 0, cs>>>(D, k); break;
-    case 1: k_solve<<<1, SOLVE_THREADS, s->solve_smem, cs>>>(D, k); break;
+    case 1:
+        if (pl.ov) k_solve_small<<<1, SOLVE_THREADS, s->solve_smem, cs>>>(D, k);
+        else k_solve<<<1, SOLVE_THREADS, s->solve_smem, cs>>>(D, k);
+        break;
     case 2:
         if (!pl.tiled) k_conv_partials<<<pl.g3, 256, 0, cs>>>(D, k);
-        else if (pl.R == 4) k_conv_partials_tiled<4><<<pl.gt, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
+        else if (pl.ov) {
+            if (pl.R == 4) k_conv_old_tiled<4><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
+            else if (pl.R == 2) k_conv_old_tiled<2><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
+            else k_conv_old_tiled<1><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
+        } else if (pl.R == 4) k_conv_partials_tiled<4><<<pl.gt, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
         else if (pl.R == 2) k_conv_partials_tiled<2><<<pl.gt, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
         else k_conv_partials_tiled<1><<<pl.gt, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
         break;
-    default: k_finish<<<pl.g4, 256, s->finish_smem, cs>>>(D, k, pl.tchunks); break;
+    case 4: k_conv_new<<<pl.g5, 256, 0, cs>>>(D, k); break;
+    default:
+        if (pl.ov) k_finish_ov<<<pl.g4, 256, s->finish_smem, cs>>>(D, k, pl.tchunks);
+        else k_finish<<<pl.g4, 256, s->finish_smem, cs>>>(D, k, pl.tchunks);
+        break;
     }
 }
 
@@ -1330,11 +1551,31 @@ static int build_graph(ludvm_sim *s, int bracket, int ksteps, cudaGraphExec_t *o
     const SimDev &D = s->d;
     const StepPlan pl = plan_step(s, bracket);
     cudaGraph_t graph;
-    if (!s->cap_stream) CUDA_TRY(cudaStreamCreateWithFlags(&s->cap_stream, cudaStreamNonBlocking));
-    cudaStream_t cs = s->cap_stream;
+    if (!s->cap_stream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);   // lo = least, hi = greatest priority
+        CUDA_TRY(cudaStreamCreateWithPriority(&s->cap_stream, cudaStreamNonBlocking, hi));   // latency-critical branch
+        CUDA_TRY(cudaStreamCreateWithPriority(&s->cap_stream2, cudaStreamNonBlocking, lo));  // bulk old-wake convection
+        CUDA_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+    }
+    cudaStream_t cs = s->cap_stream, cs2 = s->cap_stream2;
     CUDA_TRY(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    for (int k = 0; k < ksteps; k++)
-        for (int which = 0; which < 4; which++) enqueue_step_kernel(s, pl, which, k, cs);
+    for (int k = 0; k < ksteps; k++) {
+        if (pl.ov) {
+            CUDA_TRY(cudaEventRecord(s->ev_fork, cs));
+            CUDA_TRY(cudaStreamWaitEvent(cs2, s->ev_fork, 0));
+            enqueue_step_kernel(s, pl, 0, k, cs);
+            enqueue_step_kernel(s, pl, 2, k, cs2);
+            enqueue_step_kernel(s, pl, 1, k, cs);
+            CUDA_TRY(cudaEventRecord(s->ev_join, cs2));
+            CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_join, 0));
+            enqueue_step_kernel(s, pl, 4, k, cs);
+            enqueue_step_kernel(s, pl, 3, k, cs);
+        } else {
+            for (int which = 0; which < 4; which++) enqueue_step_kernel(s, pl, which, k, cs);
+        }
+    }
     k_advance<<<1, 1, 0, cs>>>(D, ksteps);
     cudaError_t e = cudaStreamEndCapture(cs, &graph);
     if (e != cudaSuccess) return set_error(LUDVM_E_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
@@ -1349,6 +1590,7 @@ static int set_smem_limits(size_t solve_smem, size_t finish_smem)
     if (solve_smem > 200 * 1024) return set_error(LUDVM_E_UNSUPPORTED, "Npoints too large for the solve kernel");
     if (solve_smem > 48 * 1024) {
         CUDA_TRY(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
         CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<CTA_THREADS, LUDVM_METHOD_FAURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
         CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<CTA_THREADS, LUDVM_METHOD_RAMESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
         CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<RAMESH_THREADS, LUDVM_METHOD_RAMESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
@@ -1463,7 +1705,7 @@ LUDVM_API int ludvm_sim_run(ludvm_sim *s, long nsteps)
             it = s->graphs.emplace(key, ge).first;
         }
         CUDA_TRY(cudaGraphLaunch(it->second, s->ctx->stream));
-        s->ctx->launches += 4L * k + 1;
+        s->ctx->launches += (plan_step(s, b).ov ? 5L : 4L) * k + 1;
         s->steps_enqueued += k;
         todo -= k;
     }
@@ -1490,6 +1732,7 @@ LUDVM_API int ludvm_sim_profile_steps(ludvm_sim *s, long nsteps, double *ms_out)
         for (int which = 0; which < 4; which++) {
             CUDA_TRY(cudaEventRecord(ev[which], st));
             enqueue_step_kernel(s, pl, which, 0, st);
+            if (which == 2 && pl.ov) enqueue_step_kernel(s, pl, 4, 0, st);
         }
         CUDA_TRY(cudaEventRecord(ev[4], st));
         k_advance<<<1, 1, 0, st>>>(s->d, 1);
@@ -1597,6 +1840,9 @@ LUDVM_API int ludvm_sim_destroy(ludvm_sim *s)
     cudaStreamSynchronize(s->ctx->stream);
     for (auto &kv : s->graphs) cudaGraphExecDestroy(kv.second);
     if (s->cap_stream) cudaStreamDestroy(s->cap_stream);
+    if (s->cap_stream2) cudaStreamDestroy(s->cap_stream2);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
     for (void *p : s->allocs) cudaFreeAsync(p, s->ctx->stream);
     delete s;
     return LUDVM_OK;
