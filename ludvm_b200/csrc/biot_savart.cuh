@@ -273,8 +273,9 @@ __device__ __forceinline__ void fast_tiled_block(const SrcView &S, const Tgt &T,
             sv[j] = ok ? (S.vc4 ? S.vc4[p] : S.vc4s) : 1.0;
         }
         __syncthreads();
+        const int cnt = min(FT_TILE, c1 - t0);   // a ragged last tile costs only its own sources
 #pragma unroll 4
-        for (int j = 0; j < FT_TILE; j++) {
+        for (int j = 0; j < cnt; j++) {
             double x = sx[j], z = sz[j], g = sg[j], v = sv[j];
 #pragma unroll
             for (int r = 0; r < R; r++) pair_fast(tx[r], tz[r], x, z, g, v, au[r], aw[r]);

@@ -39,7 +39,7 @@ namespace ludvm {
 #define RAMESH_THREADS 1024
 #define PI_D 3.141592653589793
 #define SIM_TILED_MIN_WAKE 8192   // fast mode: wakes at least this large use the tiled convection kernel
-#define SIM_TILED_CHUNKS_MAX 16
+#define SIM_TILED_CHUNKS_MAX 64   // partial-sum slots per row of the tiled convection
 #define SIM_COOP_MAX_WAKE 8192    // wakes up to this size are stepped by the persistent cooperative kernel
 #define FINISH_STAGE 4096         // doubles of staging in the loads block of k_finish
 
@@ -926,6 +926,22 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_conv_partials_tiled(SimDev S,
 // 128-register solve CTA was measured to start only when the convection kernel drained).
 // Summation order differs from the serial step (fast mode carries no order guarantee); exact mode keeps the serial step.
 // ---------------------------------------------------------------------------------------------------
+// Source chunking of the old-wake convection, chosen from the ACTUAL wake size (a graph serves a 2:1 range of sizes):
+// about eight waves of CTAs over the resident slots, chunk length a multiple of 64 sources, at most
+// SIM_TILED_CHUNKS_MAX chunks.  With chunks fixed per graph the grid was 2.4 waves at 22k vortices (79 % occupancy of
+// the last wave's worth of time).  Identical in the producer and in k_finish_ov.
+struct TiledGeom {
+    int chunk_len, chunks;
+    __host__ __device__ __forceinline__ TiledGeom(int nrows, int nsrc, int R, int slots)
+    {
+        const int rb = (nrows + FT_THREADS * R - 1) / (FT_THREADS * R);
+        int want = (8 * slots + rb - 1) / rb;
+        want = want < 1 ? 1 : (want > SIM_TILED_CHUNKS_MAX ? SIM_TILED_CHUNKS_MAX : want);
+        chunk_len = (((nsrc + want - 1) / want + 63) / 64) * 64;
+        chunks = (nsrc + chunk_len - 1) / chunk_len;
+    }
+};
+
 __global__ void __launch_bounds__(SOLVE_THREADS, 4) k_solve_small(SimDev S, int s)
 {
     extern __shared__ double sm[];
@@ -935,20 +951,20 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 4) k_solve_small(SimDev S, int 
 }
 
 template <int R>
-__global__ void __launch_bounds__(FT_THREADS, 2) k_conv_old_tiled(SimDev S, int s, int chunks)
+__global__ void __launch_bounds__(FT_THREADS, 2) k_conv_old_tiled(SimDev S, int s, int slots)
 {
     __shared__ double sx[FT_TILE], sz[FT_TILE], sg[FT_TILE], sv[FT_TILE];
     Step st;
     if (!step_begin(S, s, st)) return;
     SrcView W = wake_view(S, st.itev, st.ilev);
     const int nrows = W.n + 3;   // + the new TEV, the LEV if shed, the idle LEV slot: their rows need no solve either
-    if ((long)blockIdx.x * (FT_THREADS * R) >= nrows) return;
+    const TiledGeom G(nrows, W.n, R, slots);
+    if ((long)blockIdx.x * (FT_THREADS * R) >= nrows || (int)blockIdx.y >= G.chunks) return;
     TgtWakePlus TW;
     TW.W = W;
     place_tev(S, st.i, st.itev, TW.xt, TW.zt);
     place_lev(S, st.i, st.ilev, TW.xl, TW.zl);
-    int chunk_len = ((W.n + chunks - 1) / chunks + FT_TILE - 1) / FT_TILE * FT_TILE;
-    int c0 = blockIdx.y * chunk_len, c1 = min(W.n, c0 + chunk_len);
+    int c0 = blockIdx.y * G.chunk_len, c1 = min(W.n, c0 + G.chunk_len);
     size_t po = (size_t)blockIdx.y * nrows;
     fast_tiled_block<R>(W, TW, nrows, blockIdx.x, c0, c1, S.pb_u + po, S.pb_w + po, sx, sz, sg, sv);
 }
@@ -1010,13 +1026,13 @@ __global__ void __launch_bounds__(256) k_conv_new(SimDev S, int s)
     }
 }
 
-__global__ void __launch_bounds__(256) k_finish_ov(SimDev S, int s, int chunks)
+__global__ void __launch_bounds__(256) k_finish_ov(SimDev S, int s, int R, int slots)
 {
     extern __shared__ double sm[];
     Step st;
     if (!step_begin(S, s, st)) return;
     if (blockIdx.x == 0) {
-        phase_finish_loads(S, st, nullptr, sm, chunks, FINISH_STAGE, true);
+        phase_finish_loads(S, st, nullptr, sm, 1, FINISH_STAGE, true);
         return;
     }
     if (blockIdx.x == 1) {
@@ -1027,6 +1043,7 @@ __global__ void __launch_bounds__(256) k_finish_ov(SimDev S, int s, int chunks)
     const int i = st.i, nv = S.nv, nT = st.itev + 1, nL = st.ilev + 1;
     SrcView W = wake_view(S, nT, nL);
     const int nold = W.n - 2, npart = nold + 3;
+    const int chunks = TiledGeom(npart, nold, R, slots).chunks;
     const bool shed = S.lev_shed[i] != -1.0;
     const double dt = S.dt;
     for (long r = (long)(blockIdx.x - 2) * blockDim.x + threadIdx.x; r < W.n; r += (long)(gridDim.x - 2) * blockDim.x) {
@@ -1473,7 +1490,7 @@ static int bracket_of(long n)
 
 // Launch geometry of one step for every wake size up to 2^bracket.
 struct StepPlan {
-    int g1, g3, g4, g5, R, tchunks;
+    int g1, g3, g4, g5, R, tchunks, slots;
     bool tiled, ov;
     dim3 gto;
     dim3 gt;
@@ -1499,6 +1516,7 @@ static StepPlan plan_step(const ludvm_sim *s, int bracket)
     pl.tiled = D.mode != LUDVM_EXACT_F64 && nw >= SIM_TILED_MIN_WAKE;
     pl.ov = false;
     pl.g5 = 1;
+    pl.slots = 0;
     pl.R = 1;
     pl.tchunks = 0;
     pl.gt = dim3(1, 1);
@@ -1506,12 +1524,13 @@ static StepPlan plan_step(const ludvm_sim *s, int bracket)
         const long rows_up = D.P + nw;
         pl.R = rows_up >= 131072 ? 4 : (rows_up >= 32768 ? 2 : 1);
         const long row_blocks = (rows_up + FT_THREADS * pl.R - 1) / (FT_THREADS * pl.R);
-        pl.tchunks = (int)std::max<long>(1, std::min<long>(std::min<long>(SIM_TILED_CHUNKS_MAX, nw / (2 * FT_TILE)),
+        pl.tchunks = (int)std::max<long>(1, std::min<long>(std::min<long>(16, nw / (2 * FT_TILE)),
                                                            ((long)sm * 2 * 6 + row_blocks - 1) / row_blocks));
         pl.gt = dim3((unsigned)row_blocks, (unsigned)pl.tchunks + 1);
         // overlapped step: old-wake convection on a second graph branch beside phase 1 + solve
         pl.ov = D.P <= 256 && !getenv("LUDVM_NO_OVERLAP");
-        pl.gto = dim3((unsigned)((nw + 3 + FT_THREADS * pl.R - 1) / (FT_THREADS * pl.R)), (unsigned)pl.tchunks);
+        pl.gto = dim3((unsigned)((nw + 3 + FT_THREADS * pl.R - 1) / (FT_THREADS * pl.R)), (unsigned)SIM_TILED_CHUNKS_MAX);
+        pl.slots = sm * (pl.R == 1 ? 3 : 2);   // resident CTAs of k_conv_old_tiled<R>: 70 registers -> 3 per SM, 112-120 -> 2
         pl.g5 = 1 + (int)std::max<long>(1, std::min<long>((nw + 255) / 256, (long)sm * 8));
     }
     return pl;
@@ -1531,16 +1550,16 @@ static void enqueue_step_kernel(const ludvm_sim *s, const StepPlan &pl, int whic
     case 2:
         if (!pl.tiled) k_conv_partials<<<pl.g3, 256, 0, cs>>>(D, k);
         else if (pl.ov) {
-            if (pl.R == 4) k_conv_old_tiled<4><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
-            else if (pl.R == 2) k_conv_old_tiled<2><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
-            else k_conv_old_tiled<1><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
+            if (pl.R == 4) k_conv_old_tiled<4><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.slots);
+            else if (pl.R == 2) k_conv_old_tiled<2><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.slots);
+            else k_conv_old_tiled<1><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.slots);
         } else if (pl.R == 4) k_conv_partials_tiled<4><<<pl.gt, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
         else if (pl.R == 2) k_conv_partials_tiled<2><<<pl.gt, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
         else k_conv_partials_tiled<1><<<pl.gt, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
         break;
     case 4: k_conv_new<<<pl.g5, 256, 0, cs>>>(D, k); break;
     default:
-        if (pl.ov) k_finish_ov<<<pl.g4, 256, s->finish_smem, cs>>>(D, k, pl.tchunks);
+        if (pl.ov) k_finish_ov<<<pl.g4, 256, s->finish_smem, cs>>>(D, k, pl.R, pl.slots);
         else k_finish<<<pl.g4, 256, s->finish_smem, cs>>>(D, k, pl.tchunks);
         break;
     }
