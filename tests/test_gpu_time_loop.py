@@ -165,7 +165,7 @@ def test_free_vortex_heavy_run(oracle):
 
 
 def test_tiled_convection_matches_exact_mode():
-    """Wakes >= 8192 vortices take the shared-memory tiled convection kernel (fast mode, graph path).  9000 free
+    """Wakes >= 2048 vortices take the shared-memory tiled convection kernel (fast mode, graph path).  9000 free
     vortices put the wake there from step 0; the fast run must track the exact-mode run to rounding level."""
     from ludvm_b200 import LUDVM
     rng = np.random.default_rng(9)
