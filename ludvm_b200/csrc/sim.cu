@@ -1523,7 +1523,9 @@ static StepPlan plan_step(const ludvm_sim *s, int bracket)
     pl.gt = dim3(1, 1);
     if (pl.tiled) {
         const long rows_up = D.P + nw;
-        pl.R = rows_up >= 131072 ? 4 : (rows_up >= 32768 ? 2 : 1);
+        // rows per thread (measured on the dt = 2e-3 run: R = 1 only 5.48 s; R = 2 from 8192 rows 5.26 s; R = 4 from 16384-65536
+        // rows no better than R = 2)
+        pl.R = rows_up >= 131072 ? 4 : (rows_up >= 8192 ? 2 : 1);
         const long row_blocks = (rows_up + FT_THREADS * pl.R - 1) / (FT_THREADS * pl.R);
         pl.tchunks = (int)std::max<long>(1, std::min<long>(std::min<long>(16, nw / (2 * FT_TILE)),
                                                            ((long)sm * 2 * 6 + row_blocks - 1) / row_blocks));
