@@ -1218,6 +1218,68 @@ __device__ __noinline__ void cta_conv_partials(const SimDev &S, const Step &st)
 {
     phase_conv_partials(S, st, block_pool());
 }
+
+// Fast-mode convection of the one-CTA driver when the whole wake fits in shared memory (parameter sweeps: <= ~800
+// vortices): the lane-group tasks spend 3 loads per pair and are LSU-bound (48 % of the DFMA rate measured); here the
+// wake (x, z, Gamma/2pi) is staged once, every thread keeps R target rows in registers and the sources are broadcast
+// from shared memory -- 3 LDS per R pairs.  Writes complete row sums: pb_u/w[row] (one partial, what conv_fold
+// expects of this driver) for the gamma points ++ wake, foil_u/w[r] for the bound vortices on the wake.
+template <int R>
+__device__ __forceinline__ void cta_tiled_rows(const double *sx, const double *sz, const double *sg, int nsrc, double vc4,
+                                               const double *tx_, const double *tz_, int nrows, double *ou, double *ow)
+{
+    for (int base = 0; base < nrows; base += R * (int)blockDim.x) {
+        double tx[R], tz[R], au[R], aw[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int row = min(base + r * (int)blockDim.x + (int)threadIdx.x, nrows - 1);
+            tx[r] = tx_[row]; tz[r] = tz_[row];
+            au[r] = 0.0; aw[r] = 0.0;
+        }
+#pragma unroll 4
+        for (int j = 0; j < nsrc; j++) {
+            const double x = sx[j], z = sz[j], g = sg[j];
+#pragma unroll
+            for (int r = 0; r < R; r++) pair_fast(tx[r], tz[r], x, z, g, vc4, au[r], aw[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int row = base + r * (int)blockDim.x + (int)threadIdx.x;
+            if (row < nrows) { ou[row] = au[r]; ow[row] = aw[r]; }
+        }
+    }
+}
+
+__device__ __noinline__ void cta_conv_tiled_fast(const SimDev &S, const Step &st, double *smt)
+{
+    const int P = S.P, tid = threadIdx.x, nth = blockDim.x;
+    SrcView W = wake_view(S, st.itev + 1, st.ilev + 1);
+    const int n = W.n, nrows = P + n;
+    const double *gx = S.gp + ((size_t)st.i * 2 + 0) * P, *gz = S.gp + ((size_t)st.i * 2 + 1) * P;
+    const double *ga = S.g_airfoil + (size_t)st.itev * S.af_stride;
+    // shared layout: targets [P + n] (gamma points ++ wake), then the wake strengths [n] and the bound strengths [P];
+    // the wake's own coordinates are the tail of the target arrays
+    double *tx = smt, *tz = tx + nrows, *sgw = tz + nrows, *sgf = sgw + n;
+    __syncthreads();
+    for (int r = tid; r < nrows; r += nth) {
+        if (r < P) { tx[r] = gx[r]; tz[r] = gz[r]; sgf[r] = ga[r] * LUDVM_INV_TWO_PI; }
+        else {
+            int p = W.phys(r - P);
+            tx[r] = S.wx[p]; tz[r] = S.wz[p]; sgw[r - P] = S.wg[p] * LUDVM_INV_TWO_PI;
+        }
+    }
+    __syncthreads();
+    if (nrows > 2 * nth) {
+        cta_tiled_rows<4>(tx + P, tz + P, sgw, n, S.vc4, tx, tz, nrows, S.pb_u, S.pb_w);
+        cta_tiled_rows<4>(tx, tz, sgf, P, S.vc4, tx + P, tz + P, n, S.foil_u, S.foil_w);
+    } else if (nrows > nth) {
+        cta_tiled_rows<2>(tx + P, tz + P, sgw, n, S.vc4, tx, tz, nrows, S.pb_u, S.pb_w);
+        cta_tiled_rows<2>(tx, tz, sgf, P, S.vc4, tx + P, tz + P, n, S.foil_u, S.foil_w);
+    } else {
+        cta_tiled_rows<1>(tx + P, tz + P, sgw, n, S.vc4, tx, tz, nrows, S.pb_u, S.pb_w);
+        cta_tiled_rows<1>(tx, tz, sgf, P, S.vc4, tx + P, tz + P, n, S.foil_u, S.foil_w);
+    }
+}
 __device__ __noinline__ void cta_finish_update(const SimDev &S, const Step &st)
 {
     phase_finish_update(S, st, threadIdx.x, blockDim.x, 0);
@@ -1266,7 +1328,11 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1) k_sim_cta(con
             phase_solve<METHOD>(S, st, tab, scr, nullptr, false);
             __syncthreads();
             CTA_T(1);
-            cta_conv_partials(S, st);
+            // fast mode with the wake in shared memory: 3 (P + n) + P doubles of the scratch area
+            if (S.mode != LUDVM_EXACT_F64 && 3 * (S.P + st.itev + st.ilev + 2 + S.nfree) + S.P <= SOLVE_SCRATCH_DOUBLES(S.P, S.Nc, S.sum_nodes))
+                cta_conv_tiled_fast(S, st, scr);
+            else
+                cta_conv_partials(S, st);
             __syncthreads();
             CTA_T(2);
             phase_finish_loads(S, st, tab, scr, 0, S.sum_nodes);
