@@ -65,3 +65,22 @@ def test_sweep_slices_and_fast_mode():
     assert biteq(np.concatenate([lo["Cl"], hi["Cl"]]), full["Cl"])
     fast = sweep.run_sweep(cases, mode="fast")
     assert np.max(np.abs(fast["Cl"][:, :40] - full["Cl"][:, :40])) < 1e-10
+
+
+def test_sweep_with_many_free_vortices_covers_the_wide_shared_memory_tiles(oracle):
+    """700 free vortices from step 0 put > 512 target rows into the one-CTA driver at once, i.e. the 4-rows-per-thread
+    variant of its shared-memory convection (fast mode); exact mode of the same sweep stays bit-equal to the oracle."""
+    from ludvm_b200 import sweep
+    rng = np.random.default_rng(13)
+    nf = 700
+    xy = np.stack([rng.uniform(-4.0, -0.5, nf), rng.uniform(-0.6, 0.6, nf)])
+    gam = rng.standard_normal(nf) * 2e-3
+    base = dict(README, tf=1, circulation_freevort=gam, xy_freevort=xy)
+    cases = [dict(base, LESPcrit=0.15), dict(base, LESPcrit=0.3, k=0.5)]
+    ex, fa = sweep.run_sweep(cases, mode="exact"), sweep.run_sweep(cases, mode="fast")
+    o = oracle.OracleLUDVM(**cases[1])
+    for k in ("L", "M", "LESP", "LEV_shed"):
+        assert biteq(ex[k][1], getattr(o, k)), k
+    for k in ("L", "D", "M"):
+        assert np.max(np.abs(fa[k] - ex[k])) <= 1e-10 * np.max(np.abs(ex[k])), k
+    assert biteq(fa["LEV_shed"], ex["LEV_shed"])
