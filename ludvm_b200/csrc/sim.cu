@@ -16,14 +16,21 @@
 //                        (convection), plus the bound vortices on the wake               (LUDVM.py:1049-1054, 1095-1124)
 //   phase_finish_*       loads Fn, Fs, L, D, T, M; fold partials, forward-Euler update in place, history snapshot
 //                                                                                         (LUDVM.py:1069-1090, 1108-1127)
-// and two drivers run them:
+// and three drivers run them:
+//   * coop path   -- k_sim_coop: one persistent cooperative grid (one CTA per SM) runs all steps while the wake is
+//                    small (latency-bound), grid barriers between the phases, the solve CTA's tables resident in
+//                    shared memory.
 //   * graph path  -- four kernels per step, grid-wide warp pools, K steps captured once in a CUDA graph and replayed
 //                    (step index and vortex counts are read from device memory; graphs cached per power-of-two
-//                    bracket of the wake size).  Used for one simulation of any size (configs 1, 2).
+//                    bracket of the wake size).  In fast mode with wakes >= SIM_TILED_MIN_WAKE the step is the
+//                    overlapped one: the old wake's self-convection (shared-memory tiled kernel) on a second graph
+//                    branch beside phase 1 + solve.
 //   * CTA path    -- k_sim_cta: one persistent CTA runs ALL steps of one case with __syncthreads() between phases;
 //                    cases are pulled from an atomic counter.  Used for batched parameter sweeps (config 4: 4096
 //                    independent cases, no collective) and for method='Ramesh', whose Newton loops have a
 //                    data-dependent trip count.
+// The once-per-step scalar reductions live in block_reduce.cuh.  -DLUDVM_TRACE adds clock64 phase traces (scripts/
+// solve_trace.py); it is off in the shipped library.
 #include <algorithm>
 #include <chrono>
 #include <map>
@@ -421,7 +428,6 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *tab, double
                             bool stage_now)
 {
     const int P = S.P, Nc = S.Nc, tid = threadIdx.x, nth = blockDim.x;
-    const int lane8 = tid & 7, grp = tid >> 3, ngrp = nth >> 3;
     const int i = st.i, itev = st.itev, ilev = st.ilev, nv = S.nv;
     const StepTables t(tab, S);
     const SolveSmem m(sm, P, Nc);
