@@ -14,7 +14,7 @@ data = [r for r in rows if len(r) == len(hdr) and r[0] != "Address"]
 col = {h: i for i, h in enumerate(hdr)}
 stalls = collections.Counter()
 for h, i in col.items():
-    if h.startswith("stall_"):
+    if h.startswith("stall_") and "Not Issued" not in h:
         stalls[h] = sum(int(float(r[i] or 0)) for r in data)
 ops = collections.Counter()
 ie = col.get("Instructions Executed")
