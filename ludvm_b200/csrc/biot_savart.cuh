@@ -246,12 +246,21 @@ __device__ __forceinline__ double fast_combine_row(const double *part, int nrows
 // ---------------------------------------------------------------------------------------------------
 #define FT_THREADS 256
 #define FT_TILE 512
+#ifndef FT_UNROLL
+#define FT_UNROLL 4       // source-loop unroll of the thread-staged tiled block
+#endif
+#ifndef FT_UNROLL_TMA
+#define FT_UNROLL_TMA 2   // source-loop unroll of the TMA-staged kernel.  Measured at N = 2^20 (ms per step): 1: 905.5, 2: 872.6,
+                          // 3: 874.2, 4: 903.2, 6: 890.8, 8: 875.1, 16: 871.8 -- not monotonic (instruction scheduling), 2 is the
+                          // smallest code among the fast ones
+#endif
 
 template <int R, class Tgt>
 __device__ __forceinline__ void fast_tiled_block(const SrcView &S, const Tgt &T, int nrows, int row_block, int c0,
                                                  int c1, double *__restrict__ pu, double *__restrict__ pw_,
                                                  double *sx, double *sz, double *sg, double *sv)
 {
+    constexpr int UNROLL = R <= 2 ? 8 : FT_UNROLL;   // few rows per thread: a deeper unroll supplies the independent chains
     double tx[R], tz[R], au[R], aw[R];
     int base = row_block * (FT_THREADS * R) + threadIdx.x;
 #pragma unroll
@@ -274,7 +283,7 @@ __device__ __forceinline__ void fast_tiled_block(const SrcView &S, const Tgt &T,
         }
         __syncthreads();
         const int cnt = min(FT_TILE, c1 - t0);   // a ragged last tile costs only its own sources
-#pragma unroll 4
+#pragma unroll UNROLL
         for (int j = 0; j < cnt; j++) {
             double x = sx[j], z = sz[j], g = sg[j], v = sv[j];
 #pragma unroll
@@ -339,6 +348,7 @@ __device__ __forceinline__ void fast_tiled_block_tma(const SrcView &S, const Tgt
                                                      int c1, double *__restrict__ pu, double *__restrict__ pw_,
                                                      TmaTiles &sm)
 {
+    constexpr int UNROLL_TMA = FT_UNROLL_TMA;
     double tx[R], tz[R], au[R], aw[R];
     int base = row_block * (FT_THREADS * R) + threadIdx.x;
 #pragma unroll
@@ -383,7 +393,7 @@ __device__ __forceinline__ void fast_tiled_block_tma(const SrcView &S, const Tgt
         if (cnt != FT_TILE) __syncthreads();  // thread-filled tile: make every thread's stores visible
         mbar_wait(&sm.full[st], (k >> 1) & 1);
         const double *sx = sm.buf[st][0], *sz = sm.buf[st][1], *sg = sm.buf[st][2];
-#pragma unroll 4
+#pragma unroll UNROLL_TMA
         for (int j = 0; j < cnt; j++) {
             double x = sx[j], z = sz[j], g = sg[j];
 #pragma unroll
