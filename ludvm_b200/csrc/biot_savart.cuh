@@ -249,6 +249,9 @@ __device__ __forceinline__ double fast_combine_row(const double *part, int nrows
 #ifndef FT_UNROLL
 #define FT_UNROLL 4       // source-loop unroll of the thread-staged tiled block
 #endif
+#ifndef FT_UNROLL32
+#define FT_UNROLL32 4     // source-loop unroll of the packed fp32x2 block
+#endif
 #ifndef FT_UNROLL_TMA
 #define FT_UNROLL_TMA 2   // source-loop unroll of the TMA-staged kernel.  Measured at N = 2^20 (ms per step): 1: 905.5, 2: 872.6,
                           // 3: 874.2, 4: 903.2, 6: 890.8, 8: 875.1, 16: 871.8 -- not monotonic (instruction scheduling), 2 is the
@@ -487,6 +490,7 @@ __device__ __forceinline__ void fast32x2_tiled_block(const SrcView &S, const Tgt
                                                      int c1, double *__restrict__ pu, double *__restrict__ pw_,
                                                      Src32x2 *ssrc)
 {
+    constexpr int UNROLL32 = FT_UNROLL32;
     constexpr int R = 2 * RP;
     float2 tx[RP], tz[RP];
     double au[R], aw[R];
@@ -520,7 +524,7 @@ __device__ __forceinline__ void fast32x2_tiled_block(const SrcView &S, const Tgt
         float2 fu[RP], fw[RP];
 #pragma unroll
         for (int r = 0; r < RP; r++) fu[r] = fw[r] = make_float2(0.f, 0.f);
-#pragma unroll 4
+#pragma unroll UNROLL32
         for (int j = 0; j < FT_TILE; j++) {
             const Src32x2 v = ssrc[j];
 #pragma unroll
