@@ -61,11 +61,43 @@ struct TgtGrid {
 // ---------------------------------------------------------------------------------------------------
 // exact lane-group
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void exact_term(const SrcView &S, double xp, double zp, int j, double &tu, double &tw)
+struct ExactSrc { double x, z, g, vc4; };
+__device__ __forceinline__ ExactSrc exact_load(const SrcView &S, int j)
 {
     int p = S.phys(j);
-    double vc4 = S.vc4 ? S.vc4[p] : S.vc4s;
-    pair_exact(xp, zp, S.x[p], S.z[p], S.g[p * S.gstride], vc4, tu, tw);
+    ExactSrc s;
+    s.vc4 = S.vc4 ? S.vc4[p] : S.vc4s;
+    s.x = S.x[p]; s.z = S.z[p]; s.g = S.g[p * S.gstride];
+    return s;
+}
+__device__ __forceinline__ void exact_term(const SrcView &S, double xp, double zp, int j, double &tu, double &tw)
+{
+    ExactSrc s = exact_load(S, j);
+    pair_exact(xp, zp, s.x, s.z, s.g, s.vc4, tu, tw);
+}
+
+// K consecutive terms of one lane's accumulator (sources j0, j0+8, ...): branch-free fast paths so the K div/sqrt
+// chains interleave, library routines only if a range flag came back set; the adds keep numpy's order.
+template <int K>
+__device__ __forceinline__ void exact_batch(const SrcView &S, double xp, double zp, int j0, double &au, double &aw)
+{
+    double xw[K], zw[K], g[K], vc4[K], xps[K], zps[K], tu[K], tw[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        ExactSrc s = exact_load(S, j0 + 8 * k);
+        xw[k] = s.x; zw[k] = s.z; g[k] = s.g; vc4[k] = s.vc4; xps[k] = xp; zps[k] = zp;
+    }
+    bool bad = false;
+    pair_exact_try_batch<K>(xps, zps, xw, zw, g, vc4, tu, tw, bad);
+    if (bad) {
+#pragma unroll
+        for (int k = 0; k < K; k++) pair_exact_ref(xp, zp, xw[k], zw[k], g[k], vc4[k], tu[k], tw[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        au = __dadd_rn(au, tu[k]);
+        aw = __dadd_rn(aw, tw[k]);
+    }
 }
 
 // One leaf (n <= 128) of numpy's pairwise sum, evaluated by the 8 lanes of a group.  Result on every lane.
@@ -74,25 +106,16 @@ __device__ __forceinline__ void exact_leaf_group(const SrcView &S, double xp, do
 {
     const unsigned full = 0xffffffffu;
     int body = (m >= 8) ? (m & ~7) : 0;
-    double au = -0.0, aw = -0.0;
+    double au = -0.0, aw = -0.0;   // -0.0 + t == t bit for bit: the lane's first term needs no special case
     if (body) {
-        exact_term(S, xp, zp, off + lane8, au, aw);
-        int i = 8;
-        // four independent pair evaluations in flight (the div/sqrt chains are long); the adds keep numpy's order
-        for (; i + 24 < body; i += 32) {
-            double t0u, t0w, t1u, t1w, t2u, t2w, t3u, t3w;
-            exact_term(S, xp, zp, off + i + lane8, t0u, t0w);
-            exact_term(S, xp, zp, off + i + 8 + lane8, t1u, t1w);
-            exact_term(S, xp, zp, off + i + 16 + lane8, t2u, t2w);
-            exact_term(S, xp, zp, off + i + 24 + lane8, t3u, t3w);
-            au = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(au, t0u), t1u), t2u), t3u);
-            aw = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(aw, t0w), t1w), t2w), t3w);
-        }
-        for (; i < body; i += 8) {
-            double tu, tw;
-            exact_term(S, xp, zp, off + i + lane8, tu, tw);
-            au = __dadd_rn(au, tu);
-            aw = __dadd_rn(aw, tw);
+        const int nb = body >> 3;  // terms per lane, uniform across the warp
+        int b = 0;
+        for (; b + 4 <= nb; b += 4) exact_batch<4>(S, xp, zp, off + 8 * b + lane8, au, aw);
+        switch (nb - b) {
+        case 3: exact_batch<3>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
+        case 2: exact_batch<2>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
+        case 1: exact_batch<1>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
+        default: break;
         }
 #pragma unroll
         for (int s = 1; s < 8; s <<= 1) {
