@@ -7,14 +7,21 @@ namespace ludvm {
 // ---------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------
-template <class Tgt>
+template <int R, class Tgt>
 __global__ void __launch_bounds__(256) k_exact_rows(SrcView S, Tgt T, int nrows, int d, double *pu, double *pw_)
 {
     int lane = threadIdx.x & 31;
     long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     long nwarps = (long)gridDim.x * (blockDim.x >> 5);
-    long ntasks = (long)((nrows + 3) >> 2) << d;
-    for (long t = gw; t < ntasks; t += nwarps) exact_rows_warp_task(S, T, nrows, d, t, lane, pu, pw_);
+    long ntasks = (long)((nrows + 4 * R - 1) / (4 * R)) << d;
+    for (long t = gw; t < ntasks; t += nwarps) exact_rows_warp_task<R>(S, T, nrows, d, t, lane, pu, pw_);
+}
+
+template <class Tgt>
+__global__ void __launch_bounds__(ET_THREADS, 3) k_exact_tiled(SrcView S, Tgt T, int nrows, int d, double *pu, double *pw_)
+{
+    __shared__ __align__(16) double2 sxz[ET_TILE], sgv[ET_TILE];
+    exact_tiled_block(S, T, nrows, blockIdx.x, d, blockIdx.y, pu, pw_, sxz, sgv);
 }
 
 template <class Tgt>
@@ -160,7 +167,27 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
 {
     const int sm = ctx->sm_count;
     if (mode == LUDVM_EXACT_F64) {
-        long nquads = (nrows + 3) / 4;
+        if (nrows >= 4096 && S.n >= 1024) {
+            // Many rows: one thread per row, sources staged through shared memory; the tree is cut at depth d so
+            // that ~4 waves of 3 CTAs/SM are in flight.
+            long rblocks = (nrows + ET_THREADS - 1) / ET_THREADS;
+            int want = ilog2_ceil(std::max(1L, (long)sm * 12 / rblocks));
+            int d = std::min(pw_max_depth(S.n), want);
+            size_t bytes = sizeof(double) * (size_t)nrows * ((size_t)1 << d);
+            void *a, *b;
+            int rc;
+            if ((rc = scratch_reserve(ctx, slot, bytes, &a))) return rc;
+            if ((rc = scratch_reserve(ctx, slot + 1, bytes, &b))) return rc;
+            k_exact_tiled<<<dim3((unsigned)rblocks, 1u << d), ET_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, d, (double *)a,
+                                                                                            (double *)b);
+            ctx->launches++;
+            *pu = (double *)a; *pw_ = (double *)b; *nfold = d;
+            return LUDVM_OK;
+        }
+        // Few rows: 8 lanes per row.  R target rows per 8-lane group: two when there are plenty of rows (a loaded
+        // source then serves two pair evaluations), one when parallelism matters more.
+        const int R = nrows >= (long)sm * 512 ? 2 : 1;
+        long nquads = (nrows + 4 * R - 1) / (4 * R);
         int want = ilog2_ceil(std::max(1L, (long)sm * 64 / std::max(1L, nquads)));
         int d = std::min(pw_max_depth(S.n), want);
         size_t bytes = sizeof(double) * (size_t)nrows * ((size_t)1 << d);
@@ -170,7 +197,8 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
         if ((rc = scratch_reserve(ctx, slot + 1, bytes, &b))) return rc;
         long ntasks = nquads << d;
         int blocks = (int)std::min((ntasks + 7) / 8, (long)sm * 16);
-        k_exact_rows<<<blocks, 256, 0, ctx->stream>>>(S, T, (int)nrows, d, (double *)a, (double *)b);
+        if (R == 2) k_exact_rows<2><<<blocks, 256, 0, ctx->stream>>>(S, T, (int)nrows, d, (double *)a, (double *)b);
+        else k_exact_rows<1><<<blocks, 256, 0, ctx->stream>>>(S, T, (int)nrows, d, (double *)a, (double *)b);
         ctx->launches++;
         *pu = (double *)a; *pw_ = (double *)b; *nfold = d;
         return LUDVM_OK;

@@ -76,73 +76,95 @@ __device__ __forceinline__ void exact_term(const SrcView &S, double xp, double z
     pair_exact(xp, zp, s.x, s.z, s.g, s.vc4, tu, tw);
 }
 
-// K consecutive terms of one lane's accumulator (sources j0, j0+8, ...): branch-free fast paths so the K div/sqrt
-// chains interleave, library routines only if a range flag came back set; the adds keep numpy's order.
-template <int K>
-__device__ __forceinline__ void exact_batch(const SrcView &S, double xp, double zp, int j0, double &au, double &aw)
+// K consecutive terms (sources j0, j0+8, ...) of one lane's accumulators for its R target rows: branch-free fast
+// paths so the R*K div/sqrt chains interleave, library routines only if a range flag came back set; the adds keep
+// numpy's order.  A source is loaded once for the lane's R rows.
+template <int R, int K>
+__device__ __forceinline__ void exact_batch(const SrcView &S, const double (&xp)[R], const double (&zp)[R], int j0,
+                                            double (&au)[R], double (&aw)[R])
 {
-    double xw[K], zw[K], g[K], vc4[K], xps[K], zps[K], tu[K], tw[K];
+    double xw[R * K], zw[R * K], g[R * K], vc4[R * K], xps[R * K], zps[R * K], tu[R * K], tw[R * K];
 #pragma unroll
     for (int k = 0; k < K; k++) {
         ExactSrc s = exact_load(S, j0 + 8 * k);
-        xw[k] = s.x; zw[k] = s.z; g[k] = s.g; vc4[k] = s.vc4; xps[k] = xp; zps[k] = zp;
-    }
-    bool bad = false;
-    pair_exact_try_batch<K>(xps, zps, xw, zw, g, vc4, tu, tw, bad);
-    if (bad) {
 #pragma unroll
-        for (int k = 0; k < K; k++) pair_exact_ref(xp, zp, xw[k], zw[k], g[k], vc4[k], tu[k], tw[k]);
+        for (int r = 0; r < R; r++) {
+            xw[k * R + r] = s.x; zw[k * R + r] = s.z; g[k * R + r] = s.g; vc4[k * R + r] = s.vc4;
+            xps[k * R + r] = xp[r]; zps[k * R + r] = zp[r];
+        }
+    }
+    unsigned worst = 0;
+    pair_exact_try_batch<R * K>(xps, zps, xw, zw, g, vc4, tu, tw, worst);
+    if (ex_bad(worst)) {
+#pragma unroll
+        for (int c = 0; c < R * K; c++) pair_exact_ref(xps[c], zps[c], xw[c], zw[c], g[c], vc4[c], tu[c], tw[c]);
     }
 #pragma unroll
-    for (int k = 0; k < K; k++) {
-        au = __dadd_rn(au, tu[k]);
-        aw = __dadd_rn(aw, tw[k]);
-    }
+    for (int k = 0; k < K; k++)
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            au[r] = __dadd_rn(au[r], tu[k * R + r]);
+            aw[r] = __dadd_rn(aw[r], tw[k * R + r]);
+        }
 }
 
-// One leaf (n <= 128) of numpy's pairwise sum, evaluated by the 8 lanes of a group.  Result on every lane.
-__device__ __forceinline__ void exact_leaf_group(const SrcView &S, double xp, double zp, int off, int m, int lane8,
-                                                 double &ru, double &rw)
+// One leaf (n <= 128) of numpy's pairwise sum for the R rows of each 8-lane group.  Result on every lane.
+template <int R>
+__device__ __forceinline__ void exact_leaf_group(const SrcView &S, const double (&xp)[R], const double (&zp)[R],
+                                                 int off, int m, int lane8, double (&au)[R], double (&aw)[R])
 {
+    constexpr int K = 4 / R;   // four chains in flight per thread
     const unsigned full = 0xffffffffu;
     int body = (m >= 8) ? (m & ~7) : 0;
-    double au = -0.0, aw = -0.0;   // -0.0 + t == t bit for bit: the lane's first term needs no special case
+#pragma unroll
+    for (int r = 0; r < R; r++) au[r] = aw[r] = -0.0;   // -0.0 + t == t bit for bit: no special case for the first term
     if (body) {
         const int nb = body >> 3;  // terms per lane, uniform across the warp
         int b = 0;
-        for (; b + 4 <= nb; b += 4) exact_batch<4>(S, xp, zp, off + 8 * b + lane8, au, aw);
-        switch (nb - b) {
-        case 3: exact_batch<3>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
-        case 2: exact_batch<2>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
-        case 1: exact_batch<1>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
-        default: break;
+        for (; b + K <= nb; b += K) exact_batch<R, K>(S, xp, zp, off + 8 * b + lane8, au, aw);
+        if (K == 4) {
+            switch (nb - b) {
+            case 3: exact_batch<R, 3>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
+            case 2: exact_batch<R, 2>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
+            case 1: exact_batch<R, 1>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
+            default: break;
+            }
+        } else if (nb - b) {
+            exact_batch<R, 1>(S, xp, zp, off + 8 * b + lane8, au, aw);
         }
 #pragma unroll
-        for (int s = 1; s < 8; s <<= 1) {
-            au = __dadd_rn(au, __shfl_xor_sync(full, au, s));
-            aw = __dadd_rn(aw, __shfl_xor_sync(full, aw, s));
-        }
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int s = 1; s < 8; s <<= 1) {
+                au[r] = __dadd_rn(au[r], __shfl_xor_sync(full, au[r], s));
+                aw[r] = __dadd_rn(aw[r], __shfl_xor_sync(full, aw[r], s));
+            }
     }
     int rem = m - body;  // 0..7, uniform across the warp
     if (rem) {
-        double tu = 0.0, tw = 0.0;
-        if (lane8 < rem) exact_term(S, xp, zp, off + body + lane8, tu, tw);
-        for (int t = 0; t < rem; t++) {
-            au = __dadd_rn(au, __shfl_sync(full, tu, t, 8));
-            aw = __dadd_rn(aw, __shfl_sync(full, tw, t, 8));
+        double tu[R], tw[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            tu[r] = tw[r] = 0.0;
+            if (lane8 < rem) exact_term(S, xp[r], zp[r], off + body + lane8, tu[r], tw[r]);
         }
+        for (int t = 0; t < rem; t++)
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                au[r] = __dadd_rn(au[r], __shfl_sync(full, tu[r], t, 8));
+                aw[r] = __dadd_rn(aw[r], __shfl_sync(full, tw[r], t, 8));
+            }
     }
-    ru = au;
-    rw = aw;
 }
 
-// Pairwise sum over the logical source range [off, off+n) -- a node of the tree -- for the group's target.
+// Pairwise sum over the logical source range [off, off+n) -- a node of the tree -- for the group's R targets.
 // Must be called by all 32 lanes with identical (off, n).
-__device__ inline void exact_node_group(const SrcView &S, double xp, double zp, int off, int n, int lane8,
-                                        double &su, double &sw)
+template <int R>
+__device__ inline void exact_node_group(const SrcView &S, const double (&xp)[R], const double (&zp)[R], int off, int n,
+                                        int lane8, double (&su)[R], double (&sw)[R])
 {
     int r_off[PW_MAX_STACK], r_len[PW_MAX_STACK];
-    double l_u[PW_MAX_STACK], l_w[PW_MAX_STACK];
+    double l_u[PW_MAX_STACK][R], l_w[PW_MAX_STACK][R];
     unsigned has_l = 0;
     int sp = 0;
     for (;;) {
@@ -154,13 +176,165 @@ __device__ inline void exact_node_group(const SrcView &S, double xp, double zp, 
             sp++;
             n = n2;
         }
-        double ru, rw;
-        exact_leaf_group(S, xp, zp, off, n, lane8, ru, rw);
+        double ru[R], rw[R];
+        exact_leaf_group<R>(S, xp, zp, off, n, lane8, ru, rw);
         for (;;) {
             if (sp == 0) {
-                su = ru;
-                sw = rw;
+#pragma unroll
+                for (int r = 0; r < R; r++) { su[r] = ru[r]; sw[r] = rw[r]; }
                 return;
+            }
+            if (!((has_l >> (sp - 1)) & 1u)) {
+#pragma unroll
+                for (int r = 0; r < R; r++) { l_u[sp - 1][r] = ru[r]; l_w[sp - 1][r] = rw[r]; }
+                has_l |= 1u << (sp - 1);
+                off = r_off[sp - 1];
+                n = r_len[sp - 1];
+                break;
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                ru[r] = __dadd_rn(l_u[sp - 1][r], ru[r]);
+                rw[r] = __dadd_rn(l_w[sp - 1][r], rw[r]);
+            }
+            sp--;
+        }
+    }
+}
+
+// Warp task t -> (tree node b, row group q of 4*R rows: 8-lane group k owns rows q*4R + k*R .. +R).
+// Partials: pu[b * nrows + row].
+template <int R = 1, class Tgt>
+__device__ __forceinline__ void exact_rows_warp_task(const SrcView &S, const Tgt &T, int nrows, int d, long t,
+                                                     int lane, double *__restrict__ pu, double *__restrict__ pw_)
+{
+    int ngroups = (nrows + 4 * R - 1) / (4 * R);
+    int b = (int)(t / ngroups);
+    int q = (int)(t - (long)b * ngroups);
+    int row0 = (q * 4 + (lane >> 3)) * R;
+    double xp[R], zp[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) T.get(min(row0 + r, nrows - 1), xp[r], zp[r]);
+    int off, len;
+    pw_node(S.n, d, b, off, len);
+    double su[R], sw[R];
+    exact_node_group<R>(S, xp, zp, off, len, lane & 7, su, sw);
+    if ((lane & 7) == 0) {
+#pragma unroll
+        for (int r = 0; r < R; r++)
+            if (row0 + r < nrows) {
+                pu[(size_t)b * nrows + row0 + r] = su[r];
+                pw_[(size_t)b * nrows + row0 + r] = sw[r];
+            }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// exact tiled: many target rows.  ONE THREAD owns one target row and all eight accumulators r0..r7 of numpy's
+// unrolled leaf loop in registers; the sources of the block's tree node are staged through shared memory in tiles
+// and broadcast to the warp (two LDS.128 per source serve 32 pairs), so the per-pair instruction overhead of the
+// lane-group form -- per-lane global loads, index mapping, shuffles -- disappears and the kernel is bound by the
+// FP64 pipe rather than by instruction issue.  Four consecutive sources go to four different accumulators: four
+// independent div/sqrt chains per thread without reordering a single addition.  The traversal of the tree is
+// uniform across the block (it depends on the node only).  Same partial layout as the lane-group kernel.
+// ---------------------------------------------------------------------------------------------------
+#define ET_THREADS 128
+#define ET_TILE 1024   // sources per staged tile (a leaf is <= 128): 32 KB of shared memory
+
+// au[k] += term(source j0 + k), k = 0..3, for one target.
+__device__ __forceinline__ void exact_quad_smem(const double2 *__restrict__ sxz, const double2 *__restrict__ sgv,
+                                                double xp, double zp, double &u0, double &u1, double &u2, double &u3,
+                                                double &w0, double &w1, double &w2, double &w3)
+{
+    double xw[4], zw[4], g[4], vc4[4], xps[4], zps[4], tu[4], tw[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const double2 a = sxz[k], b = sgv[k];
+        xw[k] = a.x; zw[k] = a.y; g[k] = b.x; vc4[k] = b.y; xps[k] = xp; zps[k] = zp;
+    }
+    unsigned worst = 0;
+    pair_exact_try_batch<4>(xps, zps, xw, zw, g, vc4, tu, tw, worst);
+    if (ex_bad(worst)) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) pair_exact_ref(xp, zp, xw[k], zw[k], g[k], vc4[k], tu[k], tw[k]);
+    }
+    u0 = __dadd_rn(u0, tu[0]); u1 = __dadd_rn(u1, tu[1]); u2 = __dadd_rn(u2, tu[2]); u3 = __dadd_rn(u3, tu[3]);
+    w0 = __dadd_rn(w0, tw[0]); w1 = __dadd_rn(w1, tw[1]); w2 = __dadd_rn(w2, tw[2]); w3 = __dadd_rn(w3, tw[3]);
+}
+
+// One leaf (m <= 128 staged sources) of numpy's pairwise sum for the thread's target.
+__device__ __forceinline__ void exact_leaf_thread(const double2 *__restrict__ sxz, const double2 *__restrict__ sgv, int m,
+                                                  double xp, double zp, double &ru, double &rw)
+{
+    const int body = (m >= 8) ? (m & ~7) : 0;
+    double su = -0.0, sw = -0.0;
+    if (body) {
+        double u[8], w[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) u[k] = w[k] = -0.0;   // -0.0 + t == t bit for bit
+        for (int i = 0; i < body; i += 8) {
+            exact_quad_smem(sxz + i, sgv + i, xp, zp, u[0], u[1], u[2], u[3], w[0], w[1], w[2], w[3]);
+            exact_quad_smem(sxz + i + 4, sgv + i + 4, xp, zp, u[4], u[5], u[6], u[7], w[4], w[5], w[6], w[7]);
+        }
+        su = __dadd_rn(__dadd_rn(__dadd_rn(u[0], u[1]), __dadd_rn(u[2], u[3])),
+                       __dadd_rn(__dadd_rn(u[4], u[5]), __dadd_rn(u[6], u[7])));
+        sw = __dadd_rn(__dadd_rn(__dadd_rn(w[0], w[1]), __dadd_rn(w[2], w[3])),
+                       __dadd_rn(__dadd_rn(w[4], w[5]), __dadd_rn(w[6], w[7])));
+    }
+    for (int i = body; i < m; i++) {   // <= 7 tail terms, in order
+        const double2 a = sxz[i], b = sgv[i];
+        double tu, tw;
+        pair_exact(xp, zp, a.x, a.y, b.x, b.y, tu, tw);
+        su = __dadd_rn(su, tu);
+        sw = __dadd_rn(sw, tw);
+    }
+    ru = su;
+    rw = sw;
+}
+
+template <class Tgt>
+__device__ __forceinline__ void exact_tiled_block(const SrcView &S, const Tgt &T, int nrows, int row_block, int d, int b,
+                                                  double *__restrict__ pu, double *__restrict__ pw_, double2 *sxz,
+                                                  double2 *sgv)
+{
+    const int row = row_block * ET_THREADS + threadIdx.x;
+    double xp, zp;
+    T.get(min(row, nrows - 1), xp, zp);
+    int off, n;
+    pw_node(S.n, d, b, off, n);
+    const int node_end = off + n;
+    int tile0 = off, tile1 = off;   // staged logical source range
+    int r_off[PW_MAX_STACK], r_len[PW_MAX_STACK];
+    double l_u[PW_MAX_STACK], l_w[PW_MAX_STACK];
+    unsigned has_l = 0;
+    int sp = 0;
+    double ru, rw;
+    for (;;) {
+        while (n > PW_BLOCK) {
+            int n2 = pw_left(n);
+            r_off[sp] = off + n2;
+            r_len[sp] = n - n2;
+            has_l &= ~(1u << sp);
+            sp++;
+            n = n2;
+        }
+        if (off + n > tile1) {   // uniform across the block: leaves come in increasing source order
+            __syncthreads();
+            tile0 = off;
+            tile1 = min(off + ET_TILE, node_end);
+            for (int j = threadIdx.x; j < tile1 - tile0; j += ET_THREADS) {
+                int p = S.phys(tile0 + j);
+                sxz[j] = make_double2(S.x[p], S.z[p]);
+                sgv[j] = make_double2(S.g[p * S.gstride], S.vc4 ? S.vc4[p] : S.vc4s);
+            }
+            __syncthreads();
+        }
+        exact_leaf_thread(sxz + (off - tile0), sgv + (off - tile0), n, xp, zp, ru, rw);
+        bool done = false;
+        for (;;) {
+            if (sp == 0) {
+                done = true;
+                break;
             }
             if (!((has_l >> (sp - 1)) & 1u)) {
                 l_u[sp - 1] = ru;
@@ -174,28 +348,11 @@ __device__ inline void exact_node_group(const SrcView &S, double xp, double zp, 
             rw = __dadd_rn(l_w[sp - 1], rw);
             sp--;
         }
+        if (done) break;
     }
-}
-
-// Warp task t -> (tree node b, row quad q).  Partials: pu[b * nrows + row].
-template <class Tgt>
-__device__ __forceinline__ void exact_rows_warp_task(const SrcView &S, const Tgt &T, int nrows, int d, long t,
-                                                     int lane, double *__restrict__ pu, double *__restrict__ pw_)
-{
-    int nquads = (nrows + 3) >> 2;
-    int b = (int)(t / nquads);
-    int q = (int)(t - (long)b * nquads);
-    int row = q * 4 + (lane >> 3);
-    bool valid = row < nrows;
-    double xp, zp;
-    T.get(valid ? row : nrows - 1, xp, zp);
-    int off, len;
-    pw_node(S.n, d, b, off, len);
-    double su, sw;
-    exact_node_group(S, xp, zp, off, len, lane & 7, su, sw);
-    if (valid && (lane & 7) == 0) {
-        pu[(size_t)b * nrows + row] = su;
-        pw_[(size_t)b * nrows + row] = sw;
+    if (row < nrows) {
+        pu[(size_t)b * nrows + row] = ru;
+        pw_[(size_t)b * nrows + row] = rw;
     }
 }
 

@@ -2,7 +2,7 @@
 // ddiv2_rn_try, and the stage-by-stage pair_exact_try_batch<4> built from them) against the library routines, bit
 // for bit, over 2^32 random operand sets each, drawn (a) from the ranges the Biot-Savart kernels see and (b) from the
 // whole exponent range including zeros, subnormals, huge and tiny values.  Wherever the restatement does NOT raise
-// its `bad` flag the result must equal the library's; the flagged share (library routines used instead) is printed.
+// its range flag the result must equal the library's; the flagged share (library routines used instead) is printed.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o scripts/_build/probe_exact_arith scripts/probe_exact_arith.cu
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -23,9 +23,9 @@ __global__ void k(long n, int what, int wide, unsigned long long *out)
             double q;
             if (wide) q = __longlong_as_double((long long)rnd(s));                 // any bit pattern (negatives, NaN, inf too)
             else { double r2 = uni(s) * 3200.0 * uni(s); q = r2 * r2 + 1.78e-5 * (double)(rnd(s) & 3) * uni(s); }
-            bool bad = false;
-            double v = dsqrt_rn_try(q, bad);
-            if (bad) flagged++; else if (differ(v, __dsqrt_rn(q))) mism++;
+            unsigned worst = 0;
+            double v = dsqrt_rn_try(q, worst);
+            if (ex_bad(worst)) flagged++; else if (differ(v, __dsqrt_rn(q))) mism++;
         } else if (what == 1) {
             double a1, a2, b;
             if (wide) {
@@ -37,10 +37,10 @@ __global__ void k(long n, int what, int wide, unsigned long long *out)
                 double r2 = a1 * a1 + a2 * a2;
                 b = 6.283185307179586 * sqrt(r2 * r2 + 1.78e-5 * (double)(rnd(s) & 3));
             }
-            bool bad = false;
+            unsigned worst = 0;
             double q1, q2;
-            ddiv2_rn_try(a1, a2, b, q1, q2, bad);
-            if (bad) flagged++; else if (differ(q1, __ddiv_rn(a1, b)) || differ(q2, __ddiv_rn(a2, b))) mism++;
+            ddiv2_rn_try(a1, a2, b, q1, q2, worst);
+            if (ex_bad(worst)) flagged++; else if (differ(q1, __ddiv_rn(a1, b)) || differ(q2, __ddiv_rn(a2, b))) mism++;
         } else {
             double xp[4], zp[4], xw[4], zw[4], g[4], vc4[4], tu[4], tw[4];
             for (int c = 0; c < 4; c++) {
@@ -51,9 +51,9 @@ __global__ void k(long n, int what, int wide, unsigned long long *out)
                 g[c] = (uni(s) - 0.5) * 0.1;
                 vc4[c] = wide ? uni(s) * sc : 1.78e-5 * uni(s);
             }
-            bool bad = false;
-            pair_exact_try_batch<4>(xp, zp, xw, zw, g, vc4, tu, tw, bad);
-            if (bad) flagged++;
+            unsigned worst = 0;
+            pair_exact_try_batch<4>(xp, zp, xw, zw, g, vc4, tu, tw, worst);
+            if (ex_bad(worst)) flagged++;
             else for (int c = 0; c < 4; c++) {
                 double ru, rw;
                 pair_exact_ref(xp[c], zp[c], xw[c], zw[c], g[c], vc4[c], ru, rw);

@@ -42,7 +42,10 @@ def test_exact_golden_percall(ops):
 
 @pytest.mark.parametrize("npnt,nw", [(1, 1), (3, 5), (80, 7), (80, 8), (80, 9), (5, 127), (80, 128), (80, 129),
                                      (80, 137), (81, 1000), (80, 4097), (1, 20001), (80, 40003), (602, 602),
-                                     (2049, 2049), (5000, 3333), (9000, 700), (8192, 2000)])
+                                     (2049, 2049), (5000, 3333), (9000, 700), (8192, 2000),
+                                     # one-thread-per-row tiled exact kernel (>= 4096 rows, >= 1024 sources): self
+                                     # terms (library fallback), ragged leaves, several staged tiles, cut tree
+                                     (4096, 4096), (4100, 1025), (6000, 9999), (4097, 1031), (20000, 2500)])
 def test_exact_vs_oracle_bitwise(ops, oracle, npnt, nw):
     rng = np.random.default_rng(npnt * 100003 + nw)
     g, xw, zw = cloud(rng, nw)
@@ -88,6 +91,11 @@ def test_per_source_core_and_empty(ops, oracle):
     vcs = np.full(300, VC ** 4)
     u1, w1 = ops.induced_velocity(g, xw, zw, xp, zp, VC, mode="exact", vc4_per_source=vcs)
     u2, w2 = oracle.induced_velocity(g, xw, zw, xp, zp, VC)
+    assert biteq(u1, u2) and biteq(w1, w2)
+    g, xw, zw = cloud(rng, 1500)   # tiled exact kernel with a per-source core
+    xp2, zp2 = rng.uniform(-20, 0, 4500), rng.uniform(-4, 4, 4500)
+    u1, w1 = ops.induced_velocity(g, xw, zw, xp2, zp2, VC, mode="exact", vc4_per_source=np.full(1500, VC ** 4))
+    u2, w2 = oracle.induced_velocity(g, xw, zw, xp2, zp2, VC)
     assert biteq(u1, u2) and biteq(w1, w2)
     u, w = ops.induced_velocity(np.zeros(0), np.zeros(0), np.zeros(0), xp, zp, VC)
     assert np.all(u == 0) and np.all(w == 0)
