@@ -93,9 +93,7 @@ __device__ __forceinline__ void exact_batch(const SrcView &S, const double (&xp)
             xps[k * R + r] = xp[r]; zps[k * R + r] = zp[r];
         }
     }
-    unsigned worst = 0;
-    pair_exact_try_batch<R * K>(xps, zps, xw, zw, g, vc4, tu, tw, worst);
-    if (ex_bad(worst)) {
+    if (!pair_exact_try_batch<R * K>(xps, zps, xw, zw, g, vc4, tu, tw)) {
 #pragma unroll
         for (int c = 0; c < R * K; c++) pair_exact_ref(xps[c], zps[c], xw[c], zw[c], g[c], vc4[c], tu[c], tw[c]);
     }
@@ -252,11 +250,12 @@ __device__ __forceinline__ void exact_quad_smem(const double2 *__restrict__ sxz,
         const double2 a = sxz[k], b = sgv[k];
         xw[k] = a.x; zw[k] = a.y; g[k] = b.x; vc4[k] = b.y; xps[k] = xp; zps[k] = zp;
     }
-    unsigned worst = 0;
-    pair_exact_try_batch<4>(xps, zps, xw, zw, g, vc4, tu, tw, worst);
-    if (ex_bad(worst)) {
+    if (!pair_exact_try_batch<4>(xps, zps, xw, zw, g, vc4, tu, tw)) {
 #pragma unroll
-        for (int k = 0; k < 4; k++) pair_exact_ref(xp, zp, xw[k], zw[k], g[k], vc4[k], tu[k], tw[k]);
+        for (int k = 0; k < 4; k++) {   // rare: re-read the sources rather than keep them alive across the batch
+            const volatile double *a = (const volatile double *)(sxz + k), *b = (const volatile double *)(sgv + k);
+            pair_exact_ref(xp, zp, a[0], a[1], b[0], b[1], tu[k], tw[k]);
+        }
     }
     u0 = __dadd_rn(u0, tu[0]); u1 = __dadd_rn(u1, tu[1]); u2 = __dadd_rn(u2, tu[2]); u3 = __dadd_rn(u3, tu[3]);
     w0 = __dadd_rn(w0, tw[0]); w1 = __dadd_rn(w1, tw[1]); w2 = __dadd_rn(w2, tw[2]); w3 = __dadd_rn(w3, tw[3]);

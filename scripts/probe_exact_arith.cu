@@ -51,9 +51,7 @@ __global__ void k(long n, int what, int wide, unsigned long long *out)
                 g[c] = (uni(s) - 0.5) * 0.1;
                 vc4[c] = wide ? uni(s) * sc : 1.78e-5 * uni(s);
             }
-            unsigned worst = 0;
-            pair_exact_try_batch<4>(xp, zp, xw, zw, g, vc4, tu, tw, worst);
-            if (ex_bad(worst)) flagged++;
+            if (!pair_exact_try_batch<4>(xp, zp, xw, zw, g, vc4, tu, tw)) flagged++;
             else for (int c = 0; c < 4; c++) {
                 double ru, rw;
                 pair_exact_ref(xp[c], zp[c], xw[c], zw[c], g[c], vc4[c], ru, rw);
