@@ -48,6 +48,7 @@ namespace ludvm {
 #define SIM_TILED_MIN_WAKE 2048   // fast mode: wakes at least this large use the tiled convection kernel (measured: 8192 -> 5.48 s,
                                   // 4096 -> 5.31 s, 2048 -> 5.30 s, 1024 -> 5.29 s for the 20 000-step dt = 2e-3 run)
 #define SIM_TILED_CHUNKS_MAX 64   // partial-sum slots per row of the tiled convection
+#define SIM_EXACT_TILED_MIN_WAKE 8192   // exact mode, graph path: wakes at least this large use k_conv_partials_exact_tiled
 #define SIM_COOP_MAX_WAKE 8192    // wakes up to this size are stepped by the persistent cooperative kernel
 #define FINISH_STAGE 4096         // doubles of staging in the loads block of k_finish
 
@@ -892,6 +893,33 @@ __global__ void __launch_bounds__(256) k_conv_partials(SimDev S, int s)
     phase_conv_partials(S, st, grid_pool());
 }
 
+// Large wakes in exact mode: one thread per target row, the eight accumulators of numpy's leaf loop in registers,
+// sources broadcast from shared memory (exact_tiled_block, biot_savart.cuh) -- the FP64 pipe instead of instruction
+// issue bounds it.  grid = (row blocks, 2^dcap + 1): y < 2^d evaluates tree node y of the wake on (gamma points ++
+// wake), the last y the P bound vortices on the wake.  Same partial layout as k_conv_partials, so k_finish is shared.
+__global__ void __launch_bounds__(ET_THREADS, 3) k_conv_partials_exact_tiled(SimDev S, int s)
+{
+    __shared__ __align__(16) double2 sxz[ET_TILE], sgv[ET_TILE];
+    Step st;
+    if (!step_begin(S, s, st)) return;
+    const int P = S.P;
+    SrcView W = wake_view(S, st.itev + 1, st.ilev + 1);
+    const double *gx = S.gp + ((size_t)st.i * 2 + 0) * P, *gz = S.gp + ((size_t)st.i * 2 + 1) * P;
+    const int nrows = P + W.n;
+    if (blockIdx.y + 1 < gridDim.y) {
+        const int d = sim_depth(W.n, nrows, S.target_warps);
+        if ((long)blockIdx.x * ET_THREADS >= nrows) return;
+        TgtGammaWake TA{gx, gz, P, W};
+        for (int b = blockIdx.y; b < (1 << d); b += gridDim.y - 1)   // normally one node per CTA
+            exact_tiled_block(W, TA, nrows, blockIdx.x, d, b, S.pb_u, S.pb_w, sxz, sgv);
+    } else {
+        if ((long)blockIdx.x * ET_THREADS >= W.n) return;
+        SrcView Fo = make_src(S.g_airfoil + (size_t)st.itev * S.af_stride, 1, gx, gz, nullptr, S.vc4, P);
+        TgtWake TW{W};
+        exact_tiled_block(Fo, TW, W.n, blockIdx.x, 0, 0, S.foil_u, S.foil_w, sxz, sgv);
+    }
+}
+
 // Large wakes in fast mode: the O(N^2) part goes through the shared-memory tiled kernel (13 FP64 slots/pair at
 // ~94% of the DFMA rate) instead of the lane-group tasks.  grid = (row blocks, chunks + 1): y < chunks evaluates the
 // wake on (gamma points ++ wake) for one source chunk; y == chunks evaluates the P bound vortices on the wake.
@@ -1564,9 +1592,10 @@ static int bracket_of(long n)
 // Launch geometry of one step for every wake size up to 2^bracket.
 struct StepPlan {
     int g1, g3, g4, g5, R, tchunks, slots;
-    bool tiled, ov;
+    bool tiled, ov, tiled_exact;
     dim3 gto;
     dim3 gt;
+    dim3 gte;
 };
 
 static StepPlan plan_step(const ludvm_sim *s, int bracket)
@@ -1588,6 +1617,11 @@ static StepPlan plan_step(const ludvm_sim *s, int bracket)
     pl.g4 = 2 + (int)std::max<long>(1, std::min<long>((nw + 255) / 256, (long)sm * 8));
     pl.tiled = D.mode != LUDVM_EXACT_F64 && nw >= SIM_TILED_MIN_WAKE;
     pl.ov = false;
+    pl.tiled_exact = D.mode == LUDVM_EXACT_F64 && nw >= SIM_EXACT_TILED_MIN_WAKE && !getenv("LUDVM_NO_EXACT_TILED");
+    // grid.y covers the deepest split any wake served by this bracket's graph can ask for (the actual wake may be a
+    // quarter of the bound when no LEV is shed); deeper splits, if any, are looped over inside the kernel
+    const int dplan = std::min(dcap, ilog2_ceil_i(std::max(1, D.target_warps / std::max(1, (D.P + nw / 4 + 3) / 4))));
+    pl.gte = dim3((unsigned)((D.P + nw + ET_THREADS - 1) / ET_THREADS), (1u << dplan) + 1u);
     pl.g5 = 1;
     pl.slots = 0;
     pl.R = 1;
@@ -1623,7 +1657,8 @@ static void enqueue_step_kernel(const ludvm_sim *s, const StepPlan &pl, int whic
         else k_solve<<<1, SOLVE_THREADS, s->solve_smem, cs>>>(D, k);
         break;
     case 2:
-        if (!pl.tiled) k_conv_partials<<<pl.g3, 256, 0, cs>>>(D, k);
+        if (pl.tiled_exact) k_conv_partials_exact_tiled<<<pl.gte, ET_THREADS, 0, cs>>>(D, k);
+        else if (!pl.tiled) k_conv_partials<<<pl.g3, 256, 0, cs>>>(D, k);
         else if (pl.ov) {
             if (pl.R == 4) k_conv_old_tiled<4><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.slots);
             else if (pl.R == 2) k_conv_old_tiled<2><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.slots);
@@ -1712,7 +1747,9 @@ LUDVM_API int ludvm_sim_create(ludvm_ctx *ctx, const ludvm_sim_params *p, const 
     DevTables dt{};
     TRY(upload_tables(ctx, s->allocs, *p, *t, &dt));
     const bool cta = p->method == LUDVM_METHOD_RAMESH;  // Newton loops: the whole step runs in one CTA
-    const int target = cta ? 2 * (RAMESH_THREADS / 32) : ctx->sm_count * 48;
+    // exact mode splits the summation tree deeper: its large-wake convection kernel runs one 128-thread CTA per
+    // (128 rows, tree node) and wants a few waves of 3 CTAs/SM (the split depth never changes a result)
+    const int target = cta ? 2 * (RAMESH_THREADS / 32) : ctx->sm_count * (p->mode == LUDVM_EXACT_F64 ? 192 : 48);
     // shared-memory staging area of the block-wide folds / integrals: all Nc Fourier integrands, or 64 partials of
     // every (row, component), in one batch
     const int sum_nodes = (int)std::max<long>(cta ? 1024 : 4096, std::max<long>(p->Nc * p->P, cta ? 0 : 2 * p->P * 65));

@@ -180,3 +180,23 @@ def test_tiled_convection_matches_exact_mode():
     assert np.max(np.abs(f.M - e.M)) <= 1e-10 * np.max(np.abs(e.M))
     assert np.max(np.abs(f.path["FREE"] - e.path["FREE"])) <= 1e-12
     assert np.max(np.abs(f.path["TEV"] - e.path["TEV"])) <= 1e-12
+
+
+def test_exact_tiled_convection_bit_equal_to_oracle(oracle, monkeypatch):
+    """Exact mode, wakes >= 8192 vortices (graph path): the one-thread-per-row tiled convection kernel
+    (k_conv_partials_exact_tiled) keeps numpy's summation tree, so the run stays bit-equal to the oracle -- and to the
+    8-lanes-per-row kernel it replaces (LUDVM_NO_EXACT_TILED=1)."""
+    from ludvm_b200 import LUDVM
+    rng = np.random.default_rng(11)
+    nf = 8400
+    xy = np.stack([rng.uniform(-6.0, -0.5, nf), rng.uniform(-1.0, 1.0, nf)])
+    gam = rng.standard_normal(nf) * 1e-3
+    kw = dict(t0=0, tf=0.2, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012",
+              circulation_freevort=gam, xy_freevort=xy)
+    s, o = LUDVM(**kw, verbose=False, mode="exact"), oracle.OracleLUDVM(**kw)
+    for k in ("L", "D", "M", "LESP", "LEV_shed"):
+        assert biteq(getattr(s, k), getattr(o, k)), k
+    assert biteq(s.path["FREE"], o.path["FREE"]) and biteq(s.path["TEV"], o.path["TEV"])
+    monkeypatch.setenv("LUDVM_NO_EXACT_TILED", "1")
+    g = LUDVM(**kw, verbose=False, mode="exact")
+    assert biteq(g.L, s.L) and biteq(g.path["FREE"], s.path["FREE"])
