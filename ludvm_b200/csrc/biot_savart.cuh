@@ -239,22 +239,56 @@ __device__ __forceinline__ void exact_rows_warp_task(const SrcView &S, const Tgt
 #define ET_THREADS 128
 #define ET_TILE 1024   // sources per staged tile (a leaf is <= 128): 32 KB of shared memory
 
-// au[k] += term(source j0 + k), k = 0..3, for one target.
-__device__ __forceinline__ void exact_quad_smem(const double2 *__restrict__ sxz, const double2 *__restrict__ sgv,
-                                                double xp, double zp, double &u0, double &u1, double &u2, double &u3,
-                                                double &w0, double &w1, double &w2, double &w3)
+// Staged sources of the exact tiled kernels: (x, z) pairs plus either (Gamma, vc^4) pairs or Gamma alone with a
+// scalar core (the one-CTA driver, where shared memory is scarce).
+struct SmemSrc4 {
+    const double2 *xz, *gv;
+    __device__ __forceinline__ SmemSrc4 at(int j) const { return SmemSrc4{xz + j, gv + j}; }
+    __device__ __forceinline__ void get(int k, double &x, double &z, double &g, double &v) const
+    {
+        const double2 a = xz[k], b = gv[k];
+        x = a.x; z = a.y; g = b.x; v = b.y;
+    }
+    __device__ __forceinline__ void get_again(int k, double &x, double &z, double &g, double &v) const
+    {
+        const volatile double *a = (const volatile double *)(xz + k), *b = (const volatile double *)(gv + k);
+        x = a[0]; z = a[1]; g = b[0]; v = b[1];
+    }
+};
+struct SmemSrc3 {
+    const double2 *xz;
+    const double *gam;
+    double vc4;
+    __device__ __forceinline__ SmemSrc3 at(int j) const { return SmemSrc3{xz + j, gam + j, vc4}; }
+    __device__ __forceinline__ void get(int k, double &x, double &z, double &g, double &v) const
+    {
+        const double2 a = xz[k];
+        x = a.x; z = a.y; g = gam[k]; v = vc4;
+    }
+    __device__ __forceinline__ void get_again(int k, double &x, double &z, double &g, double &v) const
+    {
+        const volatile double *a = (const volatile double *)(xz + k), *b = (const volatile double *)(gam + k);
+        x = a[0]; z = a[1]; g = b[0]; v = vc4;
+    }
+};
+
+// au[k] += term(source k), k = 0..3, for one target.
+template <class Src>
+__device__ __forceinline__ void exact_quad_smem(const Src src, double xp, double zp, double &u0, double &u1, double &u2,
+                                                double &u3, double &w0, double &w1, double &w2, double &w3)
 {
     double xw[4], zw[4], g[4], vc4[4], xps[4], zps[4], tu[4], tw[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        const double2 a = sxz[k], b = sgv[k];
-        xw[k] = a.x; zw[k] = a.y; g[k] = b.x; vc4[k] = b.y; xps[k] = xp; zps[k] = zp;
+        src.get(k, xw[k], zw[k], g[k], vc4[k]);
+        xps[k] = xp; zps[k] = zp;
     }
     if (!pair_exact_try_batch<4>(xps, zps, xw, zw, g, vc4, tu, tw)) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {   // rare: re-read the sources rather than keep them alive across the batch
-            const volatile double *a = (const volatile double *)(sxz + k), *b = (const volatile double *)(sgv + k);
-            pair_exact_ref(xp, zp, a[0], a[1], b[0], b[1], tu[k], tw[k]);
+            double x, z, gg, v;
+            src.get_again(k, x, z, gg, v);
+            pair_exact_ref(xp, zp, x, z, gg, v, tu[k], tw[k]);
         }
     }
     u0 = __dadd_rn(u0, tu[0]); u1 = __dadd_rn(u1, tu[1]); u2 = __dadd_rn(u2, tu[2]); u3 = __dadd_rn(u3, tu[3]);
@@ -262,8 +296,8 @@ __device__ __forceinline__ void exact_quad_smem(const double2 *__restrict__ sxz,
 }
 
 // One leaf (m <= 128 staged sources) of numpy's pairwise sum for the thread's target.
-__device__ __forceinline__ void exact_leaf_thread(const double2 *__restrict__ sxz, const double2 *__restrict__ sgv, int m,
-                                                  double xp, double zp, double &ru, double &rw)
+template <class Src>
+__device__ __forceinline__ void exact_leaf_thread(const Src src, int m, double xp, double zp, double &ru, double &rw)
 {
     const int body = (m >= 8) ? (m & ~7) : 0;
     double su = -0.0, sw = -0.0;
@@ -272,8 +306,8 @@ __device__ __forceinline__ void exact_leaf_thread(const double2 *__restrict__ sx
 #pragma unroll
         for (int k = 0; k < 8; k++) u[k] = w[k] = -0.0;   // -0.0 + t == t bit for bit
         for (int i = 0; i < body; i += 8) {
-            exact_quad_smem(sxz + i, sgv + i, xp, zp, u[0], u[1], u[2], u[3], w[0], w[1], w[2], w[3]);
-            exact_quad_smem(sxz + i + 4, sgv + i + 4, xp, zp, u[4], u[5], u[6], u[7], w[4], w[5], w[6], w[7]);
+            exact_quad_smem(src.at(i), xp, zp, u[0], u[1], u[2], u[3], w[0], w[1], w[2], w[3]);
+            exact_quad_smem(src.at(i + 4), xp, zp, u[4], u[5], u[6], u[7], w[4], w[5], w[6], w[7]);
         }
         su = __dadd_rn(__dadd_rn(__dadd_rn(u[0], u[1]), __dadd_rn(u[2], u[3])),
                        __dadd_rn(__dadd_rn(u[4], u[5]), __dadd_rn(u[6], u[7])));
@@ -281,14 +315,55 @@ __device__ __forceinline__ void exact_leaf_thread(const double2 *__restrict__ sx
                        __dadd_rn(__dadd_rn(w[4], w[5]), __dadd_rn(w[6], w[7])));
     }
     for (int i = body; i < m; i++) {   // <= 7 tail terms, in order
-        const double2 a = sxz[i], b = sgv[i];
-        double tu, tw;
-        pair_exact(xp, zp, a.x, a.y, b.x, b.y, tu, tw);
+        double x, z, g, v, tu, tw;
+        src.get(i, x, z, g, v);
+        pair_exact(xp, zp, x, z, g, v, tu, tw);
         su = __dadd_rn(su, tu);
         sw = __dadd_rn(sw, tw);
     }
     ru = su;
     rw = sw;
+}
+
+// The whole pairwise tree over n sources resident in shared memory, for the thread's target (no barriers inside:
+// threads may call it a different number of times).
+template <class Src>
+__device__ __forceinline__ void exact_tree_thread(const Src src, int n, double xp, double zp, double &su, double &sw)
+{
+    int r_off[PW_MAX_STACK], r_len[PW_MAX_STACK];
+    double l_u[PW_MAX_STACK], l_w[PW_MAX_STACK];
+    unsigned has_l = 0;
+    int sp = 0, off = 0;
+    for (;;) {
+        while (n > PW_BLOCK) {
+            int n2 = pw_left(n);
+            r_off[sp] = off + n2;
+            r_len[sp] = n - n2;
+            has_l &= ~(1u << sp);
+            sp++;
+            n = n2;
+        }
+        double ru, rw;
+        exact_leaf_thread(src.at(off), n, xp, zp, ru, rw);
+        for (;;) {
+            if (sp == 0) {
+                su = ru;
+                sw = rw;
+                return;
+            }
+            if (!((has_l >> (sp - 1)) & 1u)) {
+                l_u[sp - 1] = ru;
+                l_w[sp - 1] = rw;
+                has_l |= 1u << (sp - 1);
+                off = r_off[sp - 1];
+                n = r_len[sp - 1];
+                break;
+            }
+            ru = __dadd_rn(l_u[sp - 1], ru);
+            rw = __dadd_rn(l_w[sp - 1], rw);
+            sp--;
+        }
+    }
 }
 
 template <class Tgt>
@@ -328,7 +403,7 @@ __device__ __forceinline__ void exact_tiled_block(const SrcView &S, const Tgt &T
             }
             __syncthreads();
         }
-        exact_leaf_thread(sxz + (off - tile0), sgv + (off - tile0), n, xp, zp, ru, rw);
+        exact_leaf_thread(SmemSrc4{sxz + (off - tile0), sgv + (off - tile0)}, n, xp, zp, ru, rw);
         bool done = false;
         for (;;) {
             if (sp == 0) {

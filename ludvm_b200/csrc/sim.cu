@@ -1314,6 +1314,42 @@ __device__ __noinline__ void cta_conv_tiled_fast(const SimDev &S, const Step &st
         cta_tiled_rows<1>(tx, tz, sgf, P, S.vc4, tx + P, tz + P, n, S.foil_u, S.foil_w);
     }
 }
+// Exact-mode twin: the wake ((x, z) pairs and Gamma) is staged once, every thread owns whole target rows and walks
+// numpy's summation tree with the eight leaf accumulators in registers and four div/sqrt chains in flight
+// (exact_tree_thread).  3 (P + n) doubles of scratch (+ 1 for 16-byte alignment).  One partial per row, as above.
+__device__ __noinline__ void cta_conv_tiled_exact(const SimDev &S, const Step &st, double *smt)
+{
+    const int P = S.P, tid = threadIdx.x, nth = blockDim.x;
+    SrcView W = wake_view(S, st.itev + 1, st.ilev + 1);
+    const int n = W.n, nrows = P + n;
+    const double *gx = S.gp + ((size_t)st.i * 2 + 0) * P, *gz = S.gp + ((size_t)st.i * 2 + 1) * P;
+    const double *ga = S.g_airfoil + (size_t)st.itev * S.af_stride;
+    // shared layout: (x, z) of the gamma points [P] ++ wake [n], then Gamma of the bound vortices [P] ++ wake [n]
+    double2 *txz = reinterpret_cast<double2 *>(smt + ((reinterpret_cast<size_t>(smt) >> 3) & 1));
+    double *tg = reinterpret_cast<double *>(txz + nrows);
+    __syncthreads();
+    for (int r = tid; r < nrows; r += nth) {
+        if (r < P) { txz[r] = make_double2(gx[r], gz[r]); tg[r] = ga[r]; }
+        else {
+            int p = W.phys(r - P);
+            txz[r] = make_double2(S.wx[p], S.wz[p]); tg[r] = S.wg[p];
+        }
+    }
+    __syncthreads();
+    const SmemSrc3 wake{txz + P, tg + P, S.vc4}, foil{txz, tg, S.vc4};
+    for (int row = tid; row < nrows; row += nth) {
+        const double2 t = txz[row];
+        double u, w;
+        exact_tree_thread(wake, n, t.x, t.y, u, w);
+        S.pb_u[row] = u; S.pb_w[row] = w;
+    }
+    for (int row = tid; row < n; row += nth) {
+        const double2 t = txz[P + row];
+        double u, w;
+        exact_tree_thread(foil, P, t.x, t.y, u, w);
+        S.foil_u[row] = u; S.foil_w[row] = w;
+    }
+}
 __device__ __noinline__ void cta_finish_update(const SimDev &S, const Step &st)
 {
     phase_finish_update(S, st, threadIdx.x, blockDim.x, 0);
@@ -1363,8 +1399,12 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1) k_sim_cta(con
             __syncthreads();
             CTA_T(1);
             // fast mode with the wake in shared memory: 3 (P + n) + P doubles of the scratch area
-            if (S.mode != LUDVM_EXACT_F64 && 3 * (S.P + st.itev + st.ilev + 2 + S.nfree) + S.P <= SOLVE_SCRATCH_DOUBLES(S.P, S.Nc, S.sum_nodes))
+            // (exact mode: the same footprint; only the 256-thread driver has the registers for it)
+            const bool fits = 3 * (S.P + st.itev + st.ilev + 2 + S.nfree) + S.P <= SOLVE_SCRATCH_DOUBLES(S.P, S.Nc, S.sum_nodes);
+            if (S.mode != LUDVM_EXACT_F64 && fits)
                 cta_conv_tiled_fast(S, st, scr);
+            else if (THREADS <= 256 && fits && st.itev + st.ilev + 2 + S.nfree >= 8)
+                cta_conv_tiled_exact(S, st, scr);
             else
                 cta_conv_partials(S, st);
             __syncthreads();

@@ -67,6 +67,13 @@ if 2 in only:   # high-resolution run, dt=2e-3, tf=40
     r["note"] = ("chaotic once LEV shedding starts: a 1-ulp perturbation of h_max in the CPU oracle gives 1e-8 @700, "
                  "3e-4 @800, 0.38 @900, 1.27 @1500 (scripts/chaos_envelope.py)")
     se.close()
+    # the whole run in exact mode (bit-for-bit the reference's arithmetic; the chaotic tail is then the reference's own)
+    sx = LUDVM(**kw, verbose=False, run=False, mode="exact", ctx=ctx, store_history=False)
+    t0 = time.perf_counter(); sx.time_loop(tables=tb, nsteps=nsteps); dtx = time.perf_counter() - t0
+    nlx = int((sx.LEV_shed[1:nsteps + 1] != -1).sum())
+    r["exact_full"] = {"seconds": dtx, "steps_per_s": nsteps / dtx, "lev": nlx, "Cl_last": float(sx.L[nsteps]),
+                       "prefix_equals_exact_prefix_run": biteq(sx.L[:npre + 1], o.L[:npre + 1])}
+    sx.close()
     # CPU side of SURVEY.md 8(d)-2: prefix runs of the oracle port (one core), cubic fit t(n) = a n + b n^2 + c n^3
     # (the step is O(N^2) pairs with N ~ n), EXTRAPOLATED to the full run -- nobody waits hours for the CPU.
     ns, ts = [250, 500, 1000, 2000], []
