@@ -32,6 +32,7 @@ UNIT = "pair-interactions/s"
 SEED, VCORE, DT = 20260101, 0.065, 0.05
 SLOTS_PER_PAIR = 13          # 7 DFMA + 4 DMUL + 2 DADD FP64-pipe issue slots per pair (SASS-counted)
 FLOP_PER_PAIR = 20           # N-body convention (FMA = 2)
+EXACT_OPS_PER_PAIR = 31      # exact mode: 7 (r^4 + vc^4) + 8 (sqrt) + 1 (2 pi) + 5 (reciprocal) + 6 (two quotients) + 2 (x Gamma) + 2 (sums)
 # dram__bytes_read.sum + dram__bytes_write.sum of one all-pairs launch at N = 2^20 (profiles/r01_k_fast_tiled_raw.csv):
 # 27.8 MB + 13.9 MB against 48 MB algorithmic (32 B read + 16 B written per vortex)
 NCU_DRAM_BYTES_PER_LAUNCH = 41.7e6
@@ -231,6 +232,10 @@ def run_ours(args):
     f32_ms, _, _ = timed_steps("fp32", max(1, min(args.steps, 2)), 1)
     f32_value = float(n) * n / (f32_ms / max(1, min(args.steps, 2)) * 1e-3)
 
+    # exact mode (numpy's summation tree, IEEE div/sqrt: bit-for-bit the reference's arithmetic) reported separately
+    ex_ms, _, _ = timed_steps("exact", 1, 1)
+    ex_value = float(n) * n / (ex_ms * 1e-3)
+
     # e2e through the public host-buffer API: pinned host arrays in, host arrays out
     pin = lambda a: torch.tensor(a).pin_memory().numpy()  # noqa: E731
     gp_, xp_, zp_ = pin(g_h), pin(x_h), pin(z_h)
@@ -287,6 +292,11 @@ def run_ours(args):
     }
     out["fp32_fast"] = {"value": f32_value, "unit": UNIT, "ffma_per_s_measured": ffma,
                         "note": "fp32 pair arithmetic, fp64 accumulation across tiles; accuracy ~1e-5 relative"}
+
+    out["exact_f64"] = {"value": ex_value, "unit": UNIT, "ms_per_step": ex_ms, "fp64_ops_per_pair": EXACT_OPS_PER_PAIR,
+                        "frac_of_dfma_rate": ex_value / world * EXACT_OPS_PER_PAIR / dfma,
+                        "note": "bitwise equal to the reference's numpy result (pairwise summation tree, correctly rounded "
+                                "division and square root); 31 FP64-pipe operations + 2 MUFU per pair, SASS-counted"}
 
     if world == 1:
         # CPU baseline on this box's host cores, bounded sample
