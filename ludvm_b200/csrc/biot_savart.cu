@@ -167,7 +167,7 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
 {
     const int sm = ctx->sm_count;
     if (mode == LUDVM_EXACT_F64) {
-        if (nrows >= 4096 && S.n >= 1024) {
+        if (nrows >= 4096 && (S.n >= 1024 || nrows >= (long)sm * ET_THREADS * 3)) {   // (few sources: only if the rows alone fill the GPU)
             // Many rows: one thread per row, sources staged through shared memory; the tree is cut at depth d so
             // that ~4 waves of 3 CTAs/SM are in flight.
             long rblocks = (nrows + ET_THREADS - 1) / ET_THREADS;

@@ -62,3 +62,18 @@ def test_flowfield_large_grid_properties():
     circ = np.trapezoid(np.trapezoid(ome, dx=dr, axis=0), dx=dr, axis=0)
     # the reference's convention: positive circulation is clockwise, so omega = dw/dx - du/dz integrates to -Gamma
     assert abs(circ + G) < 0.05 * G
+
+
+def test_flowfield_exact_large_grid_few_sources(oracle):
+    """A README-size wake (300 vortices, three source segments' worth of ragged leaves) on a 240 x 240 grid: enough
+    rows for the one-thread-per-row exact kernel even with a shallow summation tree.  Bit-equal to the oracle."""
+    from ludvm_b200 import ops
+    rng = np.random.default_rng(20260103)
+    n = 300
+    g, xw, zw = rng.standard_normal(n) * 1e-2, rng.uniform(-5, 0, n), rng.uniform(-1, 1, n)
+    x1, z1 = np.arange(-6.0, 0.0, 0.025), np.arange(-3.0, 3.0, 0.025)
+    assert len(x1) * len(z1) >= 148 * 128 * 3
+    u, w = ops.flowfield_velocity(g, xw, zw, None, None, None, 0.065 ** 4, x1, z1, mode="exact")
+    X, Z = np.meshgrid(x1, z1, indexing="ij")
+    uo, wo = oracle.induced_velocity(g, xw, zw, X.ravel(), Z.ravel(), 0.065)
+    assert biteq(u.ravel(), uo) and biteq(w.ravel(), wo)
