@@ -169,9 +169,9 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
     if (mode == LUDVM_EXACT_F64) {
         if (nrows >= 4096 && (S.n >= 1024 || nrows >= (long)sm * ET_THREADS * 3)) {   // (few sources: only if the rows alone fill the GPU)
             // Many rows: one thread per row, sources staged through shared memory; the tree is cut at depth d so
-            // that ~4 waves of 3 CTAs/SM are in flight.
+            // that >= ~6 waves of 4 CTAs/SM are in flight.
             long rblocks = (nrows + ET_THREADS - 1) / ET_THREADS;
-            int want = ilog2_ceil(std::max(1L, (long)sm * 12 / rblocks));
+            int want = ilog2_ceil(std::max(1L, (long)sm * 24 / rblocks));
             int d = std::min(pw_max_depth(S.n), want);
             size_t bytes = sizeof(double) * (size_t)nrows * ((size_t)1 << d);
             void *a, *b;
@@ -184,9 +184,8 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
             *pu = (double *)a; *pw_ = (double *)b; *nfold = d;
             return LUDVM_OK;
         }
-        // Few rows: 8 lanes per row.  R target rows per 8-lane group: two when there are plenty of rows (a loaded
-        // source then serves two pair evaluations), one when parallelism matters more.
-        const int R = nrows >= (long)sm * 512 ? 2 : 1;
+        // Few rows (or few rows and few sources): 8 lanes per row, tree nodes spread over warps.
+        constexpr int R = 1;
         long nquads = (nrows + 4 * R - 1) / (4 * R);
         int want = ilog2_ceil(std::max(1L, (long)sm * 64 / std::max(1L, nquads)));
         int d = std::min(pw_max_depth(S.n), want);
@@ -197,8 +196,7 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
         if ((rc = scratch_reserve(ctx, slot + 1, bytes, &b))) return rc;
         long ntasks = nquads << d;
         int blocks = (int)std::min((ntasks + 7) / 8, (long)sm * 16);
-        if (R == 2) k_exact_rows<2><<<blocks, 256, 0, ctx->stream>>>(S, T, (int)nrows, d, (double *)a, (double *)b);
-        else k_exact_rows<1><<<blocks, 256, 0, ctx->stream>>>(S, T, (int)nrows, d, (double *)a, (double *)b);
+        k_exact_rows<R><<<blocks, 256, 0, ctx->stream>>>(S, T, (int)nrows, d, (double *)a, (double *)b);
         ctx->launches++;
         *pu = (double *)a; *pw_ = (double *)b; *nfold = d;
         return LUDVM_OK;

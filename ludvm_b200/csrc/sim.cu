@@ -1788,8 +1788,9 @@ LUDVM_API int ludvm_sim_create(ludvm_ctx *ctx, const ludvm_sim_params *p, const 
     TRY(upload_tables(ctx, s->allocs, *p, *t, &dt));
     const bool cta = p->method == LUDVM_METHOD_RAMESH;  // Newton loops: the whole step runs in one CTA
     // exact mode splits the summation tree deeper: its large-wake convection kernel runs one 128-thread CTA per
-    // (128 rows, tree node) and wants a few waves of 3 CTAs/SM (the split depth never changes a result)
-    const int target = cta ? 2 * (RAMESH_THREADS / 32) : ctx->sm_count * (p->mode == LUDVM_EXACT_F64 ? 192 : 48);
+    // (128 rows, tree node) and wants several waves of 4 CTAs/SM (the split depth never changes a result).  Measured on
+    // the 20 000-step dt = 2e-3 run in exact mode: 96 x SMs 16.9 s, 192 x 15.1 s, 384 x 14.4 s.
+    const int target = cta ? 2 * (RAMESH_THREADS / 32) : ctx->sm_count * (p->mode == LUDVM_EXACT_F64 ? (getenv("LUDVM_EXACT_TARGET") ? atoi(getenv("LUDVM_EXACT_TARGET")) : 384) : 48);
     // shared-memory staging area of the block-wide folds / integrals: all Nc Fourier integrands, or 64 partials of
     // every (row, component), in one batch
     const int sum_nodes = (int)std::max<long>(cta ? 1024 : 4096, std::max<long>(p->Nc * p->P, cta ? 0 : 2 * p->P * 65));
