@@ -206,7 +206,8 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
         // The source chunking depends on the number of SOURCES only, so a row's sum does not depend on how the
         // target rows are sharded over GPUs (G-rank results are bitwise equal to 1-rank results); the rows-per-
         // thread factor R adapts to the number of rows to keep >= ~6 waves of 2 CTAs/SM in flight.
-        long chunks = std::max(1L, std::min(8L, (long)S.n / (FT_TILE * 2)));
+        const char *ce = getenv("LUDVM_FAST_CHUNKS");   // experiment knob; must be the same on every rank
+        long chunks = std::max(1L, std::min(ce ? std::max(1L, atol(ce)) : 8L, (long)S.n / (FT_TILE * 2)));
         int chunk_len = (int)(((S.n + chunks - 1) / chunks + FT_TILE - 1) / FT_TILE * FT_TILE);
         chunks = ((long)S.n + chunk_len - 1) / chunk_len;
         // fp32: the packed fp32x2 kernel (8 rows per thread) when the core radius is a scalar and there are enough rows
