@@ -206,8 +206,12 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
         // The source chunking depends on the number of SOURCES only, so a row's sum does not depend on how the
         // target rows are sharded over GPUs (G-rank results are bitwise equal to 1-rank results); the rows-per-
         // thread factor R adapts to the number of rows to keep >= ~6 waves of 2 CTAs/SM in flight.
-        const char *ce = getenv("LUDVM_FAST_CHUNKS");   // experiment knob; must be the same on every rank
-        long chunks = std::max(1L, std::min(ce ? std::max(1L, atol(ce)) : 8L, (long)S.n / (FT_TILE * 2)));
+        // 16 chunks from 131072 sources (measured at 2^20 sources: 866 ms against 875 ms with 8 for 2^20 rows, and 109.4 ms
+        // against 115.5 ms for the 131072 rows of one rank of eight, where 8 chunks force R = 2; 32 chunks: no further gain;
+        // profiles/r01e_chunks_probe.txt).  LUDVM_FAST_CHUNKS overrides (experiments; same value on every rank).
+        const char *ce = getenv("LUDVM_FAST_CHUNKS");
+        const long cap = ce ? std::max(1L, atol(ce)) : (S.n >= 131072 ? 16L : 8L);
+        long chunks = std::max(1L, std::min(cap, (long)S.n / (FT_TILE * 2)));
         int chunk_len = (int)(((S.n + chunks - 1) / chunks + FT_TILE - 1) / FT_TILE * FT_TILE);
         chunks = ((long)S.n + chunk_len - 1) / chunk_len;
         // fp32: the packed fp32x2 kernel (8 rows per thread) when the core radius is a scalar and there are enough rows
