@@ -34,7 +34,9 @@ SLOTS_PER_PAIR = 13          # 7 DFMA + 4 DMUL + 2 DADD FP64-pipe issue slots pe
 FLOP_PER_PAIR = 20           # N-body convention (FMA = 2)
 EXACT_OPS_PER_PAIR = 31      # exact mode: 7 (r^4 + vc^4) + 8 (sqrt) + 1 (2 pi) + 5 (reciprocal) + 6 (two quotients) + 2 (x Gamma) + 2 (sums)
 # dram__bytes_read.sum + dram__bytes_write.sum of one all-pairs launch at N = 2^20 (profiles/r01_k_fast_tiled_raw.csv):
-# 27.8 MB + 13.9 MB against 48 MB algorithmic (32 B read + 16 B written per vortex)
+# 27.8 MB + 13.9 MB against 48 MB algorithmic (32 B read + 16 B written per vortex).  That capture was taken with 8
+# source chunks; the launch now writes 16 partial rows per target (268 MB, no longer L2-resident) and has not been
+# re-captured, so the figure is reported only when the run is forced back to 8 chunks.
 NCU_DRAM_BYTES_PER_LAUNCH = 41.7e6
 
 
@@ -281,11 +283,13 @@ def run_ours(args):
         "bound": "fp64_fma_pipe", "unit": "TFLOP/s",
         "achieved": per_gpu_pairs * SLOTS_PER_PAIR * 2 / 1e12,
         "peak": dfma * 2 / 1e12, "frac": per_gpu_pairs * SLOTS_PER_PAIR / dfma,
-        "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and n == (1 << 20)) else None,
+        "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (world == 1 and n == (1 << 20) and os.environ.get("LUDVM_FAST_CHUNKS") == "8") else None,
         "note": "per GPU; achieved = pairs/s x 13 FP64-pipe issue slots x 2 flop; peak = DFMA issue rate measured "
                 "live by ludvm_measure_fp64_fma_rate (MEASURED_PEAKS.json has no FP64 entry); the tiled all-pairs kernel "
                 "is >99.9% of the step; algorithmic DRAM bytes are 48 B/vortex/step (negligible); traffic = dram bytes "
-                "read+written per launch from the ncu --set full capture under profiles/ (N=2^20, 1 GPU)",
+                "read+written per launch from the ncu --set full capture under profiles/ (N=2^20, 1 GPU, 8 source chunks: "
+                "41.7 MB); null since the launch went to 16 chunks (268 MB of partial sums per launch, ~0.3 GB of DRAM "
+                "traffic against a 0.87 s kernel) until it is re-captured",
         "flop20_tflops": per_gpu_pairs * FLOP_PER_PAIR / 1e12,
         "hbm_algorithmic_gbs": 48.0 * n / world / (ms_per_step * 1e-3) / 1e9,
         "mufu_per_s": per_gpu_pairs,
