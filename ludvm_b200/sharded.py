@@ -27,6 +27,23 @@ def shard_bounds(n, world, rank):
     return rank * per, per
 
 
+def case_slice(ncases, world, rank):
+    """Cases of a parameter sweep owned by `rank` (BASELINE.json configs[3]): contiguous, sizes differ by at most one
+    block of ceil(ncases / world); no collective is needed, every case is independent."""
+    per = (ncases + world - 1) // world
+    return slice(min(ncases, rank * per), min(ncases, (rank + 1) * per))
+
+
+def grid_slab(nx, world, rank):
+    """x-rows of a flow-field grid owned by `rank` (BASELINE.json configs[4]): returns (r0, r1, h0, h1) -- the rank
+    owns rows [r0, r1) and evaluates [h0, h1), one halo row per interior side, so that the central-difference
+    vorticity stencil (LUDVM.py:1222-1292) of every owned row sees its neighbours without any exchange; at the ends of
+    the grid the stencil is one-sided in the reference too.  Keep `field[r0 - h0 : r1 - h0]` of what was evaluated."""
+    per = (nx + world - 1) // world
+    r0, r1 = min(nx, rank * per), min(nx, (rank + 1) * per)
+    return r0, r1, max(0, r0 - 1), min(nx, r1 + 1)
+
+
 class ShardedSelfConvection:
     def __init__(self, g, x, z, v_core, dt, mode="fast", ctx=None, group=None, kernel=None, transport="auto"):
         self.group = group

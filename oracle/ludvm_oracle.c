@@ -290,7 +290,7 @@ ORACLE_API int oracle_sim_run(const oracle_sim_in *in, const oracle_sim_out *o)
     sim_ws ws, *s = &ws;
     memset(s, 0, sizeof(ws));
     s->in = in; s->out = o; s->nv = nv;
-    long cap = 2 * nv + nfree + 8;
+    long cap = (2 * nv + nfree > P ? 2 * nv + nfree : P) + 8;   /* the row temporaries also serve the P bound vortices as sources */
     s->g = (double *)calloc((size_t)cap * 5, sizeof(double));
     s->xw = s->g + cap; s->zw = s->xw + cap; s->tu = s->zw + cap; s->tw = s->tu + cap;
     s->u1 = (double *)calloc((size_t)P * 7, sizeof(double));

@@ -9,6 +9,7 @@ import torch
 import torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ludvm_b200 import _lib, sweep
+from ludvm_b200.sharded import case_slice, grid_slab
 
 local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -29,8 +30,7 @@ def maxtime(seconds):
 
 # ---- configs[3]: sweep, cases split evenly over the ranks
 cases = sweep.lespcrit_k_grid(np.linspace(0.1, 0.4, ncases_side), np.linspace(0.1, 1.0, ncases_side), **README)
-per = (len(cases) + world - 1) // world
-sl = slice(rank * per, min(len(cases), (rank + 1) * per))
+sl = case_slice(len(cases), world, rank)
 sweep.run_sweep(cases[:2], mode="exact", ctx=ctx)                  # warm-up: module load, kernel attributes
 for mode in ("exact", "fast"):
     dist.barrier(); torch.cuda.synchronize()
@@ -49,9 +49,7 @@ nsrc = 200000
 xh, zh, gh = rng.uniform(-20, 0, nsrc), rng.uniform(-4, 4, nsrc), rng.standard_normal(nsrc) * 1e-2
 x1, z1 = np.arange(-20.48, 0, 0.005), np.arange(-10.24, 10.24, 0.005)
 nx, nz = len(x1), len(z1)
-rows = (nx + world - 1) // world
-r0, r1 = rank * rows, min(nx, (rank + 1) * rows)
-h0, h1 = max(0, r0 - 1), min(nx, r1 + 1)                            # slab with halo
+r0, r1, h0, h1 = grid_slab(nx, world, rank)                         # owned rows, slab with halo
 g, xs, zs, X1, Z1 = (torch.tensor(a, device=dev) for a in (gh, xh, zh, x1, z1))
 u = torch.empty((h1 - h0, nz), dtype=torch.float64, device=dev); w = torch.empty_like(u); ome = torch.empty_like(u)
 X1s = X1[h0:h1].contiguous()

@@ -22,7 +22,8 @@ def _cmp(r, o):
     assert (r.itev, r.ilev) == (o.itev, o.ilev)
 
 
-@pytest.mark.parametrize("over", [dict(tf=4), dict(tf=2, method="Ramesh", LESPcrit=0.12),
+@pytest.mark.parametrize("over", [dict(tf=4), dict(tf=0.5),   # (tf=0.5: fewer wake vortices than chord stations)
+                                  dict(tf=2, method="Ramesh", LESPcrit=0.12),
                                   dict(tf=3, dt=2e-2, Npoints=61, Ncoeffs=12, chord=1.3, Uinf=1.7, alpha_m=3,
                                        alpha_max=20, k=0.7)])
 def test_time_loop_bit_equal(oracle, over):

@@ -71,3 +71,87 @@ def test_shard_bounds_rejects_ragged():
     with pytest.raises(ValueError):
         shard_bounds(10, 4, 0)
     assert shard_bounds(16, 4, 3) == (12, 4)
+
+
+# ---------------------------------------------------------------------------------------------------
+# collective-free shardings: parameter sweeps (configs[3]) and flow-field x-row slabs (configs[4])
+# ---------------------------------------------------------------------------------------------------
+SWEEP_KW = dict(t0=0, tf=0.5, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, Naca="0012")
+SWEEP_CASES = [dict(SWEEP_KW, LESPcrit=lc, k=k) for lc in (0.1, 0.2, 0.3) for k in (0.3, 0.8)][:5]   # ragged over 2 ranks
+FF_NX, FF_NZ, FF_NSRC = 37, 11, 200
+
+
+def _ff_inputs():
+    rng = np.random.default_rng(21)
+    g, xw, zw = rng.standard_normal(FF_NSRC) * 1e-2, rng.uniform(-3, 0, FF_NSRC), rng.uniform(-1, 1, FF_NSRC)
+    return g, xw, zw, np.linspace(-3.0, 0.5, FF_NX), np.linspace(-1.0, 1.0, FF_NZ)
+
+
+def _ff_eval(o, g, xw, zw, x1, z1):
+    """velocity + vorticity of the oracle on the 'ij' mesh x1 x z1 -> (u, w, ome), each [len(x1), len(z1)]"""
+    X, Z = np.meshgrid(x1, z1, indexing="ij")
+    u, w = o.induced_velocity(g, xw, zw, X.ravel(), Z.ravel(), VC, nthreads=1)
+    u, w = u.reshape(X.shape), w.reshape(X.shape)
+    return u, w, o.vorticity(X, Z, u[None], w[None])[0]
+
+
+def _worker_nocollective(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ludvm_b200.sharded import case_slice, grid_slab
+    from oracle import ludvm_oracle as o
+    sl = case_slice(len(SWEEP_CASES), world, rank)
+    cl = [o.OracleLUDVM(**kw).Cl.copy() for kw in SWEEP_CASES[sl]]
+    g, xw, zw, x1, z1 = _ff_inputs()
+    r0, r1, h0, h1 = grid_slab(FF_NX, world, rank)
+    u, w, ome = _ff_eval(o, g, xw, zw, x1[h0:h1], z1)
+    keep = slice(r0 - h0, r1 - h0)
+    q.put((rank, (sl.start, sl.stop), cl, (r0, r1), u[keep].copy(), w[keep].copy(), ome[keep].copy()))
+    dist.barrier()                       # the only collective: nothing travels on the data path
+    dist.destroy_process_group()
+
+
+def test_two_rank_sweep_and_flowfield_slabs_equal_serial(oracle):
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker_nocollective, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # sweep: the slices tile the case list, every history equals the serial run bitwise
+    assert [r[1] for r in res] == [(0, 3), (3, 5)]
+    serial_cl = [oracle.OracleLUDVM(**kw).Cl for kw in SWEEP_CASES]
+    got = [c for r in res for c in r[2]]
+    assert len(got) == len(serial_cl) and all(np.array_equal(a, b, equal_nan=True) for a, b in zip(got, serial_cl))
+    # flow field: owned rows tile the grid; velocity AND the halo-fed vorticity stencil equal the whole-grid evaluation
+    assert [r[3] for r in res] == [(0, 19), (19, 37)]
+    us, ws, oms = _ff_eval(oracle, *_ff_inputs())
+    for k, ref in ((4, us), (5, ws), (6, oms)):
+        assert np.array_equal(np.concatenate([r[k] for r in res]), ref)
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_slab_and_case_partitions(oracle, world):
+    """Any rank count: slices tile the range, halos never leave the grid, and the per-slab vorticity of the owned rows
+    equals the whole-grid stencil (checked serially, rank by rank)."""
+    from ludvm_b200.sharded import case_slice, grid_slab
+    for n in (1, 5, 64, 4096):
+        sl = [case_slice(n, world, r) for r in range(world)]
+        assert sl[0].start == 0 and sl[-1].stop == n and all(a.stop == b.start for a, b in zip(sl, sl[1:]))
+    g, xw, zw, x1, z1 = _ff_inputs()
+    _, _, oms = _ff_eval(oracle, g, xw, zw, x1, z1)
+    rows = []
+    for r in range(world):
+        r0, r1, h0, h1 = grid_slab(FF_NX, world, r)
+        assert 0 <= h0 <= r0 <= r1 <= h1 <= FF_NX and r0 - h0 <= 1 and h1 - r1 <= 1
+        rows.append((r0, r1))
+        if r1 - r0 >= 1 and h1 - h0 >= 2:
+            _, _, ome = _ff_eval(oracle, g, xw, zw, x1[h0:h1], z1)
+            assert np.array_equal(ome[r0 - h0:r1 - h0], oms[r0:r1])
+    assert rows[0][0] == 0 and rows[-1][1] == FF_NX and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
