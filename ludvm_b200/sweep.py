@@ -27,27 +27,30 @@ def run_sweep(cases, mode="exact", ctx=None, device=0, case_slice=None):
     sel = list(cases[case_slice] if case_slice is not None else cases)
     if not sel:
         raise ValueError("empty sweep")
-    shared, params, tables, keep, objs = {}, [], [], [], []
+    # The host tables and the parameter / table structs depend on everything but LESPcrit: built once per distinct
+    # motion, copied per case (filling 4096 structs field by field cost more than the fast-mode kernel's launch).
+    shared, params, tables, objs = {}, [], [], []
     for kw in sel:
         key = tuple(sorted((k, repr(v)) for k, v in kw.items() if k != "LESPcrit"))
         if key not in shared:
             s = LUDVM(**dict(kw, verbose=False, run=False))
             tb = s.step_tables()
-            arrs = {n: f64(tb[n]) for n in TABLE_FIELDS}
-            shared[key] = (s, tb, arrs)
-        s, tb, arrs = shared[key]
-        p = SimParams()
-        for name, _ in SimParams._fields_:
-            if name in tb:
-                setattr(p, name, tb[name])
+            arrs = {n: f64(tb[n]) for n in TABLE_FIELDS}          # kept alive by `shared` until the call returns
+            p0 = SimParams()
+            for name, _ in SimParams._fields_:
+                if name in tb:
+                    setattr(p0, name, tb[name])
+            p0.mode = _lib.MODES[mode]
+            p0.store_history = 0
+            t0 = SimTables()
+            for n in TABLE_FIELDS:
+                setattr(t0, n, arrs[n].ctypes.data_as(_lib.c_dp))
+            shared[key] = (s, arrs, p0, t0)
+        s, arrs, p0, t0 = shared[key]
+        p = SimParams.from_buffer_copy(p0)
         p.lespcrit = float(kw.get("LESPcrit", s.LESPcrit))
-        p.mode = _lib.MODES[mode]
-        p.store_history = 0
-        t = SimTables()
-        for n in TABLE_FIELDS:
-            setattr(t, n, arrs[n].ctypes.data_as(_lib.c_dp))
         params.append(p)
-        tables.append(t)
+        tables.append(t0)
         objs.append(s)
     n, nt = len(sel), params[0].nt
     P = (SimParams * n)(*params)

@@ -100,3 +100,39 @@ def test_store_history_argument_is_validated_on_the_host():
     assert LUDVM(**kw, store_history=7).store_history == 7
     with pytest.raises(ValueError):
         LUDVM(**kw, store_history=-2)
+
+
+def test_sweep_host_structs_per_case(monkeypatch):
+    """run_sweep builds the parameter / table structs once per distinct motion and copies them per case: every case
+    must still carry its own LESPcrit, the tables of its own reduced frequency, and the requested mode.  The C entry
+    point is replaced by a recorder (host logic only; no device work)."""
+    import ctypes as C
+    import types
+    from ludvm_b200 import LUDVM, sweep, _lib
+    seen = {}
+
+    class FakeLib:
+        def ludvm_sweep_run(self, ctx, n, P, T, out, stride):
+            seen["n"], seen["stride"] = n, stride
+            seen["p"] = [(P[i].nt, P[i].P, P[i].Nc, P[i].mode, P[i].store_history, P[i].lespcrit, P[i].dt, P[i].vc4) for i in range(n)]
+            seen["cos1"] = [T[i].cos_a[1] for i in range(n)]            # first-step kinematics: depends on k only
+            seen["ptr"] = [C.cast(T[i].gp, C.c_void_p).value for i in range(n)]
+            return 0
+
+    monkeypatch.setattr(sweep, "load", lambda: FakeLib())
+    base = dict(t0=0, tf=1, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, Naca="0012")
+    lcs, ks = (0.1, 0.25, 0.4), (0.2, 0.9)
+    cases = sweep.lespcrit_k_grid(lcs, ks, **base)
+    res = sweep.run_sweep(cases, mode="fast", ctx=types.SimpleNamespace(handle=None))
+    assert seen["n"] == 6 and seen["stride"] == len(sweep.SW_FIELDS) * res["nt"] and res["Cl"].shape == (6, res["nt"])
+    ref = {k: LUDVM(**dict(base, k=k), verbose=False, run=False) for k in ks}
+    for i, kw in enumerate(cases):
+        nt, P, Nc, mode, hist, lc, dt, vc4 = seen["p"][i]
+        r = ref[kw["k"]]
+        assert (nt, P, Nc, mode, hist) == (r.nt, 80, 30, _lib.MODES["fast"], 0)
+        assert lc == kw["LESPcrit"] and dt == 5e-2 and vc4 == r.v_core ** 4
+        assert seen["cos1"][i] == np.cos(r.alpha[1])
+    assert len(set(seen["ptr"])) == len(ks)                               # one table set per distinct motion
+    assert seen["ptr"][0] == seen["ptr"][2] == seen["ptr"][4] and seen["ptr"][0] != seen["ptr"][1]
+    sl = sweep.run_sweep(cases, mode="exact", ctx=types.SimpleNamespace(handle=None), case_slice=slice(3, 5))
+    assert seen["n"] == 2 and [p[5] for p in seen["p"]] == [0.25, 0.4] and seen["p"][0][3] == _lib.MODES["exact"]
