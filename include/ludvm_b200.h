@@ -65,6 +65,15 @@ int ludvm_ctx_destroy(ludvm_ctx *ctx);
 int ludvm_ctx_synchronize(ludvm_ctx *ctx);
 /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
 int ludvm_ctx_launch_count(ludvm_ctx *ctx, long long *out);
+/* Which all-pairs kernel the last induced_velocity / selfconv_step / flowfield_velocity call on this context chose
+ * (diagnostic; the parity tests assert that the instantiation a benchmark times is the one they checked):
+ * out[0] = LUDVM_K_* kernel id, out[1] = target rows per thread (or per lane), out[2] = source chunks folded per row
+ * (fast kernels) or depth of the summation-tree cut (exact kernels), out[3] = 1 if sources are staged with bulk
+ * copies (TMA engine), out[4] = thread-block cluster size, out[5] = kernel variant (source-loop unroll of the fused
+ * kernel; 1 = range-flag-free instantiation of the exact kernels), out[6..7] = 0. */
+enum { LUDVM_K_NONE = 0, LUDVM_K_EXACT_ROWS = 1, LUDVM_K_EXACT_TILED = 2, LUDVM_K_FAST_ROWS = 3, LUDVM_K_FAST_TILED = 4,
+       LUDVM_K_FAST_TILED_TMA = 5, LUDVM_K_FAST32_TILED = 6, LUDVM_K_FAST32X2_TILED = 7, LUDVM_K_FAST_FUSED = 8 };
+int ludvm_ctx_last_plan(ludvm_ctx *ctx, int32_t out[8]);
 
 /*
  * induced_velocity -- replaces LUDVM.induced_velocity (LUDVM.py:549-570).

@@ -53,6 +53,7 @@ SIGNATURES = {
     "ludvm_ctx_destroy": (C.c_int, [c_vp]),
     "ludvm_ctx_synchronize": (C.c_int, [c_vp]),
     "ludvm_ctx_launch_count": (C.c_int, [c_vp, C.POINTER(C.c_longlong)]),
+    "ludvm_ctx_last_plan": (C.c_int, [c_vp, C.POINTER(C.c_int32)]),
     "ludvm_induced_velocity": (C.c_int, [c_vp, C.c_int, c_vp, C.c_long, c_vp, c_vp, c_vp, C.c_double, C.c_long,
                                          c_vp, c_vp, C.c_long, c_vp, c_vp, C.c_int]),
     "ludvm_selfconv_step": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_long, C.c_long,
@@ -123,6 +124,7 @@ class Context:
         self._h = c_vp()
         if stream is not None and int(stream) == 0:
             stream = self.CUDA_STREAM_LEGACY
+        self.stream_handle = int(stream) if stream is not None else None   # None: the library's private stream
         check(load().ludvm_ctx_create(int(device), c_vp(stream) if stream is not None else None, C.byref(self._h)))
         self.device = int(device)
 
@@ -137,6 +139,16 @@ class Context:
         n = C.c_longlong(0)
         check(load().ludvm_ctx_launch_count(self._h, C.byref(n)))
         return n.value
+
+    KERNELS = ("none", "exact_rows", "exact_tiled", "fast_rows", "fast_tiled", "fast_tiled_tma", "fast32_tiled",
+               "fast32x2_tiled", "fast_fused")
+
+    def last_plan(self):
+        """The all-pairs kernel the last call chose: dict(kernel, rows_per_thread, fold, tma, cluster, variant)."""
+        out = (C.c_int32 * 8)()
+        check(load().ludvm_ctx_last_plan(self._h, out))
+        return dict(kernel=self.KERNELS[out[0]], rows_per_thread=out[1], fold=out[2], tma=bool(out[3]),
+                    cluster=out[4], variant=out[5])
 
     def fp64_fma_rate(self, ms=200.0):
         r = C.c_double(0)

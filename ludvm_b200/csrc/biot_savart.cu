@@ -75,6 +75,16 @@ k_fast32x2_tiled(SrcView S, Tgt T, int nrows, int chunk_len, double *pu, double 
     fast32x2_tiled_block<4>(S, T, nrows, blockIdx.x, c0, c1, pu + po, pw_ + po, ssrc);
 }
 
+// Whole row sums in one launch: warp-private bulk-copy pipelines, chunk partials folded through (distributed) shared
+// memory, Euler update and peer stores in the epilogue (biot_savart.cuh, "fast fused").
+template <int R, int UNROLL, int CL, class Tgt>
+__global__ void __launch_bounds__(FW_THREADS, 2)
+k_fast_fused(SrcView S, Tgt T, int nrows, int chunk_len, int nchunks, FusedOut O)
+{
+    extern __shared__ __align__(128) unsigned char fw_raw[];
+    fast_fused_block<R, UNROLL, CL>(S, T, nrows, chunk_len, nchunks, O, *reinterpret_cast<FwSmem *>(fw_raw));
+}
+
 // Fold partials.  exact: nfold = tree depth d; fast: nfold = number of chunks.  Optional second partial set
 // (the reference's `u_wake + u_foil`, LUDVM.py:1108, :1219) and optional forward-Euler update (LUDVM.py:1108-1127).
 struct CombineArgs {
@@ -159,6 +169,93 @@ static int ilog2_ceil(long v)
     return l;
 }
 
+// Source chunking of the fast tiled kernels.  It depends on the number of SOURCES only, so a row's sum does not depend
+// on how the target rows are sharded over GPUs (G-rank results are bitwise equal to 1-rank results).
+// 16 chunks from 131072 sources (measured at 2^20 sources: 866 ms against 875 ms with 8 for 2^20 rows, and 109.4 ms
+// against 115.5 ms for the 131072 rows of one rank of eight, where 8 chunks force R = 2; 32 chunks: no further gain;
+// profiles/r01e_chunks_probe.txt).  LUDVM_FAST_CHUNKS overrides (experiments; same value on every rank).
+static void fast_chunking(int n, int *chunk_len, long *chunks)
+{
+    const char *ce = getenv("LUDVM_FAST_CHUNKS");
+    const long cap = ce ? std::max(1L, atol(ce)) : (n >= 131072 ? 16L : 8L);
+    long ch = std::max(1L, std::min(cap, (long)n / (FT_TILE * 2)));
+    *chunk_len = (int)(((n + ch - 1) / ch + FT_TILE - 1) / FT_TILE * FT_TILE);
+    *chunks = ((long)n + *chunk_len - 1) / *chunk_len;
+}
+
+static void set_plan(ludvm_ctx *ctx, int kernel, int R, int fold, int tma, int cluster, int variant = 0)
+{
+    ctx->plan[0] = kernel; ctx->plan[1] = R; ctx->plan[2] = fold; ctx->plan[3] = tma; ctx->plan[4] = cluster;
+    ctx->plan[5] = variant; ctx->plan[6] = ctx->plan[7] = 0;
+}
+
+template <int R, int UNROLL, int CL, class Tgt>
+static int launch_fused_inst(ludvm_ctx *ctx, const SrcView &S, const Tgt &T, int nrows, int chunk_len, int nchunks,
+                             const FusedOut &O)
+{
+    auto kern = k_fast_fused<R, UNROLL, CL, Tgt>;
+    static bool configured[16] = {};                       // per device; a function attribute is per device
+    if (!configured[ctx->device & 15]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwSmem)));
+        configured[ctx->device & 15] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ceil_div(nrows, 32 * R), CL, 1);
+    cfg.blockDim = dim3(FW_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = sizeof(FwSmem);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 1;
+    at[0].val.clusterDim.y = CL;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = CL > 1 ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, S, T, nrows, chunk_len, nchunks, O));
+    ctx->launches++;
+    set_plan(ctx, LUDVM_K_FAST_FUSED, R, nchunks, 1, CL, UNROLL);
+    return LUDVM_OK;
+}
+
+// The fused single-launch path: fast f64, one contiguous 16-byte aligned source segment with a scalar core, 8 or 16
+// source chunks (>= 8192 sources) and enough rows for >= ~6 waves of 2 CTAs/SM.  *launched = false: not eligible, the
+// caller takes the partial-sum path.
+template <class Tgt>
+static int try_launch_fused(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt &T, long nrows, const FusedOut &O,
+                            bool *launched)
+{
+    *launched = false;
+    if (mode != LUDVM_FAST_F64 || getenv("LUDVM_NO_FUSED") || getenv("LUDVM_NO_TMA")) return LUDVM_OK;
+    if (S.vc4 != nullptr || S.gstride != 1 || S.n0 != S.n ||
+        (((uintptr_t)S.x | (uintptr_t)S.z | (uintptr_t)S.g) & 15) != 0)
+        return LUDVM_OK;
+    int chunk_len;
+    long chunks;
+    fast_chunking(S.n, &chunk_len, &chunks);
+    if (chunks != 8 && chunks != 16) return LUDVM_OK;
+    const int CL = (int)chunks / FW_WARPS;
+    const long want = (long)ctx->sm_count * 2 * 6;
+    int R = 4;
+    while (R >= 1 && (long)ceil_div(nrows, 32 * R) * CL < want) R >>= 1;
+    if (R < 1) return LUDVM_OK;
+    const char *ue = getenv("LUDVM_FUSED_UNROLL");
+    const int U = ue ? atoi(ue) : 2;
+    int rc;
+#define FUSED_CASE(RR, UU)                                                                                      \
+    rc = CL == 2 ? launch_fused_inst<RR, UU, 2>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)               \
+                 : launch_fused_inst<RR, UU, 1>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)
+    if (R == 4 && U == 1) FUSED_CASE(4, 1);
+    else if (R == 4 && U == 4) FUSED_CASE(4, 4);
+    else if (R == 4) FUSED_CASE(4, 2);
+    else if (R == 2) FUSED_CASE(2, 4);
+    else FUSED_CASE(1, 8);
+#undef FUSED_CASE
+    if (rc) return rc;
+    CUDA_TRY(cudaGetLastError());
+    *launched = true;
+    return LUDVM_OK;
+}
+
 // Evaluate partial row sums for `nrows` targets against S; on return *nfold and the partial buffers (scratch
 // slots slot/slot+1) describe what k_combine must fold.
 template <class Tgt>
@@ -181,6 +278,7 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
             k_exact_tiled<<<dim3((unsigned)rblocks, 1u << d), ET_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, d, (double *)a,
                                                                                             (double *)b);
             ctx->launches++;
+            set_plan(ctx, LUDVM_K_EXACT_TILED, 1, d, 0, 1);
             *pu = (double *)a; *pw_ = (double *)b; *nfold = d;
             return LUDVM_OK;
         }
@@ -198,22 +296,17 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
         int blocks = (int)std::min((ntasks + 7) / 8, (long)sm * 16);
         k_exact_rows<R><<<blocks, 256, 0, ctx->stream>>>(S, T, (int)nrows, d, (double *)a, (double *)b);
         ctx->launches++;
+        set_plan(ctx, LUDVM_K_EXACT_ROWS, R, d, 0, 1);
         *pu = (double *)a; *pw_ = (double *)b; *nfold = d;
         return LUDVM_OK;
     }
     const bool f32 = (mode == LUDVM_FAST_F32);
     if (f32 || nrows >= 8192) {
-        // The source chunking depends on the number of SOURCES only, so a row's sum does not depend on how the
-        // target rows are sharded over GPUs (G-rank results are bitwise equal to 1-rank results); the rows-per-
-        // thread factor R adapts to the number of rows to keep >= ~6 waves of 2 CTAs/SM in flight.
-        // 16 chunks from 131072 sources (measured at 2^20 sources: 866 ms against 875 ms with 8 for 2^20 rows, and 109.4 ms
-        // against 115.5 ms for the 131072 rows of one rank of eight, where 8 chunks force R = 2; 32 chunks: no further gain;
-        // profiles/r01e_chunks_probe.txt).  LUDVM_FAST_CHUNKS overrides (experiments; same value on every rank).
-        const char *ce = getenv("LUDVM_FAST_CHUNKS");
-        const long cap = ce ? std::max(1L, atol(ce)) : (S.n >= 131072 ? 16L : 8L);
-        long chunks = std::max(1L, std::min(cap, (long)S.n / (FT_TILE * 2)));
-        int chunk_len = (int)(((S.n + chunks - 1) / chunks + FT_TILE - 1) / FT_TILE * FT_TILE);
-        chunks = ((long)S.n + chunk_len - 1) / chunk_len;
+        // source chunking from the number of sources only (fast_chunking); the rows-per-thread factor R adapts to the
+        // number of rows to keep >= ~6 waves of 2 CTAs/SM in flight
+        int chunk_len;
+        long chunks;
+        fast_chunking(S.n, &chunk_len, &chunks);
         // fp32: the packed fp32x2 kernel (8 rows per thread) when the core radius is a scalar and there are enough rows
         const bool f32x2 = f32 && S.vc4 == nullptr && (long)ceil_div(nrows, FT_THREADS * 8) * chunks >= (long)sm * 2 &&
                            !getenv("LUDVM_NO_F32X2");
@@ -240,6 +333,8 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
         else if (R == 2) k_fast_tiled<2><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
         else k_fast_tiled<1><<<grid, FT_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, chunk_len, (double *)a, (double *)b);
         ctx->launches++;
+        set_plan(ctx, f32x2 ? LUDVM_K_FAST32X2_TILED : f32 ? LUDVM_K_FAST32_TILED : tma ? LUDVM_K_FAST_TILED_TMA : LUDVM_K_FAST_TILED,
+                 R, (int)chunks, tma ? 1 : 0, 1);
         *pu = (double *)a; *pw_ = (double *)b; *nfold = (int)chunks;
         return LUDVM_OK;
     }
@@ -254,6 +349,7 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
     int blocks = (int)std::min((ntasks + 7) / 8, (long)sm * 16);
     k_fast_rows<<<blocks, 256, 0, ctx->stream>>>(S, T, (int)nrows, (int)chunks, (double *)a, (double *)b);
     ctx->launches++;
+    set_plan(ctx, LUDVM_K_FAST_ROWS, 1, (int)chunks, 0, 1);
     *pu = (double *)a; *pw_ = (double *)b; *nfold = (int)chunks;
     return LUDVM_OK;
 }
@@ -338,14 +434,21 @@ LUDVM_API int ludvm_induced_velocity(ludvm_ctx *ctx, int mode, const double *gam
     } else {
         SrcView S = make_src(dg, ngamma == nw ? 1 : 0, dxw, dzw, dvc, vc4, (int)nw);
         TgtArray T{dxp, dzp};
-        CombineArgs a{};
-        if ((rc = launch_partials(ctx, mode, S, T, np_, 0, (double **)&a.pu, (double **)&a.pw, &a.nfold))) return rc;
-        CUDA_TRY(cudaGetLastError());
-        a.exact = (mode == LUDVM_EXACT_F64);
-        a.nrows = (int)np_;
-        a.u = du;
-        a.w = dw;
-        if ((rc = launch_combine(ctx, a))) return rc;
+        FusedOut fo{};
+        fo.u = du;
+        fo.w = dw;
+        bool fused;
+        if ((rc = try_launch_fused(ctx, mode, S, T, np_, fo, &fused))) return rc;
+        if (!fused) {
+            CombineArgs a{};
+            if ((rc = launch_partials(ctx, mode, S, T, np_, 0, (double **)&a.pu, (double **)&a.pw, &a.nfold))) return rc;
+            CUDA_TRY(cudaGetLastError());
+            a.exact = (mode == LUDVM_EXACT_F64);
+            a.nrows = (int)np_;
+            a.u = du;
+            a.w = dw;
+            if ((rc = launch_combine(ctx, a))) return rc;
+        }
     }
     if (ptr_kind == LUDVM_PTR_HOST) {
         CUDA_TRY(cudaMemcpyAsync(u, du, (size_t)np_ * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -368,6 +471,19 @@ LUDVM_API int ludvm_selfconv_step(ludvm_ctx *ctx, int mode, const double *gamma,
     DeviceGuard g(ctx->device);
     SrcView S = make_src(gamma, 1, x, z, vc4_per_source, vc4, (int)n);
     TgtArray T{x + row0, z + row0};
+    {
+        FusedOut fo{};
+        fo.u = u_out;
+        fo.w = w_out;
+        fo.x = x + row0;
+        fo.z = z + row0;
+        fo.xo = x_out + row0;
+        fo.zo = z_out + row0;
+        fo.dt = dt;
+        bool fused;
+        if ((rc = try_launch_fused(ctx, mode, S, T, nrows, fo, &fused))) return rc;
+        if (fused) return LUDVM_OK;
+    }
     CombineArgs a{};
     if ((rc = launch_partials(ctx, mode, S, T, nrows, 0, (double **)&a.pu, (double **)&a.pw, &a.nfold))) return rc;
     CUDA_TRY(cudaGetLastError());
@@ -396,6 +512,21 @@ LUDVM_API int ludvm_selfconv_step_p2p(ludvm_ctx *ctx, int mode, const double *ga
     DeviceGuard g(ctx->device);
     SrcView S = make_src(gamma, 1, x, z, vc4_per_source, vc4, (int)n);
     TgtArray T{x + row0, z + row0};
+    for (int p = 0; p < npeers; p++) ARG_CHECK(x_out_peers[p] && z_out_peers[p]);
+    {
+        FusedOut fo{};
+        fo.x = x + row0;
+        fo.z = z + row0;
+        fo.dt = dt;
+        fo.npeers = npeers;
+        for (int p = 0; p < npeers; p++) {
+            fo.xo_peer[p] = x_out_peers[p] + row0;
+            fo.zo_peer[p] = z_out_peers[p] + row0;
+        }
+        bool fused;
+        if ((rc = try_launch_fused(ctx, mode, S, T, nrows, fo, &fused))) return rc;
+        if (fused) return LUDVM_OK;
+    }
     CombineArgs a{};
     if ((rc = launch_partials(ctx, mode, S, T, nrows, 0, (double **)&a.pu, (double **)&a.pw, &a.nfold))) return rc;
     CUDA_TRY(cudaGetLastError());
@@ -450,19 +581,28 @@ LUDVM_API int ludvm_flowfield_velocity(ludvm_ctx *ctx, int mode, const double *g
         dw = du + npts;
     }
     TgtGrid T{dx1, dz1, (int)nz, (int)row0};
-    CombineArgs a{};
     SrcView SA = make_src(dga, 1, dxa, dza, nullptr, vc4, (int)na);
-    if ((rc = launch_partials(ctx, mode, SA, T, npts, 0, (double **)&a.pu, (double **)&a.pw, &a.nfold))) return rc;
-    if (nb) {
-        SrcView SB = make_src(dgb, 1, dxb, dzb, nullptr, vc4, (int)nb);
-        if ((rc = launch_partials(ctx, mode, SB, T, npts, 2, (double **)&a.qu, (double **)&a.qw, &a.qfold))) return rc;
+    bool fused = false;
+    if (nb == 0) {   // one source set: the whole sum in one launch when eligible
+        FusedOut fo{};
+        fo.u = du;
+        fo.w = dw;
+        if ((rc = try_launch_fused(ctx, mode, SA, T, npts, fo, &fused))) return rc;
     }
-    CUDA_TRY(cudaGetLastError());
-    a.exact = (mode == LUDVM_EXACT_F64);
-    a.nrows = (int)npts;
-    a.u = du;
-    a.w = dw;
-    if ((rc = launch_combine(ctx, a))) return rc;
+    if (!fused) {
+        CombineArgs a{};
+        if ((rc = launch_partials(ctx, mode, SA, T, npts, 0, (double **)&a.pu, (double **)&a.pw, &a.nfold))) return rc;
+        if (nb) {
+            SrcView SB = make_src(dgb, 1, dxb, dzb, nullptr, vc4, (int)nb);
+            if ((rc = launch_partials(ctx, mode, SB, T, npts, 2, (double **)&a.qu, (double **)&a.qw, &a.qfold))) return rc;
+        }
+        CUDA_TRY(cudaGetLastError());
+        a.exact = (mode == LUDVM_EXACT_F64);
+        a.nrows = (int)npts;
+        a.u = du;
+        a.w = dw;
+        if ((rc = launch_combine(ctx, a))) return rc;
+    }
     if (ptr_kind == LUDVM_PTR_HOST) {
         CUDA_TRY(cudaMemcpyAsync(u, du, (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(w, dw, (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));

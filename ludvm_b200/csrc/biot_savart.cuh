@@ -668,6 +668,152 @@ __device__ __forceinline__ void fast_tiled_block_tma(const SrcView &S, const Tgt
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// fast fused ("warp-split"): the whole row sum inside one thread-block cluster -- no partial sums in global memory
+// and no combine kernel.  A CTA owns 32*R target rows; each of its 8 warps holds ALL of those rows (R per lane) and
+// walks ONE source chunk with its own private, double-buffered bulk-copy pipeline (cp.async.bulk + mbarrier, SASS
+// UBLKCP/SYNCS), so the main loop has no block-wide barrier at all.  A cluster of `cl` CTAs (1 or 2: clusters of two
+// pack the 148 SMs perfectly) covers 8*cl source chunks.  The chunk partials meet in shared memory and are folded IN
+// CHUNK ORDER through distributed shared memory -- the same canonical order as fast_combine_row, so the result is
+// bitwise equal to the partial-sum path and independent of grid size and GPU count.  The epilogue applies the forward
+// Euler update (LUDVM.py:1108-1127) and the peer stores of the fused all-gather.
+// ---------------------------------------------------------------------------------------------------
+#define FW_WARPS 8
+#define FW_THREADS (32 * FW_WARPS)
+#define FW_SUB 128       // sources per warp-private stage: three 1 KB bulk copies
+#define FW_STAGES 2
+
+struct FwWarpStage {
+    double x[FW_SUB], z[FW_SUB], g[FW_SUB];
+};
+struct FwSmem {
+    FwWarpStage st[FW_WARPS][FW_STAGES];   // 48 KB; the first 2 KB of each warp's region is reused for its partials
+    uint64_t full[FW_WARPS][FW_STAGES];
+};
+
+struct FusedOut {
+    double *u, *w;           // velocities (nullable)
+    const double *x, *z;     // Euler inputs, already offset to the first row (nullable: no update)
+    double *xo, *zo;         // Euler outputs (nullable)
+    double dt;
+    int npeers;
+    double *xo_peer[LUDVM_MAX_PEERS], *zo_peer[LUDVM_MAX_PEERS];
+};
+
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+// generic address of `p` (a shared-memory address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ const double *cluster_map(const double *p, unsigned rank)
+{
+    uint64_t out;
+    asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((uint64_t)p), "r"(rank));
+    return (const double *)out;
+}
+
+template <int R, int UNROLL, int CL, class Tgt>
+__device__ __forceinline__ void fast_fused_block(const SrcView &S, const Tgt &T, int nrows, int chunk_len, int nchunks,
+                                                 const FusedOut &O, FwSmem &sm)
+{
+    constexpr int ROWS = 32 * R;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned crank = CL > 1 ? blockIdx.y : 0;
+    const int base = blockIdx.x * ROWS + lane;
+    double tx[R], tz[R], au[R], aw[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        T.get(min(base + 32 * r, nrows - 1), tx[r], tz[r]);
+        au[r] = 0.0;
+        aw[r] = 0.0;
+    }
+    const double vc4 = S.vc4s;
+    const int c = (int)crank * FW_WARPS + warp;                      // this warp's source chunk
+    const int c0 = min(S.n, c * chunk_len), c1 = c < nchunks ? min(S.n, c0 + chunk_len) : c0;
+    const int nsub = (c1 - c0 + FW_SUB - 1) / FW_SUB;
+    FwWarpStage *st = sm.st[warp];
+    uint64_t *full = sm.full[warp];
+    if (lane == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    // producer = lane 0 of each warp: whole stages go through the copy engine, a ragged last stage is filled by the lanes
+    auto issue = [&](int k) {
+        const int t0 = c0 + k * FW_SUB, cnt = min(FW_SUB, c1 - t0);
+        FwWarpStage &b = st[k & 1];
+        if (cnt == FW_SUB) {
+            if (lane == 0) {
+                mbar_expect_tx(&full[k & 1], 3 * FW_SUB * sizeof(double));
+                bulk_g2s(b.x, S.x + t0, FW_SUB * sizeof(double), &full[k & 1]);
+                bulk_g2s(b.z, S.z + t0, FW_SUB * sizeof(double), &full[k & 1]);
+                bulk_g2s(b.g, S.g + t0, FW_SUB * sizeof(double), &full[k & 1]);
+            }
+        } else {
+            for (int j = lane; j < cnt; j += 32) {
+                b.x[j] = S.x[t0 + j];
+                b.z[j] = S.z[t0 + j];
+                b.g[j] = S.g[t0 + j];
+            }
+        }
+    };
+    if (nsub > 0) issue(0);
+    for (int k = 0; k < nsub; k++) {
+        __syncwarp();                                   // every lane is done with stage (k+1)&1 (sub-tile k-1)
+        if (k + 1 < nsub) issue(k + 1);
+        const int cnt = min(FW_SUB, c1 - (c0 + k * FW_SUB));
+        if (cnt == FW_SUB) mbar_wait(&full[k & 1], (k >> 1) & 1);
+        else __syncwarp();                              // lane-filled (always the last sub-tile)
+        const FwWarpStage &b = st[k & 1];
+#pragma unroll UNROLL
+        for (int j = 0; j < cnt; j++) {
+            const double x = b.x[j], z = b.z[j], g = b.g[j];
+#pragma unroll
+            for (int r = 0; r < R; r++) pair_fast(tx[r], tz[r], x, z, g, vc4, au[r], aw[r]);
+        }
+    }
+    // chunk partials [warp][component][row] over the front of the warp's own stage memory (all its copies have landed)
+    __syncwarp();
+    double *part = (double *)st;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        part[32 * r + lane] = au[r] * LUDVM_INV_TWO_PI;
+        part[ROWS + 32 * r + lane] = aw[r] * LUDVM_INV_TWO_PI;
+    }
+    if (CL > 1) cluster_sync_all();
+    else __syncthreads();
+    // fold in chunk order; CTA `crank` of the cluster finishes rows [crank*ROWS/CL, (crank+1)*ROWS/CL), one thread
+    // per (component, row)
+    constexpr int RPC = ROWS / CL;
+    if ((int)threadIdx.x < 2 * RPC) {
+        const int comp = (int)threadIdx.x / RPC, lrow = (int)crank * RPC + (int)threadIdx.x % RPC;
+        const int row = blockIdx.x * ROWS + lrow;
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < CL; q++) {
+            const double *p0 = (const double *)sm.st[0] + comp * ROWS + lrow;
+            const double *p = (CL > 1) ? cluster_map(p0, (unsigned)q) : p0;
+#pragma unroll
+            for (int wq = 0; wq < FW_WARPS; wq++)
+                if (q * FW_WARPS + wq < nchunks) s += p[wq * (sizeof(FwWarpStage) * FW_STAGES / sizeof(double))];
+        }
+        if (row < nrows) {
+            double *vout = comp ? O.w : O.u;
+            if (vout) vout[row] = s;
+            const double *pin = comp ? O.z : O.x;
+            if (pin) {
+                const double pn = __dadd_rn(pin[row], __dmul_rn(O.dt, s));
+                double *pout = comp ? O.zo : O.xo;
+                if (pout) pout[row] = pn;
+                for (int p = 0; p < O.npeers; p++) (comp ? O.zo_peer[p] : O.xo_peer[p])[row] = pn;   // fused all-gather
+            }
+        }
+    }
+    if (CL > 1) cluster_sync_all();                     // nobody leaves while a peer still reads its shared memory
+}
+
 // fp32 pair arithmetic; R rows per thread.
 template <int R, class Tgt>
 __device__ __forceinline__ void fast32_tiled_block(const SrcView &S, const Tgt &T, int nrows, int row_block, int c0,

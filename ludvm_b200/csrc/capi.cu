@@ -189,6 +189,13 @@ LUDVM_API int ludvm_ctx_launch_count(ludvm_ctx *ctx, long long *out)
     return LUDVM_OK;
 }
 
+LUDVM_API int ludvm_ctx_last_plan(ludvm_ctx *ctx, int32_t out[8])
+{
+    ARG_CHECK(ctx && out);
+    for (int i = 0; i < 8; i++) out[i] = ctx->plan[i];
+    return LUDVM_OK;
+}
+
 LUDVM_API int ludvm_measure_fp64_fma_rate(ludvm_ctx *ctx, double ms_target, double *dfma_per_s)
 {
     return measure_rate<double>(ctx, ms_target, dfma_per_s);

@@ -71,6 +71,14 @@ def flowfield_velocity(ga, xa, za, gb, xb, zb, vc4, x1, z1, row0=0, nrows=None, 
     return u, w
 
 
+def flowfield_velocity_device(ctx, mode, g, xw, zw, vc4, x1, z1, row0, nrows, u, w):
+    """Same for one source set with torch CUDA float64 tensors; u, w are [nrows, len(z1)] (asynchronous on ctx's
+    stream)."""
+    check(load().ludvm_flowfield_velocity(ctx.handle, _mode(mode), ptr(g), ptr(xw), ptr(zw), g.numel(), None, None,
+                                          None, 0, float(vc4), ptr(x1), x1.numel(), ptr(z1), z1.numel(), int(row0),
+                                          int(nrows), ptr(u), ptr(w), PTR_DEVICE))
+
+
 def flowfield_vorticity(x1, z1, u, w, ctx=None):
     """Finite-difference vorticity of LUDVM.py:1222-1292 on [ns,nx,nz] fields, host buffers."""
     ctx = ctx or _lib.default_context()

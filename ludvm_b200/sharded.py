@@ -51,6 +51,17 @@ class ShardedSelfConvection:
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.g = g
         self.n = x.numel()
+        # The kernels are enqueued on the context's stream while the collectives / symmetric-memory barriers run on
+        # torch's current stream: the two must be the same stream, otherwise nothing orders them.
+        if kernel is None and x.is_cuda:
+            from . import _lib
+            cur = torch.cuda.current_stream(x.device).cuda_stream
+            if ctx is None:
+                ctx = _lib.Context(x.device.index if x.device.index is not None else torch.cuda.current_device(), cur)
+                ctx.stream_handle = cur
+            elif getattr(ctx, "stream_handle", None) not in (cur, _lib.Context.CUDA_STREAM_LEGACY if cur == 0 else cur):
+                raise ValueError("ShardedSelfConvection: ctx must wrap torch's current CUDA stream "
+                                 "(_lib.Context(device, torch.cuda.current_stream().cuda_stream))")
         self.vc4, self.dt, self.mode, self.ctx = float(v_core) ** 4, float(dt), mode, ctx
         self.row0, self.nrows = shard_bounds(self.n, self.world, self.rank)
         self._kernel = kernel or self._cuda_kernel

@@ -225,6 +225,50 @@ class OracleLUDVM:
         self.path = {'airfoil': pa,
                      'airfoil_gamma_points': pa[:, :, :-1] + self.xgamma * (pa[:, :, 1:] - pa[:, :, :-1])}
 
+    # LUDVM.py:459-547 (loop form as in the reference; the one-argument arctan2 of LUDVM.py:520 is the documented fix)
+    def motion_plunge(self, G=1, T=2, alpha_m=0, h0=0, x0=0.25):
+        pi, U, nt = np.pi, self.Uinf, self.nt
+        alpha_m = alpha_m * pi / 180
+        Vmax = G * U
+        T = T * self.chord / U
+        self.G, self.T = G, T
+        al, ald, h, hd, x = (np.zeros(nt) for _ in range(5))
+        for i in range(nt):
+            ti = self.t[i]
+            al[i] = alpha_m
+            if ti <= T:
+                h[i] = h0 - Vmax * ti / 2 + Vmax * T / (4 * pi) * np.sin(2 * pi * ti / T)
+                hd[i] = - Vmax * np.sin(pi * ti / T) ** 2
+            else:
+                h[i] = h[i - 1]
+                hd[i] = 0
+            x[i] = x0 - U * ti
+        self.alpha, self.alpha_dot, self.hpiv, self.h_dot, self.xpiv = al, ald, h, hd, x
+        self.x_dot = -U * np.ones(nt)
+        self.alpha_e = al - np.arctan2(hd, U)
+        pa = np.zeros([nt, 2, self.Npoints])
+        ax, ae = self.airfoil['x'], self.airfoil['eta']
+        for i in range(nt):
+            pa[i, 0, 0] = x[i] - self.piv * np.cos(-al[i])
+            pa[i, 1, 0] = h[i] + self.piv * np.sin(-al[i])
+            pa[i, 0, 1:] = pa[i, 0, 0] + np.cos(-al[i]) * ax[1:] - np.sin(-al[i]) * ae[1:]
+            pa[i, 1, 1:] = pa[i, 1, 0] + np.sin(-al[i]) * ax[1:] + np.cos(-al[i]) * ae[1:]
+        self.path = {'airfoil': pa,
+                     'airfoil_gamma_points': pa[:, :, :-1] + self.xgamma * (pa[:, :, 1:] - pa[:, :, :-1])}
+
+    # LUDVM.py:572-595, expression order kept
+    def airfoil_downwash(self, circulation, xw, zw, i):
+        alpha, alpha_dot, h_dot = self.alpha[i], self.alpha_dot[i], self.h_dot[i]
+        xp, zp = self.path['airfoil_gamma_points'][i, 0, :], self.path['airfoil_gamma_points'][i, 1, :]
+        u1, w1 = self.induced_velocity(circulation, xw, zw, xp, zp)
+        u = u1 * np.cos(alpha) - w1 * np.sin(alpha)
+        w = u1 * np.sin(alpha) + w1 * np.cos(alpha)
+        W = self.airfoil['detadx_panel'] * (self.Uinf * np.cos(alpha) + h_dot * np.sin(alpha) + u
+                                            - alpha_dot * self.airfoil['eta_panel']) \
+            - self.Uinf * np.sin(alpha) - alpha_dot * (self.airfoil['x_panel'] - self.piv) \
+            + h_dot * np.cos(alpha) - w
+        return W
+
     def tables(self):
         return tables_from(self)
 

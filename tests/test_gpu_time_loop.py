@@ -67,7 +67,8 @@ def test_readme_tolerance_statement():
 @pytest.mark.parametrize("over", [dict(tf=6), dict(tf=4, LESPcrit=0.11, k=0.9),
                                   dict(tf=3, dt=2e-2, Npoints=61, Ncoeffs=12, chord=1.3, Uinf=1.7, alpha_m=3,
                                        alpha_max=20, k=0.7),
-                                  dict(tf=1.0, dt=2e-3)])
+                                  dict(tf=1.0, dt=2e-3),
+                                  dict(tf=0.5)])   # nt = 11: fewer wake vortices than chord stations
 def test_exact_mode_full_class_vs_oracle(oracle, over):
     """The whole drop-in class (own host geometry/kinematics) against the oracle on the same host."""
     from ludvm_b200 import LUDVM
@@ -200,3 +201,66 @@ def test_exact_tiled_convection_bit_equal_to_oracle(oracle, monkeypatch):
     monkeypatch.setenv("LUDVM_NO_EXACT_TILED", "1")
     g = LUDVM(**kw, verbose=False, mode="exact")
     assert biteq(g.L, s.L) and biteq(g.path["FREE"], s.path["FREE"])
+
+
+def test_airfoil_downwash_method_vs_oracle(oracle):
+    """`LUDVM.airfoil_downwash` (LUDVM.py:572-595) as a public method: exact mode bit-equal to the oracle's restatement
+    (itself pinned against the reference, tests/test_oracle_vs_reference.py) for wakes on both sides of the
+    few-rows/many-sources kernel switch; fast mode within 1e-12 of sum |terms|."""
+    from ludvm_b200 import LUDVM
+    kw = dict(t0=0, tf=3, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012",
+              alpha_m=3)
+    s, o = LUDVM(**kw, verbose=False), oracle.OracleLUDVM(**kw)
+    f = LUDVM(**kw, verbose=False, mode="fast", run=False)
+    rng = np.random.default_rng(3)
+    for i, nw in [(1, 1), (7, 9), (30, 130), (59, 500), (60, 40001)]:
+        g, xw, zw = rng.standard_normal(nw) * 1e-2, rng.uniform(-3, 0, nw), rng.uniform(-0.5, 0.5, nw)
+        Wo = o.airfoil_downwash(g, xw, zw, i)
+        assert biteq(s.airfoil_downwash(g, xw, zw, i), Wo), (i, nw)
+        gp = o.path["airfoil_gamma_points"][i]
+        k = np.abs(g)[None, :] / (2 * np.pi * np.sqrt(((gp[0][:, None] - xw) ** 2 + (gp[1][:, None] - zw) ** 2) ** 2
+                                                      + o.v_core ** 4))
+        scale = (k * (np.abs(gp[0][:, None] - xw) + np.abs(gp[1][:, None] - zw))).sum(1)
+        assert np.all(np.abs(f.airfoil_downwash(g, xw, zw, i) - Wo) <= 2e-12 * scale + 1e-15), (i, nw)
+
+
+def test_plunge_manoeuvre_vs_oracle(oracle):
+    """motion_plunge (LUDVM.py:459-547, arctan2 fixed) + time_loop on the device against the oracle (pinned against the
+    reference's plunge run in tests/test_oracle_vs_reference.py)."""
+    from ludvm_b200 import LUDVM
+    kw = dict(t0=0, tf=3, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012",
+              alpha_m=4)
+    s, o = LUDVM(**kw, verbose=False, run=False), oracle.OracleLUDVM(**kw, run=False)
+    for m in (s, o):
+        m.motion_plunge(G=0.8, T=2, alpha_m=4, h0=0, x0=0.25)
+        m.time_loop()
+        m.compute_coefficients()
+    for k in ("alpha", "alpha_dot", "h_dot", "hpiv", "xpiv", "alpha_e"):
+        assert biteq(getattr(s, k), getattr(o, k)), k
+    for k in HIST + ("Cl", "Cd", "Cm"):
+        assert biteq(getattr(s, k), getattr(o, k)), k
+    for k in ("TEV", "LEV", "FREE", "airfoil", "airfoil_gamma_points"):
+        assert biteq(s.path[k], o.path[k]), k
+    assert s.ilev > 0 and (s.itev, s.ilev) == (o.itev, o.ilev)
+
+
+def test_propulsive_efficiency_formula():
+    """propulsive_efficiency (LUDVM.py:1353-1372, `Uinf` -> `self.Uinf` fixed) against the reference's formula written
+    out on the golden README histories, the reference's `ii-1` period indexing (an empty first period) included."""
+    g = load_golden("readme")
+    s = _run_from_tables(g)
+    s.propulsive_efficiency()
+    kw = g["kw"]
+    t = np.arange(kw["t0"], kw["tf"] + kw["dt"], kw["dt"])
+    T = 1 / (0.2 * np.pi * kw["Uinf"] / (2 * np.pi * kw["chord"]))
+    tt = t / T
+    nper = int(np.floor(tt[-1]))
+    assert nper == 2
+    exp = np.zeros(nper)
+    with np.errstate(all="ignore"):
+        for ii in range(nper):
+            idx = np.where(np.logical_and(tt >= ii - 1, tt < ii))
+            cp = abs(g["h_dot"][idx] / kw["Uinf"] * g["Cl"][idx]) + abs(g["alpha_dot"][idx] * g["Cm"][idx] * kw["chord"] / kw["Uinf"])
+            exp[ii] = np.mean(g["Ct"][idx]) / np.mean(cp)
+    assert np.isnan(exp[0]) and np.isfinite(exp[1])
+    assert np.array_equal(s.etap, exp, equal_nan=True) and biteq(s.tt, tt)

@@ -54,3 +54,33 @@ def test_induced_velocity_random(oracle):
         u, w = b.induced_velocity(g, xw, zw, xp, zp)
         uo, wo = oracle.induced_velocity(g, xw, zw, xp, zp, 0.03)
         assert biteq(u, uo) and biteq(w, wo)
+
+
+def test_airfoil_downwash_bit_equal(oracle):
+    """LUDVM.airfoil_downwash (LUDVM.py:572-595) on the state of a finished run, at several step indices."""
+    kw = dict(ref_loader.README_KW, tf=3)
+    r, o = ref_loader.run(**kw), oracle.OracleLUDVM(**kw)
+    rng = np.random.default_rng(3)
+    for i, nw in [(1, 1), (7, 9), (30, 130), (59, 500)]:
+        g, xw, zw = rng.standard_normal(nw) * 1e-2, rng.uniform(-3, 0, nw), rng.uniform(-0.5, 0.5, nw)
+        assert biteq(r.airfoil_downwash(g, xw, zw, i), o.airfoil_downwash(g, xw, zw, i)), i
+
+
+def test_plunge_manoeuvre_bit_equal(oracle, monkeypatch):
+    """motion_plunge (LUDVM.py:459-547) + time_loop.  The reference's one-argument np.arctan2 (LUDVM.py:520) raises, so
+    the reference is run with arctan2 patched to the documented fix (arctan2(h_dot/Uinf, 1)); alpha_e is a dead local
+    there, every table the time loop consumes is untouched by the patch."""
+    real = np.arctan2
+    monkeypatch.setattr(np, "arctan2", lambda *a, **k: real(*a, **k) if len(a) == 2 else real(a[0], 1.0))
+    kw = dict(ref_loader.README_KW, tf=3, alpha_m=4)
+    r = ref_loader.run(**kw)                     # the constructor runs the sinusoidal case first (LUDVM.py:282-295)
+    r.motion_plunge(G=0.8, T=2, alpha_m=4, h0=0, x0=0.25)
+    with contextlib.redirect_stdout(io.StringIO()):
+        r.time_loop()
+        r.compute_coefficients()
+    o = oracle.OracleLUDVM(**kw, run=False)
+    o.motion_plunge(G=0.8, T=2, alpha_m=4, h0=0, x0=0.25)
+    o.time_loop()
+    o.compute_coefficients()
+    _cmp(r, o)
+    assert np.ptp(o.h_dot) > 0.5 and np.all(o.alpha_dot == 0)
