@@ -70,7 +70,10 @@ int ludvm_ctx_launch_count(ludvm_ctx *ctx, long long *out);
  * out[0] = LUDVM_K_* kernel id, out[1] = target rows per thread (or per lane), out[2] = source chunks folded per row
  * (fast kernels) or depth of the summation-tree cut (exact kernels), out[3] = 1 if sources are staged with bulk
  * copies (TMA engine), out[4] = thread-block cluster size, out[5] = kernel variant (source-loop unroll of the fused
- * kernel; 1 = range-flag-free instantiation of the exact kernels), out[6..7] = 0. */
+ * kernel; exact kernels: 1 = a range scan of the coordinates preceded the launch and selects, on the device, the
+ * instantiation without per-pair range words), out[6] = warps per CTA of the fused kernel, out[7] = exact kernels
+ * with out[5] = 1: the scan's verdict (0 = every coordinate inside the window, the flag-free instantiation ran;
+ * 1 = the flagged instantiation ran); reading it synchronises the context's stream. */
 enum { LUDVM_K_NONE = 0, LUDVM_K_EXACT_ROWS = 1, LUDVM_K_EXACT_TILED = 2, LUDVM_K_FAST_ROWS = 3, LUDVM_K_FAST_TILED = 4,
        LUDVM_K_FAST_TILED_TMA = 5, LUDVM_K_FAST32_TILED = 6, LUDVM_K_FAST32X2_TILED = 7, LUDVM_K_FAST_FUSED = 8 };
 int ludvm_ctx_last_plan(ludvm_ctx *ctx, int32_t out[8]);

@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libludvm_b200.so")
+LIB_PATH = os.environ.get("LUDVM_B200_LIB") or os.path.join(HERE, "libludvm_b200.so")   # (override: kernel experiments)
 
 EXACT_F64, FAST_F64, FAST_F32 = 0, 1, 2
 PTR_HOST, PTR_DEVICE = 0, 1
@@ -148,7 +148,7 @@ class Context:
         out = (C.c_int32 * 8)()
         check(load().ludvm_ctx_last_plan(self._h, out))
         return dict(kernel=self.KERNELS[out[0]], rows_per_thread=out[1], fold=out[2], tma=bool(out[3]),
-                    cluster=out[4], variant=out[5])
+                    cluster=out[4], variant=out[5], warps=out[6], range_bad=out[7])
 
     def fp64_fma_rate(self, ms=200.0):
         r = C.c_double(0)

@@ -7,21 +7,46 @@ namespace ludvm {
 // ---------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------
+// Range scan behind the flag-free exact kernels (common.cuh, coord_in_safe_window): *bad |= 1 if any coordinate of the
+// four arrays lies outside the window in which the branch-free division / square root need no range test.
+__global__ void __launch_bounds__(256) k_range_scan(const double *a, int na, const double *b, int nb, const double *c,
+                                                    int nc, const double *d, int nd, int *bad)
+{
+    const long tot = (long)na + nb + nc + nd;
+    bool ok = true;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long)gridDim.x * blockDim.x) {
+        double v;
+        if (i < na) v = a[i];
+        else if (i < (long)na + nb) v = b[i - na];
+        else if (i < (long)na + nb + nc) v = c[i - na - nb];
+        else v = d[i - na - nb - nc];
+        ok = ok && coord_in_safe_window(v);
+    }
+    if (!ok) atomicOr(bad, 1);
+}
+
+// `bad`: nullptr = always evaluate the range words; otherwise the scan's verdict selects the instantiation (uniform).
 template <int R, class Tgt>
-__global__ void __launch_bounds__(256) k_exact_rows(SrcView S, Tgt T, int nrows, int d, double *pu, double *pw_)
+__global__ void __launch_bounds__(256) k_exact_rows(SrcView S, Tgt T, int nrows, int d, double *pu, double *pw_,
+                                                    const int *bad)
 {
     int lane = threadIdx.x & 31;
     long gw = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     long nwarps = (long)gridDim.x * (blockDim.x >> 5);
     long ntasks = (long)((nrows + 4 * R - 1) / (4 * R)) << d;
-    for (long t = gw; t < ntasks; t += nwarps) exact_rows_warp_task<R>(S, T, nrows, d, t, lane, pu, pw_);
+    if (bad && *bad == 0)
+        for (long t = gw; t < ntasks; t += nwarps) exact_rows_warp_task<R, false>(S, T, nrows, d, t, lane, pu, pw_);
+    else
+        for (long t = gw; t < ntasks; t += nwarps) exact_rows_warp_task<R, true>(S, T, nrows, d, t, lane, pu, pw_);
 }
 
 template <class Tgt>
-__global__ void __launch_bounds__(ET_THREADS, 3) k_exact_tiled(SrcView S, Tgt T, int nrows, int d, double *pu, double *pw_)
+__global__ void __launch_bounds__(ET_THREADS, 3) k_exact_tiled(SrcView S, Tgt T, int nrows, int d, double *pu, double *pw_,
+                                                               const int *bad)
 {
     __shared__ __align__(16) double2 sxz[ET_TILE], sgv[ET_TILE];
-    exact_tiled_block(S, T, nrows, blockIdx.x, d, blockIdx.y, pu, pw_, sxz, sgv);
+    if (bad && *bad == 0) exact_tiled_block<false>(S, T, nrows, blockIdx.x, d, blockIdx.y, pu, pw_, sxz, sgv);
+    else exact_tiled_block<true>(S, T, nrows, blockIdx.x, d, blockIdx.y, pu, pw_, sxz, sgv);
 }
 
 template <class Tgt>
@@ -77,12 +102,12 @@ k_fast32x2_tiled(SrcView S, Tgt T, int nrows, int chunk_len, double *pu, double 
 
 // Whole row sums in one launch: warp-private bulk-copy pipelines, chunk partials folded through (distributed) shared
 // memory, Euler update and peer stores in the epilogue (biot_savart.cuh, "fast fused").
-template <int R, int UNROLL, int CL, class Tgt>
-__global__ void __launch_bounds__(FW_THREADS, 2)
+template <int R, int UNROLL, int WARPS, int CL, class Tgt>
+__global__ void __launch_bounds__(32 * WARPS, 16 / WARPS)
 k_fast_fused(SrcView S, Tgt T, int nrows, int chunk_len, int nchunks, FusedOut O)
 {
     extern __shared__ __align__(128) unsigned char fw_raw[];
-    fast_fused_block<R, UNROLL, CL>(S, T, nrows, chunk_len, nchunks, O, *reinterpret_cast<FwSmem *>(fw_raw));
+    fast_fused_block<R, UNROLL, WARPS, CL>(S, T, nrows, chunk_len, nchunks, O, *reinterpret_cast<FwSmem<WARPS> *>(fw_raw));
 }
 
 // Fold partials.  exact: nfold = tree depth d; fast: nfold = number of chunks.  Optional second partial set
@@ -189,20 +214,54 @@ static void set_plan(ludvm_ctx *ctx, int kernel, int R, int fold, int tma, int c
     ctx->plan[5] = variant; ctx->plan[6] = ctx->plan[7] = 0;
 }
 
-template <int R, int UNROLL, int CL, class Tgt>
+// Targets as (up to) two coordinate arrays for the range scan.
+static void tgt_arrays(const TgtArray &T, long nrows, const double **a, int *na, const double **b, int *nb)
+{
+    *a = T.x; *na = (int)nrows; *b = T.z; *nb = (int)nrows;
+}
+static void tgt_arrays(const TgtGrid &T, long nrows, const double **a, int *na, const double **b, int *nb)
+{
+    *a = T.x1 + T.row0; *na = (int)((nrows + T.nz - 1) / T.nz); *b = T.z1; *nb = T.nz;
+}
+
+// Launch the range scan for an exact-mode evaluation; *flag = device flag for the kernels, or nullptr when the proof
+// does not apply (per-source cores, vc^4 outside its window -- e.g. viscous=False --, LUDVM_EXACT_FLAGS=1).
+template <class Tgt>
+static int prove_exact_ranges(ludvm_ctx *ctx, const SrcView &S, const Tgt &T, long nrows, const int **flag)
+{
+    *flag = nullptr;
+    if (S.vc4 != nullptr || !vc4_in_safe_window(S.vc4s) || S.n0 != S.n || getenv("LUDVM_EXACT_FLAGS")) return LUDVM_OK;
+    void *p;
+    int rc = scratch_reserve(ctx, 7, 256, &p);
+    if (rc) return rc;
+    int *bad = (int *)((char *)p + 128);
+    CUDA_TRY(cudaMemsetAsync(bad, 0, sizeof(int), ctx->stream));
+    const double *ta, *tb;
+    int na, nb;
+    tgt_arrays(T, nrows, &ta, &na, &tb, &nb);
+    const long tot = 2L * S.n + na + nb;
+    const int blocks = (int)std::min<long>((tot + 1023) / 1024, (long)ctx->sm_count * 8);
+    k_range_scan<<<blocks, 256, 0, ctx->stream>>>(S.x, S.n, S.z, S.n, ta, na, tb, nb, bad);
+    ctx->launches++;
+    ctx->range_flag = bad;
+    *flag = bad;
+    return LUDVM_OK;
+}
+
+template <int R, int UNROLL, int WARPS, int CL, class Tgt>
 static int launch_fused_inst(ludvm_ctx *ctx, const SrcView &S, const Tgt &T, int nrows, int chunk_len, int nchunks,
                              const FusedOut &O)
 {
-    auto kern = k_fast_fused<R, UNROLL, CL, Tgt>;
+    auto kern = k_fast_fused<R, UNROLL, WARPS, CL, Tgt>;
     static bool configured[16] = {};                       // per device; a function attribute is per device
     if (!configured[ctx->device & 15]) {
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwSmem)));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwSmem<WARPS>)));
         configured[ctx->device & 15] = true;
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)ceil_div(nrows, 32 * R), CL, 1);
-    cfg.blockDim = dim3(FW_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = sizeof(FwSmem);
+    cfg.blockDim = dim3(32 * WARPS, 1, 1);
+    cfg.dynamicSmemBytes = sizeof(FwSmem<WARPS>);
     cfg.stream = ctx->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
@@ -214,6 +273,7 @@ static int launch_fused_inst(ludvm_ctx *ctx, const SrcView &S, const Tgt &T, int
     CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, S, T, nrows, chunk_len, nchunks, O));
     ctx->launches++;
     set_plan(ctx, LUDVM_K_FAST_FUSED, R, nchunks, 1, CL, UNROLL);
+    ctx->plan[6] = WARPS;
     return LUDVM_OK;
 }
 
@@ -233,17 +293,21 @@ static int try_launch_fused(ludvm_ctx *ctx, int mode, const SrcView &S, const Tg
     long chunks;
     fast_chunking(S.n, &chunk_len, &chunks);
     if (chunks != 8 && chunks != 16) return LUDVM_OK;
-    const int CL = (int)chunks / FW_WARPS;
+    // 16 chunks: one 16-warp CTA per SM (LUDVM_FUSED_WARPS=16) or a cluster of two 8-warp CTAs (default)
+    const char *we = getenv("LUDVM_FUSED_WARPS");
+    const int W = (chunks == 16 && we && atoi(we) == 16) ? 16 : 8;
+    const int CL = (int)chunks / W;
     const long want = (long)ctx->sm_count * 2 * 6;
     int R = 4;
-    while (R >= 1 && (long)ceil_div(nrows, 32 * R) * CL < want) R >>= 1;
+    while (R >= 1 && (long)ceil_div(nrows, 32 * R) * (chunks / 8) < want) R >>= 1;
     if (R < 1) return LUDVM_OK;
     const char *ue = getenv("LUDVM_FUSED_UNROLL");
     const int U = ue ? atoi(ue) : 2;
     int rc;
-#define FUSED_CASE(RR, UU)                                                                                      \
-    rc = CL == 2 ? launch_fused_inst<RR, UU, 2>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)               \
-                 : launch_fused_inst<RR, UU, 1>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)
+#define FUSED_CASE(RR, UU)                                                                                          \
+    rc = W == 16 ? launch_fused_inst<RR, UU, 16, 1>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)               \
+       : CL == 2 ? launch_fused_inst<RR, UU, 8, 2>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)                \
+                 : launch_fused_inst<RR, UU, 8, 1>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)
     if (R == 4 && U == 1) FUSED_CASE(4, 1);
     else if (R == 4 && U == 4) FUSED_CASE(4, 4);
     else if (R == 4) FUSED_CASE(4, 2);
@@ -264,6 +328,11 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
 {
     const int sm = ctx->sm_count;
     if (mode == LUDVM_EXACT_F64) {
+        const int *bad;
+        {
+            int rc = prove_exact_ranges(ctx, S, T, nrows, &bad);
+            if (rc) return rc;
+        }
         if (nrows >= 4096 && (S.n >= 1024 || nrows >= (long)sm * ET_THREADS * 3)) {   // (few sources: only if the rows alone fill the GPU)
             // Many rows: one thread per row, sources staged through shared memory; the tree is cut at depth d so
             // that >= ~6 waves of 4 CTAs/SM are in flight.
@@ -276,9 +345,9 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
             if ((rc = scratch_reserve(ctx, slot, bytes, &a))) return rc;
             if ((rc = scratch_reserve(ctx, slot + 1, bytes, &b))) return rc;
             k_exact_tiled<<<dim3((unsigned)rblocks, 1u << d), ET_THREADS, 0, ctx->stream>>>(S, T, (int)nrows, d, (double *)a,
-                                                                                            (double *)b);
+                                                                                            (double *)b, bad);
             ctx->launches++;
-            set_plan(ctx, LUDVM_K_EXACT_TILED, 1, d, 0, 1);
+            set_plan(ctx, LUDVM_K_EXACT_TILED, 1, d, 0, 1, bad ? 1 : 0);
             *pu = (double *)a; *pw_ = (double *)b; *nfold = d;
             return LUDVM_OK;
         }
@@ -294,9 +363,9 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
         if ((rc = scratch_reserve(ctx, slot + 1, bytes, &b))) return rc;
         long ntasks = nquads << d;
         int blocks = (int)std::min((ntasks + 7) / 8, (long)sm * 16);
-        k_exact_rows<R><<<blocks, 256, 0, ctx->stream>>>(S, T, (int)nrows, d, (double *)a, (double *)b);
+        k_exact_rows<R><<<blocks, 256, 0, ctx->stream>>>(S, T, (int)nrows, d, (double *)a, (double *)b, bad);
         ctx->launches++;
-        set_plan(ctx, LUDVM_K_EXACT_ROWS, R, d, 0, 1);
+        set_plan(ctx, LUDVM_K_EXACT_ROWS, R, d, 0, 1, bad ? 1 : 0);
         *pu = (double *)a; *pw_ = (double *)b; *nfold = d;
         return LUDVM_OK;
     }

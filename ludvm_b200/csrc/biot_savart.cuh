@@ -79,7 +79,7 @@ __device__ __forceinline__ void exact_term(const SrcView &S, double xp, double z
 // K consecutive terms (sources j0, j0+8, ...) of one lane's accumulators for its R target rows: branch-free fast
 // paths so the R*K div/sqrt chains interleave, library routines only if a range flag came back set; the adds keep
 // numpy's order.  A source is loaded once for the lane's R rows.
-template <int R, int K>
+template <int R, int K, bool FLAGS = true>
 __device__ __forceinline__ void exact_batch(const SrcView &S, const double (&xp)[R], const double (&zp)[R], int j0,
                                             double (&au)[R], double (&aw)[R])
 {
@@ -93,7 +93,7 @@ __device__ __forceinline__ void exact_batch(const SrcView &S, const double (&xp)
             xps[k * R + r] = xp[r]; zps[k * R + r] = zp[r];
         }
     }
-    if (!pair_exact_try_batch<R * K>(xps, zps, xw, zw, g, vc4, tu, tw)) {
+    if (!pair_exact_try_batch<R * K, FLAGS>(xps, zps, xw, zw, g, vc4, tu, tw)) {
 #pragma unroll
         for (int c = 0; c < R * K; c++) pair_exact_ref(xps[c], zps[c], xw[c], zw[c], g[c], vc4[c], tu[c], tw[c]);
     }
@@ -107,7 +107,7 @@ __device__ __forceinline__ void exact_batch(const SrcView &S, const double (&xp)
 }
 
 // One leaf (n <= 128) of numpy's pairwise sum for the R rows of each 8-lane group.  Result on every lane.
-template <int R>
+template <int R, bool FLAGS = true>
 __device__ __forceinline__ void exact_leaf_group(const SrcView &S, const double (&xp)[R], const double (&zp)[R],
                                                  int off, int m, int lane8, double (&au)[R], double (&aw)[R])
 {
@@ -119,16 +119,16 @@ __device__ __forceinline__ void exact_leaf_group(const SrcView &S, const double 
     if (body) {
         const int nb = body >> 3;  // terms per lane, uniform across the warp
         int b = 0;
-        for (; b + K <= nb; b += K) exact_batch<R, K>(S, xp, zp, off + 8 * b + lane8, au, aw);
+        for (; b + K <= nb; b += K) exact_batch<R, K, FLAGS>(S, xp, zp, off + 8 * b + lane8, au, aw);
         if (K == 4) {
             switch (nb - b) {
-            case 3: exact_batch<R, 3>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
-            case 2: exact_batch<R, 2>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
-            case 1: exact_batch<R, 1>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
+            case 3: exact_batch<R, 3, FLAGS>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
+            case 2: exact_batch<R, 2, FLAGS>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
+            case 1: exact_batch<R, 1, FLAGS>(S, xp, zp, off + 8 * b + lane8, au, aw); break;
             default: break;
             }
         } else if (nb - b) {
-            exact_batch<R, 1>(S, xp, zp, off + 8 * b + lane8, au, aw);
+            exact_batch<R, 1, FLAGS>(S, xp, zp, off + 8 * b + lane8, au, aw);
         }
 #pragma unroll
         for (int r = 0; r < R; r++)
@@ -157,7 +157,7 @@ __device__ __forceinline__ void exact_leaf_group(const SrcView &S, const double 
 
 // Pairwise sum over the logical source range [off, off+n) -- a node of the tree -- for the group's R targets.
 // Must be called by all 32 lanes with identical (off, n).
-template <int R>
+template <int R, bool FLAGS = true>
 __device__ inline void exact_node_group(const SrcView &S, const double (&xp)[R], const double (&zp)[R], int off, int n,
                                         int lane8, double (&su)[R], double (&sw)[R])
 {
@@ -175,7 +175,7 @@ __device__ inline void exact_node_group(const SrcView &S, const double (&xp)[R],
             n = n2;
         }
         double ru[R], rw[R];
-        exact_leaf_group<R>(S, xp, zp, off, n, lane8, ru, rw);
+        exact_leaf_group<R, FLAGS>(S, xp, zp, off, n, lane8, ru, rw);
         for (;;) {
             if (sp == 0) {
 #pragma unroll
@@ -202,7 +202,7 @@ __device__ inline void exact_node_group(const SrcView &S, const double (&xp)[R],
 
 // Warp task t -> (tree node b, row group q of 4*R rows: 8-lane group k owns rows q*4R + k*R .. +R).
 // Partials: pu[b * nrows + row].
-template <int R = 1, class Tgt>
+template <int R = 1, bool FLAGS = true, class Tgt>
 __device__ __forceinline__ void exact_rows_warp_task(const SrcView &S, const Tgt &T, int nrows, int d, long t,
                                                      int lane, double *__restrict__ pu, double *__restrict__ pw_)
 {
@@ -216,7 +216,7 @@ __device__ __forceinline__ void exact_rows_warp_task(const SrcView &S, const Tgt
     int off, len;
     pw_node(S.n, d, b, off, len);
     double su[R], sw[R];
-    exact_node_group<R>(S, xp, zp, off, len, lane & 7, su, sw);
+    exact_node_group<R, FLAGS>(S, xp, zp, off, len, lane & 7, su, sw);
     if ((lane & 7) == 0) {
 #pragma unroll
         for (int r = 0; r < R; r++)
@@ -273,7 +273,7 @@ struct SmemSrc3 {
 };
 
 // au[k] += term(source k), k = 0..3, for one target.
-template <class Src>
+template <bool FLAGS = true, class Src>
 __device__ __forceinline__ void exact_quad_smem(const Src src, double xp, double zp, double &u0, double &u1, double &u2,
                                                 double &u3, double &w0, double &w1, double &w2, double &w3)
 {
@@ -283,7 +283,7 @@ __device__ __forceinline__ void exact_quad_smem(const Src src, double xp, double
         src.get(k, xw[k], zw[k], g[k], vc4[k]);
         xps[k] = xp; zps[k] = zp;
     }
-    if (!pair_exact_try_batch<4>(xps, zps, xw, zw, g, vc4, tu, tw)) {
+    if (!pair_exact_try_batch<4, FLAGS>(xps, zps, xw, zw, g, vc4, tu, tw)) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {   // rare: re-read the sources rather than keep them alive across the batch
             double x, z, gg, v;
@@ -296,7 +296,7 @@ __device__ __forceinline__ void exact_quad_smem(const Src src, double xp, double
 }
 
 // One leaf (m <= 128 staged sources) of numpy's pairwise sum for the thread's target.
-template <class Src>
+template <bool FLAGS = true, class Src>
 __device__ __forceinline__ void exact_leaf_thread(const Src src, int m, double xp, double zp, double &ru, double &rw)
 {
     const int body = (m >= 8) ? (m & ~7) : 0;
@@ -306,8 +306,8 @@ __device__ __forceinline__ void exact_leaf_thread(const Src src, int m, double x
 #pragma unroll
         for (int k = 0; k < 8; k++) u[k] = w[k] = -0.0;   // -0.0 + t == t bit for bit
         for (int i = 0; i < body; i += 8) {
-            exact_quad_smem(src.at(i), xp, zp, u[0], u[1], u[2], u[3], w[0], w[1], w[2], w[3]);
-            exact_quad_smem(src.at(i + 4), xp, zp, u[4], u[5], u[6], u[7], w[4], w[5], w[6], w[7]);
+            exact_quad_smem<FLAGS>(src.at(i), xp, zp, u[0], u[1], u[2], u[3], w[0], w[1], w[2], w[3]);
+            exact_quad_smem<FLAGS>(src.at(i + 4), xp, zp, u[4], u[5], u[6], u[7], w[4], w[5], w[6], w[7]);
         }
         su = __dadd_rn(__dadd_rn(__dadd_rn(u[0], u[1]), __dadd_rn(u[2], u[3])),
                        __dadd_rn(__dadd_rn(u[4], u[5]), __dadd_rn(u[6], u[7])));
@@ -327,7 +327,7 @@ __device__ __forceinline__ void exact_leaf_thread(const Src src, int m, double x
 
 // The whole pairwise tree over n sources resident in shared memory, for the thread's target (no barriers inside:
 // threads may call it a different number of times).
-template <class Src>
+template <bool FLAGS = true, class Src>
 __device__ __forceinline__ void exact_tree_thread(const Src src, int n, double xp, double zp, double &su, double &sw)
 {
     int r_off[PW_MAX_STACK], r_len[PW_MAX_STACK];
@@ -344,7 +344,7 @@ __device__ __forceinline__ void exact_tree_thread(const Src src, int n, double x
             n = n2;
         }
         double ru, rw;
-        exact_leaf_thread(src.at(off), n, xp, zp, ru, rw);
+        exact_leaf_thread<FLAGS>(src.at(off), n, xp, zp, ru, rw);
         for (;;) {
             if (sp == 0) {
                 su = ru;
@@ -366,7 +366,7 @@ __device__ __forceinline__ void exact_tree_thread(const Src src, int n, double x
     }
 }
 
-template <class Tgt>
+template <bool FLAGS = true, class Tgt>
 __device__ __forceinline__ void exact_tiled_block(const SrcView &S, const Tgt &T, int nrows, int row_block, int d, int b,
                                                   double *__restrict__ pu, double *__restrict__ pw_, double2 *sxz,
                                                   double2 *sgv)
@@ -403,7 +403,7 @@ __device__ __forceinline__ void exact_tiled_block(const SrcView &S, const Tgt &T
             }
             __syncthreads();
         }
-        exact_leaf_thread(SmemSrc4{sxz + (off - tile0), sgv + (off - tile0)}, n, xp, zp, ru, rw);
+        exact_leaf_thread<FLAGS>(SmemSrc4{sxz + (off - tile0), sgv + (off - tile0)}, n, xp, zp, ru, rw);
         bool done = false;
         for (;;) {
             if (sp == 0) {
@@ -670,25 +670,27 @@ __device__ __forceinline__ void fast_tiled_block_tma(const SrcView &S, const Tgt
 
 // ---------------------------------------------------------------------------------------------------
 // fast fused ("warp-split"): the whole row sum inside one thread-block cluster -- no partial sums in global memory
-// and no combine kernel.  A CTA owns 32*R target rows; each of its 8 warps holds ALL of those rows (R per lane) and
+// and no combine kernel.  A CTA owns 32*R target rows; each of its WARPS warps holds ALL of those rows (R per lane) and
 // walks ONE source chunk with its own private, double-buffered bulk-copy pipeline (cp.async.bulk + mbarrier, SASS
-// UBLKCP/SYNCS), so the main loop has no block-wide barrier at all.  A cluster of `cl` CTAs (1 or 2: clusters of two
-// pack the 148 SMs perfectly) covers 8*cl source chunks.  The chunk partials meet in shared memory and are folded IN
+// UBLKCP/SYNCS), so the main loop has no block-wide barrier at all.  A cluster of CL CTAs (1 or 2: clusters of two
+// pack the 148 SMs perfectly) covers WARPS*CL source chunks: 8 chunks = one 8-warp CTA, 16 chunks = one 16-warp CTA
+// or a cluster of two 8-warp CTAs.  The chunk partials meet in shared memory and are folded IN
 // CHUNK ORDER through distributed shared memory -- the same canonical order as fast_combine_row, so the result is
 // bitwise equal to the partial-sum path and independent of grid size and GPU count.  The epilogue applies the forward
 // Euler update (LUDVM.py:1108-1127) and the peer stores of the fused all-gather.
 // ---------------------------------------------------------------------------------------------------
-#define FW_WARPS 8
-#define FW_THREADS (32 * FW_WARPS)
+#ifndef FW_SUB
 #define FW_SUB 128       // sources per warp-private stage: three 1 KB bulk copies
+#endif
 #define FW_STAGES 2
 
 struct FwWarpStage {
     double x[FW_SUB], z[FW_SUB], g[FW_SUB];
 };
+template <int WARPS>
 struct FwSmem {
-    FwWarpStage st[FW_WARPS][FW_STAGES];   // 48 KB; the first 2 KB of each warp's region is reused for its partials
-    uint64_t full[FW_WARPS][FW_STAGES];
+    FwWarpStage st[WARPS][FW_STAGES];   // 6 KB per warp; the front of each warp's region is reused for its partials
+    uint64_t full[WARPS][FW_STAGES];
 };
 
 struct FusedOut {
@@ -713,10 +715,11 @@ __device__ __forceinline__ const double *cluster_map(const double *p, unsigned r
     return (const double *)out;
 }
 
-template <int R, int UNROLL, int CL, class Tgt>
+template <int R, int UNROLL, int WARPS, int CL, class Tgt>
 __device__ __forceinline__ void fast_fused_block(const SrcView &S, const Tgt &T, int nrows, int chunk_len, int nchunks,
-                                                 const FusedOut &O, FwSmem &sm)
+                                                 const FusedOut &O, FwSmem<WARPS> &sm)
 {
+    constexpr int FW_WARPS = WARPS;
     constexpr int ROWS = 32 * R;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned crank = CL > 1 ? blockIdx.y : 0;

@@ -193,6 +193,13 @@ LUDVM_API int ludvm_ctx_last_plan(ludvm_ctx *ctx, int32_t out[8])
 {
     ARG_CHECK(ctx && out);
     for (int i = 0; i < 8; i++) out[i] = ctx->plan[i];
+    if ((ctx->plan[0] == LUDVM_K_EXACT_ROWS || ctx->plan[0] == LUDVM_K_EXACT_TILED) && ctx->plan[5] == 1 && ctx->range_flag) {
+        DeviceGuard g(ctx->device);   // which instantiation the kernel took is decided on the device: read the verdict
+        int bad = 0;
+        CUDA_TRY(cudaMemcpyAsync(&bad, ctx->range_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        out[7] = bad;
+    }
     return LUDVM_OK;
 }
 

@@ -37,13 +37,22 @@ def timed(nrows, reps=3):
 
 dfma = ctx.fp64_fma_rate(300.0)
 print("dfma/s %.4g" % dfma)
-for nrows in (N, N // 8, N // 2):
-    for env in ({"LUDVM_NO_FUSED": "1"}, {"LUDVM_FUSED_UNROLL": "1"}, {"LUDVM_FUSED_UNROLL": "2"}, {"LUDVM_FUSED_UNROLL": "4"}):
-        for k in ("LUDVM_NO_FUSED", "LUDVM_FUSED_UNROLL"):
+CONFIGS = [{"LUDVM_NO_FUSED": "1"}, {"LUDVM_FUSED_UNROLL": "2"}, {"LUDVM_FUSED_UNROLL": "4"},
+           {"LUDVM_FUSED_WARPS": "16", "LUDVM_FUSED_UNROLL": "2"}, {"LUDVM_FUSED_WARPS": "16", "LUDVM_FUSED_UNROLL": "4"},
+           {"LUDVM_FAST_CHUNKS": "8", "LUDVM_NO_FUSED": "1"}, {"LUDVM_FAST_CHUNKS": "8", "LUDVM_FUSED_UNROLL": "2"},
+           {"LUDVM_FAST_CHUNKS": "8", "LUDVM_FUSED_UNROLL": "4"}]
+if os.environ.get("PROBE_FUSED_ONLY"):
+    CONFIGS = [c for c in CONFIGS if "LUDVM_NO_FUSED" not in c]
+KEYS = ("LUDVM_NO_FUSED", "LUDVM_FUSED_UNROLL", "LUDVM_FUSED_WARPS", "LUDVM_FAST_CHUNKS")
+print("lib", _lib.LIB_PATH)
+for nrows in (N, N // 8):
+    for env in CONFIGS:
+        for k in KEYS:
             os.environ.pop(k, None)
         os.environ.update(env)
         ms = timed(nrows)
         p = ctx.last_plan()
         rate = float(nrows) * N / (ms * 1e-3)
-        print("rows %8d  %-28s %-14s R=%d cl=%d  %9.3f ms  %.4g pairs/s  %.3f of dfma" %
-              (nrows, env, p["kernel"], p["rows_per_thread"], p["cluster"], ms, rate, rate * 13 / dfma), flush=True)
+        print("rows %8d  %-62s %-14s R=%d cl=%d w=%d  %9.3f ms  %.4g pairs/s  %.3f of dfma" %
+              (nrows, env, p["kernel"], p["rows_per_thread"], p["cluster"], p["warps"], ms, rate, rate * 13 / dfma),
+              flush=True)

@@ -64,7 +64,7 @@ def test_selfconv_step_2p20_fast_vs_oracle(cloud, oracle, monkeypatch):
     per-rank launch of the 8-GPU run) and the p2p entry point against the full launch bit for bit."""
     g, x, z = cloud["g"], cloud["x"], cloud["z"]
     u, w, xo, zo, plan = _step(cloud, "fast")
-    assert plan == dict(kernel="fast_fused", rows_per_thread=4, fold=16, tma=True, cluster=2, variant=2), plan
+    assert plan == dict(kernel="fast_fused", rows_per_thread=4, fold=16, tma=True, cluster=2, variant=2, warps=8, range_bad=0), plan
     rows = np.sort(np.random.default_rng(7).choice(N, 4096, replace=False))
     uo, wo = oracle.induced_velocity(g, x, z, x[rows], z[rows], VCORE)
     assert np.max(np.abs(u[rows] - uo)) <= 1e-12 * np.max(np.abs(uo))
@@ -76,7 +76,7 @@ def test_selfconv_step_2p20_fast_vs_oracle(cloud, oracle, monkeypatch):
     # the partial-sum path bench.py timed in round 1
     monkeypatch.setenv("LUDVM_NO_FUSED", "1")
     u2, w2, xo2, zo2, plan2 = _step(cloud, "fast")
-    assert plan2 == dict(kernel="fast_tiled_tma", rows_per_thread=4, fold=16, tma=True, cluster=1, variant=0), plan2
+    assert plan2 == dict(kernel="fast_tiled_tma", rows_per_thread=4, fold=16, tma=True, cluster=1, variant=0, warps=0, range_bad=0), plan2
     assert biteq(u2, u) and biteq(w2, w) and biteq(xo2, xo) and biteq(zo2, zo)
     us, ws, xs, zs, plans = _step(cloud, "fast", row0=3 * (N // 8), nrows=N // 8)
     assert plans["kernel"] == "fast_tiled_tma" and plans["rows_per_thread"] == 4 and plans["fold"] == 16
@@ -131,7 +131,7 @@ def test_selfconv_step_2p17_exact_all_rows_bit_equal(cloud, oracle):
     n = 1 << 17
     g, x, z = cloud["g"][:n], cloud["x"][:n], cloud["z"][:n]
     u, w, xo, zo, plan = _step(cloud, "exact", n=n)
-    assert plan["kernel"] == "exact_tiled", plan
+    assert plan["kernel"] == "exact_tiled" and plan["variant"] == 1 and plan["range_bad"] == 0, plan   # flag-free
     uo, wo = oracle.induced_velocity(g, x, z, x, z, VCORE)
     assert biteq(u, uo) and biteq(w, wo)
     assert biteq(xo, x + DT * uo) and biteq(zo, z + DT * wo)
@@ -172,7 +172,7 @@ def test_flowfield_quarter_million_points(cloud, oracle, monkeypatch):
     vc4, ctx = VCORE ** 4, cloud["ctx"]
     u, w = ops.flowfield_velocity(g, xw, zw, None, None, None, vc4, x1, z1, mode="fast", ctx=ctx)
     plan = ctx.last_plan()
-    assert plan == dict(kernel="fast_fused", rows_per_thread=4, fold=16, tma=True, cluster=2, variant=2), plan
+    assert plan == dict(kernel="fast_fused", rows_per_thread=4, fold=16, tma=True, cluster=2, variant=2, warps=8, range_bad=0), plan
     pts = np.sort(np.random.default_rng(3).choice(512 * 512, 2048, replace=False))
     X, Z = np.meshgrid(x1, z1, indexing="ij")
     uo, wo = oracle.induced_velocity(g, xw, zw, X.ravel()[pts], Z.ravel()[pts], VCORE)
@@ -188,7 +188,7 @@ def test_flowfield_quarter_million_points(cloud, oracle, monkeypatch):
     u2, w2 = ops.flowfield_velocity(g, xw, zw, None, None, None, vc4, x1, z1, mode="fast", ctx=ctx)
     monkeypatch.delenv("LUDVM_NO_FUSED")
     plan2 = ctx.last_plan()
-    assert plan2 == dict(kernel="fast_tiled_tma", rows_per_thread=4, fold=16, tma=True, cluster=1, variant=0), plan2
+    assert plan2 == dict(kernel="fast_tiled_tma", rows_per_thread=4, fold=16, tma=True, cluster=1, variant=0, warps=0, range_bad=0), plan2
     assert biteq(u2, u) and biteq(w2, w)
     # with a second (bound-vortex) source set the partial-sum path serves both sets; compare with the sum of two calls
     gb, xb, zb = np.linspace(0.01, 0.02, 80), np.linspace(-1.0, 0.0, 80), np.zeros(80)

@@ -114,3 +114,57 @@ def test_linearity_and_self_term(ops):
     assert np.array_equal(u2, 2.0 * u1) and np.array_equal(w2, 2.0 * w1)   # scaling by 2 is exact in binary fp
     u, w = ops.induced_velocity(np.array([3.0]), np.array([1.5]), np.array([-2.5]), np.array([1.5]), np.array([-2.5]), VC)
     assert u[0] == 0.0 and w[0] == 0.0
+
+
+def _plan():
+    from ludvm_b200 import _lib
+    return _lib.default_context().last_plan()
+
+
+@pytest.mark.parametrize("npnt,nw", [(80, 700), (300, 4100), (4500, 1500), (8200, 5000)])
+def test_exact_range_proof_and_its_fallback(ops, oracle, npnt, nw, monkeypatch):
+    """The exact kernels drop the per-pair range words when a scan of the coordinate arrays proves them redundant
+    (common.cuh: coord_in_safe_window).  Operands the proof does not cover must still reach the flagged
+    instantiation and, through it, the library's __ddiv_rn / __dsqrt_rn: results stay bit-equal to the oracle for
+      * ordinary clouds (flag-free), with many exactly coincident coordinates (zero numerators) and signed zeros;
+      * coordinates of 1e-300, subnormals, 1e+200 (out of the window: flagged instantiation, library fallback);
+      * viscous=False (vc^4 = 0: no proof attempted), coincident points included (0/0 = nan like numpy)."""
+    rng = np.random.default_rng(npnt + nw)
+    g, xw, zw = cloud(rng, nw)
+    xp, zp = rng.uniform(-20, 0, npnt), rng.uniform(-4, 4, npnt)
+    # coincidences and signed zeros
+    xp[::3], zp[::5] = xw[(np.arange(0, npnt, 3) * 7) % nw], zw[(np.arange(0, npnt, 5) * 11) % nw]
+    xp[1], zp[1], xw[2], zw[2], xw[3], zw[4] = 0.0, -0.0, -0.0, 0.0, 0.0, -0.0
+    kinds = ("exact_rows", "exact_tiled")
+    u, w = ops.induced_velocity(g, xw, zw, xp, zp, VC, mode="exact")
+    p = _plan()
+    assert p["kernel"] in kinds and p["variant"] == 1 and p["range_bad"] == 0, p
+    uo, wo = oracle.induced_velocity(g, xw, zw, xp, zp, VC)
+    assert biteq(u, uo) and biteq(w, wo)
+    monkeypatch.setenv("LUDVM_EXACT_FLAGS", "1")          # the flagged instantiation on the same operands
+    u, w = ops.induced_velocity(g, xw, zw, xp, zp, VC, mode="exact")
+    assert _plan()["variant"] == 0 and biteq(u, uo) and biteq(w, wo)
+    monkeypatch.delenv("LUDVM_EXACT_FLAGS")
+    # out-of-window operands, one family at a time and together
+    for fam in range(4):
+        xw2, zw2, xp2, zp2 = xw.copy(), zw.copy(), xp.copy(), zp.copy()
+        if fam in (0, 3):
+            xw2[5::97], zp2[7::89] = 1e-300, -3e-301
+        if fam in (1, 3):
+            xw2[11::101], zw2[13::103], xp2[17::107] = 5e-324, -2.5e-310, 1e-320
+        if fam in (2, 3):
+            xw2[19::109], zp2[23::113] = 1e200, -4e199
+        u, w = ops.induced_velocity(g, xw2, zw2, xp2, zp2, VC, mode="exact")
+        p = _plan()
+        assert p["variant"] == 1 and p["range_bad"] == 1, (fam, p)
+        with np.errstate(all="ignore"):
+            uo2, wo2 = oracle.induced_velocity(g, xw2, zw2, xp2, zp2, VC)
+        assert biteq(u, uo2) and biteq(w, wo2), fam
+    with np.errstate(all="ignore"):
+        uo3, wo3 = oracle.induced_velocity(g, xw, zw, xp, zp, VC, viscous=False)
+    u, w = ops.induced_velocity(g, xw, zw, xp, zp, VC, viscous=False, mode="exact")
+    assert _plan()["variant"] == 0
+    assert np.isnan(uo3).any() or npnt < 3
+    assert np.array_equal(np.isnan(u), np.isnan(uo3)) and np.array_equal(np.isnan(w), np.isnan(wo3))
+    ok = ~np.isnan(uo3) & ~np.isnan(wo3)
+    assert biteq(u[ok], uo3[ok]) and biteq(w[ok], wo3[ok])
