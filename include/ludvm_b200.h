@@ -192,7 +192,10 @@ enum {
     LUDVM_F_CUR_LEV = 20,  /* current LEV positions [2,nt-1] */
     LUDVM_F_CUR_FREE = 21, /* current FREE positions [2,nfree] */
     LUDVM_F_COUNTERS = 22, /* int64[4]: steps done, itev, ilev (next free slots), error flags */
-    LUDVM_F__COUNT = 23
+    LUDVM_F_RANGE_BAD = 23, /* int32[1], exact mode: 0 = every coordinate seen so far lay inside the window in which the
+                               pair arithmetic needs no per-pair range words (the flag-free instantiation ran), 1 = the
+                               flagged instantiation took over (sticky) */
+    LUDVM_F__COUNT = 24
 };
 /* Copy a result field to a host buffer of `bytes` bytes (must equal the field's size).  Synchronises. */
 int ludvm_sim_fetch(ludvm_sim *sim, int field, void *dst, size_t bytes);

@@ -43,7 +43,7 @@ class SimTables(C.Structure):
 
 FIELDS = dict(PATH_TEV=0, PATH_LEV=1, PATH_FREE=2, G_TEV=3, G_LEV=4, G_BOUND=5, G_AIRFOIL=6, GAMMA_AIRFOIL=7,
               GAMMA_INT_AIRFOIL=8, FOURIER=9, LESP=10, LESP_PREV=11, LEV_SHED=12, FN=13, FS=14, L=15, D=16, T=17,
-              M=18, CUR_TEV=19, CUR_LEV=20, CUR_FREE=21, COUNTERS=22)
+              M=18, CUR_TEV=19, CUR_LEV=20, CUR_FREE=21, COUNTERS=22, RANGE_BAD=23)
 
 # name -> (restype, argtypes); every symbol include/ludvm_b200.h declares
 SIGNATURES = {

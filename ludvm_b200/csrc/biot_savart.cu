@@ -302,15 +302,20 @@ static int try_launch_fused(ludvm_ctx *ctx, int mode, const SrcView &S, const Tg
     while (R >= 1 && (long)ceil_div(nrows, 32 * R) * (chunks / 8) < want) R >>= 1;
     if (R < 1) return LUDVM_OK;
     const char *ue = getenv("LUDVM_FUSED_UNROLL");
-    const int U = ue ? atoi(ue) : 2;
+    const int U = ue ? atoi(ue) : 4;
     int rc;
 #define FUSED_CASE(RR, UU)                                                                                          \
     rc = W == 16 ? launch_fused_inst<RR, UU, 16, 1>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)               \
        : CL == 2 ? launch_fused_inst<RR, UU, 8, 2>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)                \
                  : launch_fused_inst<RR, UU, 8, 1>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)
     if (R == 4 && U == 1) FUSED_CASE(4, 1);
-    else if (R == 4 && U == 4) FUSED_CASE(4, 4);
-    else if (R == 4) FUSED_CASE(4, 2);
+    else if (R == 4 && U == 2) FUSED_CASE(4, 2);
+#ifdef FW_EXPERIMENT
+    else if (R == 4 && U == 3) FUSED_CASE(4, 3);
+    else if (R == 4 && U == 6) FUSED_CASE(4, 6);
+    else if (R == 4 && U == 8) FUSED_CASE(4, 8);
+#endif
+    else if (R == 4) FUSED_CASE(4, 4);
     else if (R == 2) FUSED_CASE(2, 4);
     else FUSED_CASE(1, 8);
 #undef FUSED_CASE

@@ -721,7 +721,9 @@ __device__ __forceinline__ void fast_fused_block(const SrcView &S, const Tgt &T,
 {
     constexpr int FW_WARPS = WARPS;
     constexpr int ROWS = 32 * R;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the stage addresses and the loop
+    // counter on the uniform datapath (ULEA / UIADD3 + LDS [UR + imm]) instead of vector integer instructions
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const unsigned crank = CL > 1 ? blockIdx.y : 0;
     const int base = blockIdx.x * ROWS + lane;
     double tx[R], tz[R], au[R], aw[R];
@@ -731,7 +733,8 @@ __device__ __forceinline__ void fast_fused_block(const SrcView &S, const Tgt &T,
         au[r] = 0.0;
         aw[r] = 0.0;
     }
-    const double vc4 = S.vc4s;
+    double vc4;   // opaque copy: otherwise ptxas re-reads the kernel parameter (LDCU.64) in every trip of the source loop
+    asm volatile("mov.f64 %0, %1;" : "=d"(vc4) : "d"(S.vc4s));
     const int c = (int)crank * FW_WARPS + warp;                      // this warp's source chunk
     const int c0 = min(S.n, c * chunk_len), c1 = c < nchunks ? min(S.n, c0 + chunk_len) : c0;
     const int nsub = (c1 - c0 + FW_SUB - 1) / FW_SUB;

@@ -64,6 +64,7 @@ struct SimDev {
     int target_warps;   // parallelism target used to pick split depths (same value in every phase of a case)
     int sum_nodes;      // doubles of shared-memory staging (block_np_sum tree nodes, block_fold / block_trapz batches)
     int sinn_smem;      // 1: the sin(n theta) table [Nc,P] is copied to shared memory at the head of the solve phase
+    int range_bad_init; // host verdict on the tables and vc^4 (1: outside the range-proof window, or LUDVM_EXACT_FLAGS set)
     int af_stride;      // row stride of the [nv,P] bound-vortex arrays (P, or 0 in compact sweep mode)
     int fourier_rows;   // nt, or 2 in compact sweep mode (row i lives at i % fourier_rows)
     double dt, Uinf, chord, rho, piv, vc4, ic, sum_free, maxerror, epsilon, lespcrit0, a0_init, a1_init;
@@ -87,7 +88,19 @@ struct SimDev {
     double *foil_u, *foil_w;  // bound vortices on the wake [Nw2]
     double *gp_u, *gp_w;      // overlapped step: wake velocity at the gamma points [P]
     double *pre_sums;         // graph path: np.sum(Gamma_TEV[:itev]), np.sum(Gamma_LEV[:ilev]) of the current step
+    // exact mode: sticky verdict of the range proof behind the flag-free pair arithmetic (common.cuh,
+    // coord_in_safe_window).  0 = every coordinate the all-pairs kernels have seen so far -- host tables, free vortices,
+    // every vortex placed or moved by a step -- lies in the window, so the per-pair range words are skipped; set to 1
+    // (by the host for the tables / vc^4, by k_case_init, the solve and the Euler update on the device) it sends every
+    // later evaluation through the flagged instantiation.
+    int *range_bad;
 };
+
+__device__ __forceinline__ bool range_safe(const SimDev &S) { return *(volatile const int *)S.range_bad == 0; }
+__device__ __forceinline__ void range_note(const SimDev &S, double x, double z)
+{
+    if (!(coord_in_safe_window(x) && coord_in_safe_window(z))) *(volatile int *)S.range_bad = 1;
+}
 
 __host__ __device__ __forceinline__ int ilog2_ceil_i(int v)
 {
@@ -254,8 +267,12 @@ __device__ __forceinline__ void phase_wake_on_foil(const SimDev &S, const Step &
     long nquads = (S.P + 3) >> 2;
     const int fold = wof_fold(S.mode, W.n, S.P, S.target_warps);
     if (S.mode == LUDVM_EXACT_F64) {
-        for (long t = pl.wid; t < (nquads << fold); t += pl.nwarps)
-            exact_rows_warp_task(W, T, S.P, fold, t, pl.lane, S.pa_u, S.pa_w);
+        if (range_safe(S))
+            for (long t = pl.wid; t < (nquads << fold); t += pl.nwarps)
+                exact_rows_warp_task<1, false>(W, T, S.P, fold, t, pl.lane, S.pa_u, S.pa_w);
+        else
+            for (long t = pl.wid; t < (nquads << fold); t += pl.nwarps)
+                exact_rows_warp_task<1, true>(W, T, S.P, fold, t, pl.lane, S.pa_u, S.pa_w);
     } else {
         for (long t = pl.wid; t < nquads * fold; t += pl.nwarps)
             fast_rows_warp_task(W, T, S.P, fold, t, pl.lane, S.pa_u, S.pa_w);
@@ -472,6 +489,7 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *tab, double
         sc[1] = zt;
         S.wx[itev] = xt;
         S.wz[itev] = zt;
+        range_note(S, xt, zt);
         sc[15] = lc0;
         sc[11] = 0.0;
         if (ramesh && ilev < nv) {  // row i of path['LEV'] starts with a zero slot
@@ -603,6 +621,7 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *tab, double
                 S.lev_shed[i] = (double)ilev;
                 S.wx[nv + ilev] = xl;
                 S.wz[nv + ilev] = zl;
+                range_note(S, xl, zl);
                 // Ramesh 2-D Newton on (LEV, TEV) strengths (LUDVM.py:807-909)
                 sc[26] = 0.1;          // f1
                 sc[27] = 0.1;          // f2
@@ -658,6 +677,7 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *tab, double
             S.wg[nv + ilev] = sc[11];
             S.wx[nv + ilev] = sc[13];
             S.wz[nv + ilev] = sc[14];
+            range_note(S, sc[13], sc[14]);
         } else if (ilev < nv) {  // untouched slot of row i: zero circulation at the origin
             S.wx[nv + ilev] = 0.0;
             S.wz[nv + ilev] = 0.0;
@@ -712,9 +732,16 @@ __device__ __forceinline__ void phase_conv_partials(const SimDev &S, const Step 
     if (S.mode == LUDVM_EXACT_F64) {
         int d = sim_depth(W.n, nrows, S.target_warps);
         long nA = nquadsA << d;
-        for (long t = pl.wid; t < nA + nquadsW; t += pl.nwarps) {
-            if (t < nA) exact_rows_warp_task(W, TA, nrows, d, t, pl.lane, S.pb_u, S.pb_w);
-            else exact_rows_warp_task(Fo, TW, W.n, 0, t - nA, pl.lane, S.foil_u, S.foil_w);
+        if (range_safe(S)) {
+            for (long t = pl.wid; t < nA + nquadsW; t += pl.nwarps) {
+                if (t < nA) exact_rows_warp_task<1, false>(W, TA, nrows, d, t, pl.lane, S.pb_u, S.pb_w);
+                else exact_rows_warp_task<1, false>(Fo, TW, W.n, 0, t - nA, pl.lane, S.foil_u, S.foil_w);
+            }
+        } else {
+            for (long t = pl.wid; t < nA + nquadsW; t += pl.nwarps) {
+                if (t < nA) exact_rows_warp_task<1, true>(W, TA, nrows, d, t, pl.lane, S.pb_u, S.pb_w);
+                else exact_rows_warp_task<1, true>(Fo, TW, W.n, 0, t - nA, pl.lane, S.foil_u, S.foil_w);
+            }
         }
     } else {
         int c = sim_chunks(W.n, nrows, S.target_warps);
@@ -829,6 +856,7 @@ __device__ __forceinline__ void phase_finish_update(const SimDev &S, const Step 
         double zn = S.wz[p] + dt * (ww + wf);
         S.wx[p] = xn;
         S.wz[p] = zn;
+        if (exact) range_note(S, xn, zn);
         if (S.store_history) {   // snapshot row i / k of the strided TEV / LEV history; the FREE history is kept in full
             double *hx, *hz;
             const bool snap = (i % S.store_history) == 0;
@@ -910,13 +938,18 @@ __global__ void __launch_bounds__(ET_THREADS, 3) k_conv_partials_exact_tiled(Sim
         const int d = sim_depth(W.n, nrows, S.target_warps);
         if ((long)blockIdx.x * ET_THREADS >= nrows) return;
         TgtGammaWake TA{gx, gz, P, W};
-        for (int b = blockIdx.y; b < (1 << d); b += gridDim.y - 1)   // normally one node per CTA
-            exact_tiled_block(W, TA, nrows, blockIdx.x, d, b, S.pb_u, S.pb_w, sxz, sgv);
+        if (range_safe(S))
+            for (int b = blockIdx.y; b < (1 << d); b += gridDim.y - 1)   // normally one node per CTA
+                exact_tiled_block<false>(W, TA, nrows, blockIdx.x, d, b, S.pb_u, S.pb_w, sxz, sgv);
+        else
+            for (int b = blockIdx.y; b < (1 << d); b += gridDim.y - 1)
+                exact_tiled_block<true>(W, TA, nrows, blockIdx.x, d, b, S.pb_u, S.pb_w, sxz, sgv);
     } else {
         if ((long)blockIdx.x * ET_THREADS >= W.n) return;
         SrcView Fo = make_src(S.g_airfoil + (size_t)st.itev * S.af_stride, 1, gx, gz, nullptr, S.vc4, P);
         TgtWake TW{W};
-        exact_tiled_block(Fo, TW, W.n, blockIdx.x, 0, 0, S.foil_u, S.foil_w, sxz, sgv);
+        if (range_safe(S)) exact_tiled_block<false>(Fo, TW, W.n, blockIdx.x, 0, 0, S.foil_u, S.foil_w, sxz, sgv);
+        else exact_tiled_block<true>(Fo, TW, W.n, blockIdx.x, 0, 0, S.foil_u, S.foil_w, sxz, sgv);
     }
 }
 
@@ -1337,16 +1370,19 @@ __device__ __noinline__ void cta_conv_tiled_exact(const SimDev &S, const Step &s
     }
     __syncthreads();
     const SmemSrc3 wake{txz + P, tg + P, S.vc4}, foil{txz, tg, S.vc4};
+    const bool safe = range_safe(S);
     for (int row = tid; row < nrows; row += nth) {
         const double2 t = txz[row];
         double u, w;
-        exact_tree_thread(wake, n, t.x, t.y, u, w);
+        if (safe) exact_tree_thread<false>(wake, n, t.x, t.y, u, w);
+        else exact_tree_thread<true>(wake, n, t.x, t.y, u, w);
         S.pb_u[row] = u; S.pb_w[row] = w;
     }
     for (int row = tid; row < n; row += nth) {
         const double2 t = txz[P + row];
         double u, w;
-        exact_tree_thread(foil, P, t.x, t.y, u, w);
+        if (safe) exact_tree_thread<false>(foil, P, t.x, t.y, u, w);
+        else exact_tree_thread<true>(foil, P, t.x, t.y, u, w);
         S.foil_u[row] = u; S.foil_w[row] = w;
     }
 }
@@ -1431,10 +1467,12 @@ __global__ void __launch_bounds__(256) k_case_init(const SimDev *cases, int ncas
     if (c >= ncases) return;
     const SimDev S = cases[c];
     for (int j = threadIdx.x; j < S.nt; j += blockDim.x) S.lev_shed[j] = -1.0;
+    if (threadIdx.x == 0 && S.range_bad_init) *S.range_bad = 1;
     for (int j = threadIdx.x; j < S.nfree; j += blockDim.x) {
         S.wg[2 * S.nv + j] = S.free_g[j];
         S.wx[2 * S.nv + j] = S.free_xz[j];
         S.wz[2 * S.nv + j] = S.free_xz[S.nfree + j];
+        range_note(S, S.free_xz[j], S.free_xz[S.nfree + j]);
         if (S.store_history) {
             S.path_free[j] = S.free_xz[j];
             S.path_free[S.nfree + j] = S.free_xz[S.nfree + j];
@@ -1479,7 +1517,19 @@ struct Arena {
 struct DevTables {  // device copies of one ludvm_sim_tables
     const double *cos_a, *sin_a, *alpha_dot, *h_dot, *gp, *le, *te;
     const double *detadx_p, *eta_p, *x_p, *theta_p, *dtheta, *cos_tp, *sin_tp, *cosn, *sinn, *free_g, *free_xz;
+    bool coords_in_window;   // every gamma-point / LE / TE coordinate passes coord_in_safe_window (host scan)
 };
+
+static bool host_coords_in_window(const double *a, size_t n)
+{
+    for (size_t i = 0; i < n; i++) {
+        uint64_t b;
+        memcpy(&b, &a[i], 8);
+        const unsigned h = (unsigned)(b >> 32) & 0x7fffffffu;
+        if (!((h >= LUDVM_SAFE_LO && h < LUDVM_SAFE_HI) || (h == 0u && (unsigned)b == 0u))) return false;
+    }
+    return true;
+}
 
 static int check_params(const ludvm_sim_params *p, const ludvm_sim_tables *t)
 {
@@ -1512,6 +1562,8 @@ static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t
     D.te = t.te; D.detadx_p = t.detadx_p; D.eta_p = t.eta_p; D.x_p = t.x_p; D.theta_p = t.theta_p;
     D.dtheta = t.dtheta; D.cos_tp = t.cos_tp; D.sin_tp = t.sin_tp; D.cosn = t.cosn; D.sinn = t.sinn;
     D.free_g = t.free_g; D.free_xz = t.free_xz;
+    D.range_bad_init = (t.coords_in_window && vc4_in_safe_window(p.vc4) && !getenv("LUDVM_EXACT_FLAGS")) ? 0 : 1;
+    D.range_bad = a.take<int>(1);
     D.wx = a.take<double>(nstate); D.wz = a.take<double>(nstate); D.wg = a.take<double>(nstate);
     D.g_bound = a.take<double>(nv);
     const size_t afrows = compact ? 1 : nv;
@@ -1612,6 +1664,8 @@ static int upload_tables(ludvm_ctx *ctx, std::vector<void *> &allocs, const ludv
         CUDA_TRY(cudaMemcpyAsync(d, it.h, it.n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         *it.d = d;
     }
+    out->coords_in_window = host_coords_in_window(t.gp, nt * 2 * P) && host_coords_in_window(t.le, nt * 2) &&
+                            host_coords_in_window(t.te, nt * 2);
     return LUDVM_OK;
 }
 
@@ -1823,6 +1877,8 @@ LUDVM_API int ludvm_sim_create(ludvm_ctx *ctx, const ludvm_sim_params *p, const 
         if (coop && !cta && cudaFuncSetAttribute(k_sim_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->solve_smem) == cudaSuccess &&
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_coop, 256, s->solve_smem) == cudaSuccess && per_sm >= 1)
             s->coop_grid = ctx->sm_count;
+        if (const char *ge = getenv("LUDVM_COOP_GRID"))   // experiments: a smaller persistent grid (>= 3 CTAs)
+            if (s->coop_grid) s->coop_grid = std::max(3, std::min(s->coop_grid, atoi(ge)));
         cudaGetLastError();
     }
     CU(cudaStreamSynchronize(ctx->stream));  // the host tables may be freed by the caller after return
@@ -1969,6 +2025,7 @@ static int field_info(ludvm_sim *s, int field, const void **ptr, size_t *bytes)
     case LUDVM_F_T: *ptr = D.T; *bytes = nt * d8; break;
     case LUDVM_F_M: *ptr = D.M; *bytes = nt * d8; break;
     case LUDVM_F_COUNTERS: *ptr = D.counters; *bytes = 4 * sizeof(long long); break;
+    case LUDVM_F_RANGE_BAD: *ptr = D.range_bad; *bytes = sizeof(int); break;
     case LUDVM_F_CUR_TEV: case LUDVM_F_CUR_LEV: case LUDVM_F_CUR_FREE:
         *ptr = nullptr; *bytes = 2 * (field == LUDVM_F_CUR_FREE ? nf : nv) * d8; break;
     default: return set_error(LUDVM_E_ARG, "unknown field %d", field);

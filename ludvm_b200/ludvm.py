@@ -335,6 +335,7 @@ class LUDVM:
         self.BC = np.zeros([nv, self.Npoints])
         cnt = self._fetch('COUNTERS', 4, np.int64)
         self.steps_done, self.itev, self.ilev = int(cnt[0]), int(cnt[1]), int(cnt[2])
+        self.range_proof_held = not bool(self._fetch('RANGE_BAD', 1, np.int32)[0])   # exact mode: flag-free arithmetic ran
         if cnt[3] != 0:
             raise _lib.LudvmError("device time loop reported error flags %d (grid barrier timed out)" % int(cnt[3]))
 

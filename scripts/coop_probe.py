@@ -4,9 +4,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ludvm_b200 import LUDVM, _lib
 L = _lib.load()
 README = dict(t0=0, tf=20, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012")
-for label, env in (("coop", None), ("graph", "1")):
-    if env: os.environ["LUDVM_NO_COOP"] = env
-    else: os.environ.pop("LUDVM_NO_COOP", None)
+GRIDS = [int(a) for a in sys.argv[1:]]   # optional: sizes of the persistent grid to try (LUDVM_COOP_GRID)
+for label, env in [("coop", None), ("graph", "1")] + [("coop%d" % g, g) for g in GRIDS]:
+    os.environ.pop("LUDVM_NO_COOP", None); os.environ.pop("LUDVM_COOP_GRID", None)
+    if env == "1": os.environ["LUDVM_NO_COOP"] = env
+    elif env: os.environ["LUDVM_COOP_GRID"] = str(env)
     for mode in ("exact", "fast"):
         best = 1e9
         for rep in range(4):

@@ -41,6 +41,9 @@ CONFIGS = [{"LUDVM_NO_FUSED": "1"}, {"LUDVM_FUSED_UNROLL": "2"}, {"LUDVM_FUSED_U
            {"LUDVM_FUSED_WARPS": "16", "LUDVM_FUSED_UNROLL": "2"}, {"LUDVM_FUSED_WARPS": "16", "LUDVM_FUSED_UNROLL": "4"},
            {"LUDVM_FAST_CHUNKS": "8", "LUDVM_NO_FUSED": "1"}, {"LUDVM_FAST_CHUNKS": "8", "LUDVM_FUSED_UNROLL": "2"},
            {"LUDVM_FAST_CHUNKS": "8", "LUDVM_FUSED_UNROLL": "4"}]
+if os.environ.get("PROBE_UNROLLS"):
+    CONFIGS = [dict(LUDVM_FUSED_UNROLL=u, **w) for u in os.environ["PROBE_UNROLLS"].split(",")
+               for w in ({}, {"LUDVM_FUSED_WARPS": "16"})]
 if os.environ.get("PROBE_FUSED_ONLY"):
     CONFIGS = [c for c in CONFIGS if "LUDVM_NO_FUSED" not in c]
 KEYS = ("LUDVM_NO_FUSED", "LUDVM_FUSED_UNROLL", "LUDVM_FUSED_WARPS", "LUDVM_FAST_CHUNKS")

@@ -53,6 +53,7 @@ def test_exact_mode_bit_equal_to_reference_golden(name):
         assert sha(s.path[k]) == str(g["path_" + k + "_sha256"]), k
     assert [s.itev, s.ilev] == list(g["itev_ilev"])
     assert s.steps_done == s.nt - 1
+    assert s.range_proof_held        # these runs were evaluated by the instantiation without per-pair range words
 
 
 def test_readme_tolerance_statement():
@@ -264,3 +265,26 @@ def test_propulsive_efficiency_formula():
             exp[ii] = np.mean(g["Ct"][idx]) / np.mean(cp)
     assert np.isnan(exp[0]) and np.isfinite(exp[1])
     assert np.array_equal(s.etap, exp, equal_nan=True) and biteq(s.tt, tt)
+
+
+@pytest.mark.parametrize("drv", ["coop", "graph", "cta"])
+def test_exact_time_loop_outside_the_range_proof(oracle, drv, monkeypatch):
+    """Exact mode skips the per-pair range words while every coordinate stays inside the proof's window
+    (SimDev::range_bad).  A free vortex at z = 1e-300 and one at a subnormal x break the proof from step 0: the run
+    must fall back to the flagged instantiation (-> library division / square root for tiny operands) and stay
+    bit-equal to the oracle, on the cooperative, the graph and the one-CTA (Ramesh) driver."""
+    from ludvm_b200 import LUDVM
+    if drv == "graph":
+        monkeypatch.setenv("LUDVM_NO_COOP", "1")
+    xy = np.array([[-1.0, -2.0, -1e-310, -3.0], [0.3, 1e-300, -0.2, -1e-300]])
+    gam = np.array([0.01, -0.02, 0.015, 0.005])
+    kw = dict(t0=0, tf=1.5, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012",
+              circulation_freevort=gam, xy_freevort=xy, method="Ramesh" if drv == "cta" else "Faure")
+    s, o = LUDVM(**kw, verbose=False), oracle.OracleLUDVM(**kw)
+    assert not s.range_proof_held
+    for k in ("L", "D", "M", "LESP", "LEV_shed", "fourier"):
+        assert biteq(getattr(s, k), getattr(o, k)), k
+    for k in ("TEV", "LEV", "FREE"):
+        assert biteq(s.path[k], o.path[k]), k
+    ok = LUDVM(**dict(kw, circulation_freevort=gam[:1], xy_freevort=xy[:, :1]), verbose=False)
+    assert ok.range_proof_held
