@@ -1037,6 +1037,146 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_conv_old_tiled(SimDev S, int 
     fast_tiled_block<R>(W, TW, nrows, blockIdx.x, c0, c1, S.pb_u + po, S.pb_w + po, sx, sz, sg, sv);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Old-wake convection as independent WARP TASKS with warp-private bulk-copy pipelines (the shape of the fused all-pairs
+// kernel, biot_savart.cuh): task = (group of 32*R target rows, source chunk); the warp keeps its R rows per lane in
+// registers and streams the chunk's sources through its own double-buffered stages (cp.async.bulk + mbarrier), so the
+// kernel has no block-wide barrier at all -- the thread-staged tiles of k_conv_old_tiled spent 16 % of their issue
+// slots waiting at __syncthreads (profiles/r01c_k_conv_old_tiled_stalls.txt).
+// Bulk copies need 16-byte aligned, contiguous sources, and the wake is three physical segments whose ends move every
+// step.  The traversal is therefore defined on ALIGNED PHYSICAL BLOCKS of WT_SB sources: every block that overlaps a
+// segment is copied whole (the state arrays live in one arena, so a block may reach past a segment's end into
+// neighbouring storage; those entries are loaded and never used) and the source loop runs over the block's valid
+// sub-range.  Chunk = a contiguous run of blocks; partial sums [chunk][row] as before (fast mode: no order guarantee).
+// ---------------------------------------------------------------------------------------------------
+#define WT_SB 128   // sources per block / stage
+#ifndef WT_ROUNDS
+#define WT_ROUNDS 4 // rounds of warp tasks over the resident warps (more rounds: finer tail, earlier free slots for the
+                    // solve branch; fewer: less per-task pipeline fill)
+#endif
+struct BlockMap {
+    int a[3], b[3], nb[3], total;
+    __host__ __device__ __forceinline__ explicit BlockMap(const SrcView &W)
+    {
+        a[0] = 0; b[0] = W.n0;
+        a[1] = W.o1; b[1] = W.o1 + (W.n01 - W.n0);
+        a[2] = W.o2; b[2] = W.o2 + (W.n - W.n01);
+        total = 0;
+        for (int k = 0; k < 3; k++) {
+            nb[k] = b[k] > a[k] ? (b[k] - 1) / WT_SB - a[k] / WT_SB + 1 : 0;
+            total += nb[k];
+        }
+    }
+    // q-th block of the traversal -> physical block index and the valid entries [lo, hi) inside it
+    __device__ __forceinline__ void get(int q, int &pblk, int &lo, int &hi) const
+    {
+        int k = 0;
+        if (q >= nb[0]) { q -= nb[0]; k = 1; if (q >= nb[1]) { q -= nb[1]; k = 2; } }
+        pblk = a[k] / WT_SB + q;
+        lo = max(a[k] - pblk * WT_SB, 0);
+        hi = min(b[k] - pblk * WT_SB, WT_SB);
+    }
+};
+// Task geometry from the ACTUAL wake: about WT_ROUNDS rounds of warp tasks over the resident warps, whole blocks per chunk.
+// Identical in the producer and in k_finish_ov.
+struct WtGeom {
+    int nrg, chunks, bpc;
+    __host__ __device__ __forceinline__ WtGeom(int nrows, int nblocks, int R, int task_budget)
+    {
+        nrg = (nrows + 32 * R - 1) / (32 * R);
+        int want = task_budget / nrg;   // task_budget = rounds x resident warps
+        want = want < 1 ? 1 : (want > SIM_TILED_CHUNKS_MAX ? SIM_TILED_CHUNKS_MAX : want);
+        want = want > nblocks ? nblocks : want;
+        want = want < 1 ? 1 : want;
+        bpc = (nblocks + want - 1) / want;
+        bpc = bpc < 1 ? 1 : bpc;
+        chunks = (nblocks + bpc - 1) / bpc;
+        chunks = chunks < 1 ? 1 : chunks;
+    }
+};
+struct WtStage { double x[WT_SB], z[WT_SB], g[WT_SB]; };
+struct WtSmem {
+    WtStage st[8][2];
+    uint64_t full[8][2];
+};
+
+template <int R>
+__global__ void __launch_bounds__(256, 2) k_conv_old_wt(SimDev S, int s, int task_budget)
+{
+    extern __shared__ __align__(128) unsigned char wt_raw[];
+    WtSmem &sm = *reinterpret_cast<WtSmem *>(wt_raw);
+    Step st;
+    if (!step_begin(S, s, st)) return;
+    SrcView W = wake_view(S, st.itev, st.ilev);
+    const int nrows = W.n + 3;   // + the new TEV, the LEV if shed, the idle LEV slot (TgtWakePlus)
+    const BlockMap B(W);
+    const WtGeom G(nrows, B.total, R, task_budget);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+    const long task = (long)blockIdx.x * 8 + warp;
+    if (task >= (long)G.nrg * G.chunks) return;
+    const int c = (int)(task / G.nrg), rg = (int)(task - (long)c * G.nrg);
+    TgtWakePlus TW;
+    TW.W = W;
+    place_tev(S, st.i, st.itev, TW.xt, TW.zt);
+    place_lev(S, st.i, st.ilev, TW.xl, TW.zl);
+    double tx[R], tz[R], au[R], aw[R];
+    const int base = rg * 32 * R + lane;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        TW.get(min(base + 32 * r, nrows - 1), tx[r], tz[r]);
+        au[r] = 0.0;
+        aw[r] = 0.0;
+    }
+    double vc4;
+    asm volatile("mov.f64 %0, %1;" : "=d"(vc4) : "d"(S.vc4));
+    const int q0 = c * G.bpc, q1 = min(B.total, q0 + G.bpc);
+    WtStage *stg = sm.st[warp];
+    uint64_t *full = sm.full[warp];
+    if (lane == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int k) {   // lane 0: three 1 KB bulk copies of physical block pblk into stage k & 1
+        if (lane == 0) {
+            int pblk, lo, hi;
+            B.get(q0 + k, pblk, lo, hi);
+            WtStage &b = stg[k & 1];
+            const size_t off = (size_t)pblk * WT_SB;
+            mbar_expect_tx(&full[k & 1], 3 * WT_SB * sizeof(double));
+            bulk_g2s(b.x, S.wx + off, WT_SB * sizeof(double), &full[k & 1]);
+            bulk_g2s(b.z, S.wz + off, WT_SB * sizeof(double), &full[k & 1]);
+            bulk_g2s(b.g, S.wg + off, WT_SB * sizeof(double), &full[k & 1]);
+        }
+    };
+    const int nblk = q1 - q0;
+    if (nblk > 0) issue(0);
+    for (int k = 0; k < nblk; k++) {
+        __syncwarp();                               // every lane is done with stage (k + 1) & 1
+        if (k + 1 < nblk) issue(k + 1);
+        int pblk, lo, hi;
+        B.get(q0 + k, pblk, lo, hi);
+        mbar_wait(&full[k & 1], (k >> 1) & 1);
+        const WtStage &b = stg[k & 1];
+#pragma unroll 2
+        for (int j = lo; j < hi; j++) {
+            const double x = b.x[j], z = b.z[j], g = b.g[j];
+#pragma unroll
+            for (int r = 0; r < R; r++) pair_fast(tx[r], tz[r], x, z, g, vc4, au[r], aw[r]);
+        }
+    }
+    const size_t po = (size_t)c * nrows;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int row = base + 32 * r;
+        if (row < nrows) {
+            S.pb_u[po + row] = au[r] * LUDVM_INV_TWO_PI;
+            S.pb_w[po + row] = aw[r] * LUDVM_INV_TWO_PI;
+        }
+    }
+}
+
 // Row of the updated wake TEV[:itev+1] ++ LEV[:ilev+1] ++ FREE -> row of k_conv_old_tiled's partials (nold = rows of
 // the old wake; the step's two additions map to the extra rows, see TgtWakePlus).
 __device__ __forceinline__ int old_row(int r, int itev, int ilev, int nold, bool shed)
@@ -1094,7 +1234,7 @@ __global__ void __launch_bounds__(256) k_conv_new(SimDev S, int s)
     }
 }
 
-__global__ void __launch_bounds__(256) k_finish_ov(SimDev S, int s, int R, int slots)
+__global__ void __launch_bounds__(256) k_finish_ov(SimDev S, int s, int R, int slots, int wt)
 {
     extern __shared__ double sm[];
     Step st;
@@ -1111,7 +1251,8 @@ __global__ void __launch_bounds__(256) k_finish_ov(SimDev S, int s, int R, int s
     const int i = st.i, nv = S.nv, nT = st.itev + 1, nL = st.ilev + 1;
     SrcView W = wake_view(S, nT, nL);
     const int nold = W.n - 2, npart = nold + 3;
-    const int chunks = TiledGeom(npart, nold, R, slots).chunks;
+    const int chunks = wt ? WtGeom(npart, BlockMap(wake_view(S, st.itev, st.ilev)).total, R, slots).chunks
+                          : TiledGeom(npart, nold, R, slots).chunks;
     const bool shed = S.lev_shed[i] != -1.0;
     const double dt = S.dt;
     for (long r = (long)(blockIdx.x - 2) * blockDim.x + threadIdx.x; r < W.n; r += (long)(gridDim.x - 2) * blockDim.x) {
@@ -1685,8 +1826,8 @@ static int bracket_of(long n)
 
 // Launch geometry of one step for every wake size up to 2^bracket.
 struct StepPlan {
-    int g1, g3, g4, g5, R, tchunks, slots;
-    bool tiled, ov, tiled_exact;
+    int g1, g3, g4, g5, R, tchunks, slots, g_wt;
+    bool tiled, ov, tiled_exact, wt;
     dim3 gto;
     dim3 gt;
     dim3 gte;
@@ -1734,6 +1875,16 @@ static StepPlan plan_step(const ludvm_sim *s, int bracket)
         pl.ov = D.P <= 256 && !getenv("LUDVM_NO_OVERLAP");
         pl.gto = dim3((unsigned)((nw + 3 + FT_THREADS * pl.R - 1) / (FT_THREADS * pl.R)), (unsigned)SIM_TILED_CHUNKS_MAX);
         pl.slots = sm * (pl.R == 1 ? 3 : 2);   // resident CTAs of k_conv_old_tiled<R>: 70 registers -> 3 per SM, 112-120 -> 2
+        // warp-task form of the old-wake convection (k_conv_old_wt): 2 CTAs x 8 warps resident per SM
+        pl.wt = pl.ov && !getenv("LUDVM_CONV_TILED");
+        if (pl.wt) {
+            const char *re = getenv("LUDVM_WT_R");
+            pl.R = re ? atoi(re) : (rows_up >= 8192 ? 4 : (rows_up >= 4096 ? 2 : 1));
+            const char *ro = getenv("LUDVM_WT_ROUNDS");
+            pl.slots = sm * 16 * (ro ? std::max(1, atoi(ro)) : WT_ROUNDS);   // the task budget: rounds x resident warps
+            const long nrg_max = (nw + 3 + 32 * pl.R - 1) / (32 * pl.R);
+            pl.g_wt = (int)((std::max<long>(pl.slots, nrg_max) + 7) / 8);
+        }
         pl.g5 = 1 + (int)std::max<long>(1, std::min<long>((nw + 255) / 256, (long)sm * 8));
     }
     return pl;
@@ -1753,7 +1904,11 @@ static void enqueue_step_kernel(const ludvm_sim *s, const StepPlan &pl, int whic
     case 2:
         if (pl.tiled_exact) k_conv_partials_exact_tiled<<<pl.gte, ET_THREADS, 0, cs>>>(D, k);
         else if (!pl.tiled) k_conv_partials<<<pl.g3, 256, 0, cs>>>(D, k);
-        else if (pl.ov) {
+        else if (pl.wt) {
+            if (pl.R == 4) k_conv_old_wt<4><<<pl.g_wt, 256, sizeof(WtSmem), cs>>>(D, k, pl.slots);
+            else if (pl.R == 2) k_conv_old_wt<2><<<pl.g_wt, 256, sizeof(WtSmem), cs>>>(D, k, pl.slots);
+            else k_conv_old_wt<1><<<pl.g_wt, 256, sizeof(WtSmem), cs>>>(D, k, pl.slots);
+        } else if (pl.ov) {
             if (pl.R == 4) k_conv_old_tiled<4><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.slots);
             else if (pl.R == 2) k_conv_old_tiled<2><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.slots);
             else k_conv_old_tiled<1><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.slots);
@@ -1763,7 +1918,7 @@ static void enqueue_step_kernel(const ludvm_sim *s, const StepPlan &pl, int whic
         break;
     case 4: k_conv_new<<<pl.g5, 256, 0, cs>>>(D, k); break;
     default:
-        if (pl.ov) k_finish_ov<<<pl.g4, 256, s->finish_smem, cs>>>(D, k, pl.R, pl.slots);
+        if (pl.ov) k_finish_ov<<<pl.g4, 256, s->finish_smem, cs>>>(D, k, pl.R, pl.slots, pl.wt ? 1 : 0);
         else k_finish<<<pl.g4, 256, s->finish_smem, cs>>>(D, k, pl.tchunks);
         break;
     }
@@ -1820,6 +1975,9 @@ static int set_smem_limits(size_t solve_smem, size_t finish_smem)
     }
     if (finish_smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(k_finish, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)finish_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_conv_old_wt<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WtSmem)));
+    CUDA_TRY(cudaFuncSetAttribute(k_conv_old_wt<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WtSmem)));
+    CUDA_TRY(cudaFuncSetAttribute(k_conv_old_wt<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WtSmem)));
     return LUDVM_OK;
 }
 
