@@ -132,7 +132,7 @@ int ludvm_flowfield_vorticity(ludvm_ctx *ctx, const double *x1, long nx, const d
  */
 typedef struct {
     int64_t nt;        /* len(self.t)                          LUDVM.py:254-255 */
-    int64_t P;         /* Npoints - 1 panels / gamma points    LUDVM.py:345     */
+    int64_t P;         /* Npoints - 1 panels / gamma points    LUDVM.py:345; at most 1024 (LUDVM_E_UNSUPPORTED above) */
     int64_t Nc;        /* Ncoeffs                              LUDVM.py:245     */
     int64_t nfree;     /* n_freevort >= 1                      LUDVM.py:268-277 */
     int32_t method;    /* LUDVM_METHOD_*                       LUDVM.py:252     */

@@ -51,6 +51,8 @@ namespace ludvm {
 #define SIM_EXACT_TILED_MIN_WAKE 8192   // exact mode, graph path: wakes at least this large use k_conv_partials_exact_tiled
 #define SIM_COOP_MAX_WAKE 8192    // wakes up to this size are stepped by the persistent cooperative kernel
 #define FINISH_STAGE 4096         // doubles of staging in the loads block of k_finish
+#define SOLVE_SMEM_LIMIT (200 * 1024)   // dynamic shared memory of the solve kernel (bytes)
+#define LUDVM_MAX_PANELS 1024     // Npoints - 1 <= this: 18 doubles per panel of the solve kernel's fixed shared memory
 
 #ifdef LUDVM_TRACE
 __device__ long long g_trace[64];
@@ -1674,7 +1676,10 @@ static bool host_coords_in_window(const double *a, size_t n)
 
 static int check_params(const ludvm_sim_params *p, const ludvm_sim_tables *t)
 {
-    ARG_CHECK(p->nt >= 2 && p->nt < (1 << 24) && p->P >= 2 && p->P <= 2048 && p->Nc >= 4 && p->Nc <= 512);
+    ARG_CHECK(p->nt >= 2 && p->nt < (1 << 24) && p->P >= 2 && p->Nc >= 4 && p->Nc <= 512);
+    if (p->P > LUDVM_MAX_PANELS)
+        return set_error(LUDVM_E_UNSUPPORTED, "Npoints - 1 = %ld panels; the solve kernel keeps 18 doubles per panel in "
+                         "shared memory and supports at most %d", (long)p->P, LUDVM_MAX_PANELS);
     ARG_CHECK(p->nfree >= 1 && p->nfree < (1 << 28));
     ARG_CHECK(p->mode == LUDVM_EXACT_F64 || p->mode == LUDVM_FAST_F64);
     ARG_CHECK(p->method == LUDVM_METHOD_FAURE || p->method == LUDVM_METHOD_RAMESH);
@@ -1736,6 +1741,18 @@ static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t
     D.foil_u = a.take<double>(nstate + 8); D.foil_w = a.take<double>(nstate + 8);
     D.pre_sums = a.take<double>(2);
     D.gp_u = a.take<double>(P); D.gp_w = a.take<double>(P);
+}
+
+// Shared-memory staging area of the block-wide folds / integrals (block_reduce.cuh batches whatever does not fit):
+// `want` doubles if the solve kernel's total stays inside SOLVE_SMEM_LIMIT, else what is left -- never less than one
+// np.trapz row (P) or one row of 64 + 1 partials.  The fixed part is 18 P + Nc + 32 doubles (+ the cos/sin(n theta)
+// tables when they are small enough to be resident), so P <= LUDVM_MAX_PANELS always fits.
+static int clamp_sum_nodes(long P, long Nc, long want)
+{
+    const bool big = Nc * P <= SINN_SMEM_MAX;
+    const long fixed = SOLVE_SMEM_DOUBLES(P, Nc, 0, big);
+    const long room = SOLVE_SMEM_LIMIT / (long)sizeof(double) - fixed;
+    return (int)std::max<long>(std::max<long>(P, 130), std::min(want, room));
 }
 
 static size_t solve_smem_bytes(const SimDev &D) { return (size_t)SOLVE_SMEM_DOUBLES(D.P, D.Nc, D.sum_nodes, D.sinn_smem) * sizeof(double); }
@@ -1876,7 +1893,10 @@ static StepPlan plan_step(const ludvm_sim *s, int bracket)
         pl.gto = dim3((unsigned)((nw + 3 + FT_THREADS * pl.R - 1) / (FT_THREADS * pl.R)), (unsigned)SIM_TILED_CHUNKS_MAX);
         pl.slots = sm * (pl.R == 1 ? 3 : 2);   // resident CTAs of k_conv_old_tiled<R>: 70 registers -> 3 per SM, 112-120 -> 2
         // warp-task form of the old-wake convection (k_conv_old_wt): 2 CTAs x 8 warps resident per SM
-        pl.wt = pl.ov && !getenv("LUDVM_CONV_TILED");
+        // (opt-in, LUDVM_CONV_WT=1: measured 5.40-5.58 s against 5.24 s for the thread-staged tiles on the 20 000-step
+        // dt = 2e-3 run -- whole-block chunks quantise the task count and a few long tasks free their slots late for
+        // the solve branch; profiles/r02f_hires.txt)
+        pl.wt = pl.ov && getenv("LUDVM_CONV_WT") != nullptr;
         if (pl.wt) {
             const char *re = getenv("LUDVM_WT_R");
             pl.R = re ? atoi(re) : (rows_up >= 8192 ? 4 : (rows_up >= 4096 ? 2 : 1));
@@ -1965,7 +1985,7 @@ static int build_graph(ludvm_sim *s, int bracket, int ksteps, cudaGraphExec_t *o
 
 static int set_smem_limits(size_t solve_smem, size_t finish_smem)
 {
-    if (solve_smem > 200 * 1024) return set_error(LUDVM_E_UNSUPPORTED, "Npoints too large for the solve kernel");
+    if (solve_smem > SOLVE_SMEM_LIMIT + 4096) return set_error(LUDVM_E_UNSUPPORTED, "Npoints too large for the solve kernel");
     if (solve_smem > 48 * 1024) {
         CUDA_TRY(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
         CUDA_TRY(cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
@@ -2005,7 +2025,7 @@ LUDVM_API int ludvm_sim_create(ludvm_ctx *ctx, const ludvm_sim_params *p, const 
     const int target = cta ? 2 * (RAMESH_THREADS / 32) : ctx->sm_count * (p->mode == LUDVM_EXACT_F64 ? (getenv("LUDVM_EXACT_TARGET") ? atoi(getenv("LUDVM_EXACT_TARGET")) : 384) : 48);
     // shared-memory staging area of the block-wide folds / integrals: all Nc Fourier integrands, or 64 partials of
     // every (row, component), in one batch
-    const int sum_nodes = (int)std::max<long>(cta ? 1024 : 4096, std::max<long>(p->Nc * p->P, cta ? 0 : 2 * p->P * 65));
+    const int sum_nodes = clamp_sum_nodes(p->P, p->Nc, std::max<long>(cta ? 1024 : 4096, std::max<long>(p->Nc * p->P, cta ? 0 : 2 * p->P * 65)));
     Arena measure;
     layout_case(s->d, *p, dt, measure, target, sum_nodes, false);
     void *base;
@@ -2265,7 +2285,7 @@ LUDVM_API int ludvm_sweep_run(ludvm_ctx *ctx, long ncases, const ludvm_sim_param
     std::map<const double *, DevTables> uploaded;
     std::vector<SimDev> host_cases((size_t)ncases);
     std::vector<DevTables> dts((size_t)ncases);
-    const int target = 2 * (CTA_THREADS / 32), sum_nodes = (int)std::max<long>(256, p0.Nc * p0.P);
+    const int target = 2 * (CTA_THREADS / 32), sum_nodes = clamp_sum_nodes(p0.P, p0.Nc, std::max<long>(256, p0.Nc * p0.P));
     Arena measure;
     for (long c = 0; c < ncases; c++) {
         auto it = uploaded.find(tables[c].gp);

@@ -271,6 +271,9 @@ class LUDVM:
             raise NotImplementedError("BCcheck=True raises ValueError in the reference (LUDVM.py:1150-1153 mixes "
                                       "length-Npoints and length-(Npoints-1) arrays); not provided")
         tb = tables if tables is not None else self.step_tables()
+        if tb['P'] > 1024:
+            raise ValueError("Npoints = %d: the device step supports at most 1025 chord stations (18 doubles of shared "
+                             "memory per panel in the solve kernel)" % (tb['P'] + 1))
         self._tables = tb
         nt, P, Nc, nf = tb['nt'], tb['P'], tb['Nc'], tb['nfree']
         nv = nt - 1

@@ -288,3 +288,27 @@ def test_exact_time_loop_outside_the_range_proof(oracle, drv, monkeypatch):
         assert biteq(s.path[k], o.path[k]), k
     ok = LUDVM(**dict(kw, circulation_freevort=gam[:1], xy_freevort=xy[:, :1]), verbose=False)
     assert ok.range_proof_held
+
+
+@pytest.mark.parametrize("npoints,ncoeffs,method", [(201, 30, "Faure"), (401, 30, "Faure"), (401, 40, "Ramesh"),
+                                                    (1025, 12, "Faure")])
+def test_many_chord_stations(oracle, npoints, ncoeffs, method):
+    """Npoints far above the README's 81: the solve kernel's shared-memory staging is capped and its folds / integrals
+    run in batches (round 1 rejected Npoints > 173).  Exact mode stays bit-equal to the oracle; the documented limit
+    (1025 stations) is enforced up front."""
+    from ludvm_b200 import LUDVM
+    kw = dict(t0=0, tf=0.6, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=npoints, Ncoeffs=ncoeffs, LESPcrit=0.05,
+              Naca="0012", alpha_max=30, k=3, method=method)
+    s, o = LUDVM(**kw, verbose=False), oracle.OracleLUDVM(**kw)
+    for k in HIST + ("Cl", "Cd", "Cm"):
+        assert biteq(getattr(s, k), getattr(o, k)), k
+    for k in ("TEV", "LEV"):
+        assert biteq(s.path[k], o.path[k]), k
+    for k in ("airfoil", "gamma_airfoil", "Gamma_airfoil"):
+        assert biteq(s.circulation[k], o.circulation[k]), k
+    assert o.ilev > 0
+    f = LUDVM(**kw, verbose=False, mode="fast")
+    assert np.max(np.abs(f.L - o.L)) <= 1e-9 * np.max(np.abs(o.L))
+    if npoints == 1025:
+        with pytest.raises(ValueError):
+            LUDVM(**dict(kw, Npoints=1027), verbose=False)
