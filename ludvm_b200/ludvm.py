@@ -267,9 +267,8 @@ class LUDVM:
 
     def time_loop(self, print_dt=50, BCcheck=False, tables=None, nsteps=None):
         """The time integrator (LUDVM.py:597-1171) on the device: CUDA-graph replay of the 4-kernel step."""
-        if BCcheck:
-            raise NotImplementedError("BCcheck=True raises ValueError in the reference (LUDVM.py:1150-1153 mixes "
-                                      "length-Npoints and length-(Npoints-1) arrays); not provided")
+        if BCcheck and not (self.store_history == 1 and nsteps is None):
+            raise ValueError("BCcheck=True is evaluated from the full vortex-path history (store_history=True, whole run)")
         tb = tables if tables is not None else self.step_tables()
         if tb['P'] > 1024:
             raise ValueError("Npoints = %d: the device step supports at most 1025 chord stations (18 doubles of shared "
@@ -308,7 +307,63 @@ class LUDVM:
                 self.ctx.synchronize()
                 print('Step {} out of {}. Elapsed time {}'.format(done, nv, timeit.default_timer() - self.start_time))
         self._fetch_results(nt, P, Nc, nf, nv)
+        if BCcheck:
+            self.BC = self._bc_check()
         return None
+
+    def _wake_before_convection(self, i, ilev):
+        """(circulation, xw, zw) of the wake TEV[:itev+1] ++ LEV[:ilev+1] ++ FREE as it stood at step i BEFORE that step's
+        convection (LUDVM.py:1095-1100): row i-1 of the stored paths plus the vortices placed in step i
+        (LUDVM.py:672-681, :784-800).  Needs the full history."""
+        itev = i - 1
+        pa = self.path['airfoil']
+        TEV, LEV, FREE = self.path['TEV'], self.path['LEV'], self.path['FREE']
+        xT, zT = TEV[i - 1, 0, :itev + 1].copy(), TEV[i - 1, 1, :itev + 1].copy()
+        if itev == 0:
+            xT[0], zT[0] = pa[0, :, -1] + [0.5 * self.Uinf * self.dt, 0]
+        else:
+            xT[itev], zT[itev] = pa[i, :, -1] + 1 / 3 * (TEV[i - 1, :, itev - 1] - pa[i, :, -1])
+        xL, zL = LEV[i - 1, 0, :ilev + 1].copy(), LEV[i - 1, 1, :ilev + 1].copy()
+        cL = self.circulation['LEV'][:ilev + 1].copy()
+        if self.LEV_shed[i] != -1:
+            if ilev > 0 and self.LEV_shed[i - 1] != -1:
+                xL[ilev], zL[ilev] = pa[i, :, 0] + 1 / 3 * (LEV[i - 1, :, ilev - 1] - pa[i, :, 0])
+            else:
+                xL[ilev], zL[ilev] = pa[i, :, 0]
+        else:           # idle slot of row i: zero circulation at the origin (SURVEY.md B.3)
+            xL[ilev], zL[ilev], cL[ilev] = 0.0, 0.0, 0.0
+        ap = np.append
+        return (ap(ap(self.circulation['TEV'][:itev + 1], cL), self.circulation['FREE']),
+                ap(ap(xT, xL), FREE[i - 1, 0, :]), ap(ap(zT, zL), FREE[i - 1, 1, :]))
+
+    def _bc_check(self):
+        """Boundary-condition residual of LUDVM.py:1144-1161 (BCcheck=True), evaluated after the run from the stored
+        history.  The reference raises there (it mixes `airfoil['x']`, length Npoints, with length-(Npoints-1) arrays
+        at LUDVM.py:1153 and assigns Npoints-1 values to a row of Npoints at :1161); with `airfoil['x_panel']` in the
+        first place, BC[itev, :Npoints-1] = BCnx + BCnz is the no-penetration residual, zero up to rounding; the last
+        column keeps the reference's allocation (LUDVM.py:625) and stays zero."""
+        nt, P = self.nt, self.Npoints - 1
+        BC = np.zeros([nt - 1, self.Npoints])
+        af, gpts = self.airfoil, self.path['airfoil_gamma_points']
+        ilev = 0
+        for i in range(1, nt):
+            g, xw, zw = self._wake_before_convection(i, ilev)
+            alpha, alpha_dot, h_dot = self.alpha[i], self.alpha_dot[i], self.h_dot[i]
+            u1, w1 = self.induced_velocity(g, xw, zw, gpts[i, 0, :], gpts[i, 1, :])
+            u = u1 * np.cos(alpha) - w1 * np.sin(alpha)
+            w = u1 * np.sin(alpha) + w1 * np.cos(alpha)
+            W = af['detadx_panel'] * (self.Uinf * np.cos(alpha) + h_dot * np.sin(alpha) + u
+                                      - alpha_dot * af['eta_panel']) \
+                - self.Uinf * np.sin(alpha) - alpha_dot * (af['x_panel'] - self.piv) \
+                + h_dot * np.cos(alpha) - w
+            BCnx = af['detadx_panel'] * (- u - self.Uinf * np.cos(alpha)
+                                         - h_dot * np.sin(alpha) + alpha_dot * af['eta_panel'])
+            BCnz = W + w + self.Uinf * np.sin(alpha) - h_dot * np.cos(alpha) \
+                + alpha_dot * (af['x_panel'] - self.piv)
+            BC[i - 1, :P] = BCnx + BCnz
+            if self.LEV_shed[i] != -1:
+                ilev += 1
+        return BC
 
     def _fetch(self, field, shape, dtype=np.float64):
         a = np.empty(shape, dtype=dtype)
@@ -355,14 +410,20 @@ class LUDVM:
     def flowfield(self, xmin=-10, xmax=0, zmin=-4, zmax=4, dr=0.02, tsteps=[0, 1, 2], rows=None):
         """Velocity and vorticity on a uniform grid for the chosen steps (LUDVM.py:1186-1298), GPU kernels.
 
-        `rows=(row0, nrows)` restricts the evaluation to a slab of x-rows (multi-GPU sharding); the vorticity
-        stencil needs one halo row per side, which callers sharding the grid must include."""
+        `rows=(row0, nrows)` restricts the evaluation to a slab of x-rows (multi-GPU sharding, see
+        `sharded.grid_slab`): `x_ff, z_ff, u_ff, w_ff, ome_ff` then hold only those rows.  The vorticity stencil of a
+        slab's first / last row is one-sided (LUDVM.py:1222-1292 applied to the slab), so a caller that shards a grid
+        includes one halo row per interior side and drops it afterwards."""
         if not self.store_history:
             raise RuntimeError("flowfield needs the vortex path history (store_history=True)")
         x1, z1 = np.arange(xmin, xmax, dr), np.arange(zmin, zmax, dr)
-        x, z = np.meshgrid(x1, z1, indexing='ij')
+        row0, nrows = (0, len(x1)) if rows is None else (int(rows[0]), int(rows[1]))
+        if row0 < 0 or nrows < 2 or row0 + nrows > len(x1):
+            raise ValueError("rows=(row0, nrows) must select at least two rows of the %d-row grid" % len(x1))
+        xs = x1[row0:row0 + nrows]
+        x, z = np.meshgrid(xs, z1, indexing='ij')
         ns = len(tsteps)
-        u, w = np.zeros([ns, len(x1), len(z1)]), np.zeros([ns, len(x1), len(z1)])
+        u, w = np.zeros([ns, nrows, len(z1)]), np.zeros([ns, nrows, len(z1)])
         vc4 = float(self.v_core ** 4)
         ap = np.append
         for ii, itev in enumerate(tsteps):
@@ -371,7 +432,7 @@ class LUDVM:
             if itev == 0:     # only the free vortices exist (LUDVM.py:1202-1207)
                 u[ii], w[ii] = ops.flowfield_velocity(self.circulation['FREE'], self.path['FREE'][0, 0],
                                                       self.path['FREE'][0, 1], None, None, None, vc4, x1, z1,
-                                                      mode=self.mode, ctx=self.ctx)
+                                                      row0=row0, nrows=nrows, mode=self.mode, ctx=self.ctx)
             else:             # index conventions of LUDVM.py:1209-1217 kept
                 if (itev - 1) % self.store_history:
                     raise ValueError("flowfield step %d needs path row %d, which the strided history (every %d steps) "
@@ -386,10 +447,10 @@ class LUDVM:
                         self.path['FREE'][itev, 1])
                 gp = self.path['airfoil_gamma_points'][itev - 1]
                 u[ii], w[ii] = ops.flowfield_velocity(g, xw, zw, self.circulation['airfoil'][itev - 1], gp[0], gp[1],
-                                                      vc4, x1, z1, mode=self.mode, ctx=self.ctx)
+                                                      vc4, x1, z1, row0=row0, nrows=nrows, mode=self.mode, ctx=self.ctx)
         self.x_ff, self.z_ff = x, z
         self.u_ff, self.w_ff = u, w
-        self.ome_ff = ops.flowfield_vorticity(x1, z1, u, w, ctx=self.ctx)
+        self.ome_ff = ops.flowfield_vorticity(xs, z1, u, w, ctx=self.ctx)
         return None
 
     def animation(self, step=1, ani_interval=10):

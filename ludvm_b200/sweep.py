@@ -2,6 +2,8 @@
 CTA per case (C ABI `ludvm_sweep_run`), no collective.  Cases are constructor-kwarg dicts of `ludvm_b200.LUDVM`;
 cases that differ only in `LESPcrit` share one set of host tables (geometry + kinematics are computed once)."""
 import ctypes as C
+import hashlib
+import inspect
 
 import numpy as np
 
@@ -11,6 +13,17 @@ from .ludvm import LUDVM
 
 SW_FIELDS = ("Fn", "Fs", "L", "D", "T", "M", "LESP", "LESP_prev", "LEV_shed", "circulation_TEV", "circulation_LEV",
              "circulation_bound")
+
+
+_LESPCRIT_DEFAULT = inspect.signature(LUDVM.__init__).parameters["LESPcrit"].default
+
+
+def _key_of(v):
+    """Hashable identity of a constructor argument for table sharing: arrays by their bytes (repr() elides long ones)."""
+    if isinstance(v, (np.ndarray, list, tuple)):
+        a = np.asarray(v)
+        return ("array", a.shape, str(a.dtype), hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest())
+    return repr(v)
 
 
 def lespcrit_k_grid(lespcrits, ks, **base):
@@ -31,7 +44,7 @@ def run_sweep(cases, mode="exact", ctx=None, device=0, case_slice=None):
     # motion, copied per case (filling 4096 structs field by field cost more than the fast-mode kernel's launch).
     shared, params, tables, objs = {}, [], [], []
     for kw in sel:
-        key = tuple(sorted((k, repr(v)) for k, v in kw.items() if k != "LESPcrit"))
+        key = tuple(sorted((k, _key_of(v)) for k, v in kw.items() if k != "LESPcrit"))
         if key not in shared:
             s = LUDVM(**dict(kw, verbose=False, run=False))
             tb = s.step_tables()
@@ -48,7 +61,7 @@ def run_sweep(cases, mode="exact", ctx=None, device=0, case_slice=None):
             shared[key] = (s, arrs, p0, t0)
         s, arrs, p0, t0 = shared[key]
         p = SimParams.from_buffer_copy(p0)
-        p.lespcrit = float(kw.get("LESPcrit", s.LESPcrit))
+        p.lespcrit = float(kw.get("LESPcrit", _LESPCRIT_DEFAULT))
         params.append(p)
         tables.append(t0)
         objs.append(s)

@@ -303,6 +303,61 @@ class OracleLUDVM:
         self.Fn, self.Fs, self.L, self.D, self.T, self.M = (out[k] for k in ('Fn', 'Fs', 'L', 'D', 'T', 'M'))
         self.dp = np.zeros([nt, P])
         self.itev, self.ilev = itev.value, ilev.value
+        self.BC = self._bc_check() if BCcheck else np.zeros([nv, self.Npoints])
+
+    def _wake_before_convection(self, i, ilev):
+        """(circulation, xw, zw) of the wake TEV[:itev+1] ++ LEV[:ilev+1] ++ FREE as it stood at step i BEFORE that step's
+        convection (LUDVM.py:1095-1100): row i-1 of the stored paths plus the vortices placed in step i
+        (LUDVM.py:672-681, :784-800).  Needs the full history."""
+        itev = i - 1
+        pa = self.path['airfoil']
+        TEV, LEV, FREE = self.path['TEV'], self.path['LEV'], self.path['FREE']
+        xT, zT = TEV[i - 1, 0, :itev + 1].copy(), TEV[i - 1, 1, :itev + 1].copy()
+        if itev == 0:
+            xT[0], zT[0] = pa[0, :, -1] + [0.5 * self.Uinf * self.dt, 0]
+        else:
+            xT[itev], zT[itev] = pa[i, :, -1] + 1 / 3 * (TEV[i - 1, :, itev - 1] - pa[i, :, -1])
+        xL, zL = LEV[i - 1, 0, :ilev + 1].copy(), LEV[i - 1, 1, :ilev + 1].copy()
+        cL = self.circulation['LEV'][:ilev + 1].copy()
+        if self.LEV_shed[i] != -1:
+            if ilev > 0 and self.LEV_shed[i - 1] != -1:
+                xL[ilev], zL[ilev] = pa[i, :, 0] + 1 / 3 * (LEV[i - 1, :, ilev - 1] - pa[i, :, 0])
+            else:
+                xL[ilev], zL[ilev] = pa[i, :, 0]
+        else:           # idle slot of row i: zero circulation at the origin (SURVEY.md B.3)
+            xL[ilev], zL[ilev], cL[ilev] = 0.0, 0.0, 0.0
+        ap = np.append
+        return (ap(ap(self.circulation['TEV'][:itev + 1], cL), self.circulation['FREE']),
+                ap(ap(xT, xL), FREE[i - 1, 0, :]), ap(ap(zT, zL), FREE[i - 1, 1, :]))
+
+    def _bc_check(self):
+        """Boundary-condition residual of LUDVM.py:1144-1161 (BCcheck=True), evaluated after the run from the stored
+        history.  The reference raises there (it mixes `airfoil['x']`, length Npoints, with length-(Npoints-1) arrays
+        at LUDVM.py:1153 and assigns Npoints-1 values to a row of Npoints at :1161); with `airfoil['x_panel']` in the
+        first place, BC[itev, :Npoints-1] = BCnx + BCnz is the no-penetration residual, zero up to rounding; the last
+        column keeps the reference's allocation (LUDVM.py:625) and stays zero."""
+        nt, P = self.nt, self.Npoints - 1
+        BC = np.zeros([nt - 1, self.Npoints])
+        af, gpts = self.airfoil, self.path['airfoil_gamma_points']
+        ilev = 0
+        for i in range(1, nt):
+            g, xw, zw = self._wake_before_convection(i, ilev)
+            alpha, alpha_dot, h_dot = self.alpha[i], self.alpha_dot[i], self.h_dot[i]
+            u1, w1 = self.induced_velocity(g, xw, zw, gpts[i, 0, :], gpts[i, 1, :])
+            u = u1 * np.cos(alpha) - w1 * np.sin(alpha)
+            w = u1 * np.sin(alpha) + w1 * np.cos(alpha)
+            W = af['detadx_panel'] * (self.Uinf * np.cos(alpha) + h_dot * np.sin(alpha) + u
+                                      - alpha_dot * af['eta_panel']) \
+                - self.Uinf * np.sin(alpha) - alpha_dot * (af['x_panel'] - self.piv) \
+                + h_dot * np.cos(alpha) - w
+            BCnx = af['detadx_panel'] * (- u - self.Uinf * np.cos(alpha)
+                                         - h_dot * np.sin(alpha) + alpha_dot * af['eta_panel'])
+            BCnz = W + w + self.Uinf * np.sin(alpha) - h_dot * np.cos(alpha) \
+                + alpha_dot * (af['x_panel'] - self.piv)
+            BC[i - 1, :P] = BCnx + BCnz
+            if self.LEV_shed[i] != -1:
+                ilev += 1
+        return BC
 
     def compute_coefficients(self):                                        # LUDVM.py:1173-1184
         q = 0.5 * self.rho * self.Uinf ** 2

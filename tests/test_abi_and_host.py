@@ -136,3 +136,35 @@ def test_sweep_host_structs_per_case(monkeypatch):
     assert seen["ptr"][0] == seen["ptr"][2] == seen["ptr"][4] and seen["ptr"][0] != seen["ptr"][1]
     sl = sweep.run_sweep(cases, mode="exact", ctx=types.SimpleNamespace(handle=None), case_slice=slice(3, 5))
     assert seen["n"] == 2 and [p[5] for p in seen["p"]] == [0.25, 0.4] and seen["p"][0][3] == _lib.MODES["exact"]
+
+
+def test_sweep_table_sharing_keys_long_arrays_by_content(monkeypatch):
+    """Cases whose free-vortex arrays differ only in entries that numpy's repr() elides (> 1000 elements) must not share
+    one table set; a case that omits LESPcrit gets the constructor default (0.2), not the value of the case that
+    happened to create the shared entry."""
+    import ctypes as C
+    import types
+    from ludvm_b200 import sweep
+    seen = {}
+
+    class FakeLib:
+        def ludvm_sweep_run(self, ctx, n, P, T, out, stride):
+            seen["lc"] = [P[i].lespcrit for i in range(n)]
+            seen["g600"] = [T[i].free_g[600] for i in range(n)]
+            seen["ptr"] = [C.cast(T[i].free_g, C.c_void_p).value for i in range(n)]
+            return 0
+
+    monkeypatch.setattr(sweep, "load", lambda: FakeLib())
+    rng = np.random.default_rng(0)
+    nf = 1500
+    xy, g1 = np.stack([rng.uniform(-3, -1, nf), rng.uniform(-0.5, 0.5, nf)]), rng.standard_normal(nf) * 1e-3
+    g2 = g1.copy()
+    g2[600] += 1e-3                                           # inside the part repr() prints as '...'
+    assert repr(g1) == repr(g2)
+    base = dict(t0=0, tf=0.5, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, Naca="0012", xy_freevort=xy)
+    cases = [dict(base, circulation_freevort=g1, LESPcrit=0.35), dict(base, circulation_freevort=g2),
+             dict(base, circulation_freevort=g1.copy())]
+    sweep.run_sweep(cases, mode="fast", ctx=types.SimpleNamespace(handle=None))
+    assert seen["lc"] == [0.35, 0.2, 0.2]
+    assert seen["g600"] == [g1[600], g2[600], g1[600]]
+    assert seen["ptr"][0] == seen["ptr"][2] != seen["ptr"][1]

@@ -77,3 +77,26 @@ def test_flowfield_exact_large_grid_few_sources(oracle):
     X, Z = np.meshgrid(x1, z1, indexing="ij")
     uo, wo = oracle.induced_velocity(g, xw, zw, X.ravel(), Z.ravel(), 0.065)
     assert biteq(u.ravel(), uo) and biteq(w.ravel(), wo)
+
+
+def test_flowfield_method_row_slabs():
+    """`LUDVM.flowfield(rows=(row0, nrows))`: slabs with one halo row per interior side reassemble the whole-grid
+    fields bit for bit (velocity rows are independent; the stencil of an interior row only needs its neighbours)."""
+    from ludvm_b200.sharded import grid_slab
+    g = load_golden("freevort_tf3")
+    s = _sim(g)
+    kw = dict(g["ff_kw"])
+    s.flowfield(**kw)
+    full = {k: getattr(s, k).copy() for k in ("x_ff", "z_ff", "u_ff", "w_ff", "ome_ff")}
+    nx = full["x_ff"].shape[0]
+    parts = {k: [] for k in full}
+    for rank in range(3):
+        r0, r1, h0, h1 = grid_slab(nx, 3, rank)
+        s.flowfield(**kw, rows=(h0, h1 - h0))
+        assert s.u_ff.shape[1] == h1 - h0
+        for k in full:
+            a = getattr(s, k)
+            parts[k].append(a[r0 - h0:r1 - h0] if a.ndim == 2 else a[:, r0 - h0:r1 - h0])
+    for k in full:
+        assert biteq(np.concatenate(parts[k], axis=0 if full[k].ndim == 2 else 1), full[k]), k
+    assert biteq(full["u_ff"], g["u_ff"])

@@ -312,3 +312,17 @@ def test_many_chord_stations(oracle, npoints, ncoeffs, method):
     if npoints == 1025:
         with pytest.raises(ValueError):
             LUDVM(**dict(kw, Npoints=1027), verbose=False)
+
+
+def test_bccheck_vs_oracle(oracle):
+    """time_loop(BCcheck=True) (LUDVM.py:1144-1161 with its shape bug fixed): the residual, evaluated after the run with
+    the GPU induced_velocity, is bit-equal to the oracle's (whose wake reconstruction is verified step by step in
+    tests/test_oracle_golden.py) and vanishes to rounding."""
+    from ludvm_b200 import LUDVM
+    kw = dict(t0=0, tf=3, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012")
+    s, o = LUDVM(**kw, verbose=False, run=False), oracle.OracleLUDVM(**kw, run=False)
+    s.time_loop(BCcheck=True)
+    o.time_loop(BCcheck=True)
+    assert s.BC.shape == (s.nt - 1, s.Npoints) and biteq(s.BC, o.BC) and np.max(np.abs(s.BC)) < 1e-13
+    with pytest.raises(ValueError):
+        LUDVM(**kw, verbose=False, run=False, store_history=0).time_loop(BCcheck=True)

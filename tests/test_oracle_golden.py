@@ -108,3 +108,50 @@ def test_numpy_primitives(oracle):
     # only reports drift of the local BLAS.
     if nbad:
         pytest.skip("local BLAS dgesv differs from the pinned recipe on %d/2000 systems" % nbad)
+
+
+def test_bccheck_reconstruction_and_residual(oracle):
+    """BCcheck=True (LUDVM.py:1144-1161, shape bug fixed) is evaluated after the run from the stored history.  The
+    delicate part is rebuilding the wake as it stood before each step's convection; check it by redoing the
+    convection of every step from the rebuilt wake (LUDVM.py:1095-1127) and landing on the stored next row bit for
+    bit.  The residual itself must vanish to rounding.  (Parity of BC against the reference is unpinned: it raises.)"""
+    kw = dict(t0=0, tf=3, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012")
+    o = oracle.OracleLUDVM(**kw, run=False)
+    o.time_loop(BCcheck=True)
+    assert o.BC.shape == (o.nt - 1, o.Npoints) and o.ilev > 3
+    assert np.max(np.abs(o.BC)) < 1e-13 and np.any(o.BC != 0) and np.all(o.BC[:, -1] == 0)
+    ilev = 0
+    gp = o.path["airfoil_gamma_points"]
+    for i in range(1, o.nt):
+        itev = i - 1
+        g, xw, zw = o._wake_before_convection(i, ilev)
+        nT, nL = itev + 1, ilev + 1
+        cf = o.circulation["airfoil"][itev]
+        uw, ww = o.induced_velocity(g, xw, zw, xw, zw)
+        uf, wf = o.induced_velocity(cf, gp[i, 0], gp[i, 1], xw, zw)
+        xn, zn = xw + o.dt * (uw + uf), zw + o.dt * (ww + wf)
+        assert biteq(xn[:nT], o.path["TEV"][i, 0, :nT]) and biteq(zn[:nT], o.path["TEV"][i, 1, :nT]), i
+        assert biteq(xn[nT:nT + nL], o.path["LEV"][i, 0, :nL]) and biteq(zn[nT:nT + nL], o.path["LEV"][i, 1, :nL]), i
+        assert biteq(xn[nT + nL:], o.path["FREE"][i, 0]), i
+        if o.LEV_shed[i] != -1:
+            ilev += 1
+
+
+def test_naca4_mean_line_against_the_published_formula():
+    """The camber line the reference takes from the un-vendored `airfoils` package (LUDVM.py:328-335) is the NACA
+    4-digit mean line (Abbott & von Doenhoff, Theory of Wing Sections, eq. 6.4): y_c = m/p^2 (2 p x - x^2) ahead of the
+    maximum-camber station p, m/(1-p)^2 ((1 - 2 p) + 2 p x - x^2) behind it.  Pin `_naca4_camber` at tabulated stations
+    so that a typo cannot hide behind the symmetric sections every BASELINE config uses."""
+    from ludvm_b200.ludvm import _naca4_camber
+    x = np.array([0.0, 0.1, 0.2, 0.4, 0.7, 1.0])
+    assert np.allclose(_naca4_camber("2412", x), [0.0, 0.00875, 0.015, 0.02, 0.015, 0.0], rtol=0, atol=1e-15)
+    assert np.allclose(_naca4_camber("4415", x), [0.0, 0.0175, 0.03, 0.04, 0.03, 0.0], rtol=0, atol=1e-15)
+    assert np.allclose(_naca4_camber("6309", np.array([0.15, 0.3, 0.65, 1.0])),
+                       [0.06 / 0.09 * (0.09 - 0.0225), 0.06, 0.06 / 0.49 * (0.4 + 0.39 - 0.4225), 0.0], rtol=0, atol=1e-15)
+    assert not np.any(_naca4_camber("0012", np.linspace(0, 1, 33)))
+    for code, m, p in (("2412", 0.02, 0.4), ("6309", 0.06, 0.3), ("9521", 0.09, 0.5)):
+        xs = np.linspace(0, 1, 2001)
+        yc = _naca4_camber(code, xs)
+        assert abs(yc.max() - m) < 1e-12 and abs(xs[np.argmax(yc)] - p) < 1e-3       # maximum camber m at station p
+        h = 1e-7                                                                      # slope continuous (zero) at p
+        assert abs(_naca4_camber(code, np.array([p + h]))[0] - _naca4_camber(code, np.array([p - h]))[0]) < 1e-12
