@@ -46,8 +46,11 @@ FLOP_PER_PAIR = 20           # N-body convention (FMA = 2)
 EXACT_OPS_PER_PAIR = 31      # exact mode: 7 (r^4 + vc^4) + 8 (sqrt) + 1 (2 pi) + 5 (reciprocal) + 6 (two quotients) + 2 (x Gamma) + 2 (sums)
 NOMINAL_DFMA_PER_S = 148 * 64 * 1.965e9      # 148 SMs x 64 FP64 lanes x 1.965 GHz (clocks.max.sm)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused kernel at N = 2^20 on one GPU, from the
-# `ncu --set full` capture under profiles/ (see profiles/README.md); None until captured for the shipped launch.
-NCU_DRAM_BYTES_PER_LAUNCH = {"fast_fused": None, "fast_tiled_tma": None}
+# `ncu --set full` capture under profiles/ (see profiles/README.md).  Algorithmic: 32 B read + 16 B written per vortex =
+# 50.3 MB; the capture sees the 25 MB of sources read once and almost none of the 16.8 MB of results, which are still
+# dirty in the 126 MB L2 when the kernel ends.
+NCU_DRAM_BYTES_PER_LAUNCH = {"fast_fused": 25.52e6,       # profiles/r02g_k_fast_fused_raw.csv: 25.34 MB read + 0.18 MB written
+                             "fast_tiled_tma": None}      # (round-1 partial-sum path: 41.7 MB with 8 chunks, not re-captured with 16)
 README = dict(t0=0, tf=20, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012")
 README_PAIRS_PER_CASE = 8.262e7   # pair evaluations of one README run (SURVEY.md / BASELINE.md, cProfile of the reference)
 
@@ -372,6 +375,8 @@ def selfconv_leg(env, args):
     f32_steps = max(1, min(args.steps, 2))
     f32_ms, _ = timed_steps("fp32", f32_steps, 1)            # fp32-fast, reported separately
     f32_value = float(n) * n / (f32_ms / f32_steps * 1e-3)
+    f12_ms, _ = timed_steps("fast12", f32_steps, 1)          # opt-in 12-slot pair (4.3e-13 per pair), reported separately
+    f12_value = float(n) * n / (f12_ms / f32_steps * 1e-3)
     ex_ms, _ = timed_steps("exact", 1, 1)                    # exact mode, reported separately
     ex_value = float(n) * n / (ex_ms * 1e-3)
 
@@ -428,6 +433,10 @@ def selfconv_leg(env, args):
             "hbm_algorithmic_gbs": 48.0 * n / world / (ms_per_step * 1e-3) / 1e9, "mufu_per_s": per_gpu},
         "fp32_fast": {"value": f32_value, "unit": UNIT, "ffma_per_s_measured": ffma, "kernel": info["plan_fp32"],
                       "note": "fp32 pair arithmetic, fp64 accumulation across tiles; accuracy ~1e-5 relative"},
+        "fast12_f64": {"value": f12_value, "unit": UNIT, "fp64_slots_per_pair": 12, "kernel": info["plan_fast12"],
+                       "frac_of_dfma_rate": f12_value / world * 12 / dfma,
+                       "note": "opt-in mode LUDVM_FAST12_F64: one second-order refinement of the centred MUFU.RSQ64H seed, "
+                               "|error| <= 4.3e-13 per pair (inside the 1e-12 statement) instead of 2.7e-16; not the headline"},
         "exact_f64": {"value": ex_value, "unit": UNIT, "ms_per_step": ex_ms, "fp64_ops_per_pair": EXACT_OPS_PER_PAIR,
                       "frac_of_dfma_rate": ex_value / world * EXACT_OPS_PER_PAIR / dfma,
                       "frac_of_nominal": ex_value / world * EXACT_OPS_PER_PAIR / NOMINAL_DFMA_PER_S,

@@ -11,9 +11,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("LUDVM_B200_LIB") or os.path.join(HERE, "libludvm_b200.so")   # (override: kernel experiments)
 
-EXACT_F64, FAST_F64, FAST_F32 = 0, 1, 2
+EXACT_F64, FAST_F64, FAST_F32, FAST12_F64 = 0, 1, 2, 3
 PTR_HOST, PTR_DEVICE = 0, 1
-MODES = {"exact": EXACT_F64, "fast": FAST_F64, "fp32": FAST_F32}
+MODES = {"exact": EXACT_F64, "fast": FAST_F64, "fp32": FAST_F32, "fast12": FAST12_F64}
 
 c_dp = C.POINTER(C.c_double)
 c_vp = C.c_void_p
@@ -147,8 +147,10 @@ class Context:
         """The all-pairs kernel the last call chose: dict(kernel, rows_per_thread, fold, tma, cluster, variant)."""
         out = (C.c_int32 * 8)()
         check(load().ludvm_ctx_last_plan(self._h, out))
-        return dict(kernel=self.KERNELS[out[0]], rows_per_thread=out[1], fold=out[2], tma=bool(out[3]),
-                    cluster=out[4], variant=out[5], warps=out[6], range_bad=out[7])
+        k = self.KERNELS[out[0]]
+        return dict(kernel=k, rows_per_thread=out[1], fold=out[2], tma=bool(out[3]), cluster=out[4], variant=out[5],
+                    warps=out[6], range_bad=out[7] if k.startswith("exact") else 0,
+                    pair_slots=(12 if (k == "fast_fused" and out[7] == 1) else 13) if k.startswith("fast_") else 0)
 
     def fp64_fma_rate(self, ms=200.0):
         r = C.c_double(0)

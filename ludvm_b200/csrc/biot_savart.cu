@@ -102,12 +102,12 @@ k_fast32x2_tiled(SrcView S, Tgt T, int nrows, int chunk_len, double *pu, double 
 
 // Whole row sums in one launch: warp-private bulk-copy pipelines, chunk partials folded through (distributed) shared
 // memory, Euler update and peer stores in the epilogue (biot_savart.cuh, "fast fused").
-template <int R, int UNROLL, int WARPS, int CL, class Tgt>
+template <int R, int UNROLL, int WARPS, int CL, int V, class Tgt>
 __global__ void __launch_bounds__(32 * WARPS, 16 / WARPS)
 k_fast_fused(SrcView S, Tgt T, int nrows, int chunk_len, int nchunks, FusedOut O)
 {
     extern __shared__ __align__(128) unsigned char fw_raw[];
-    fast_fused_block<R, UNROLL, WARPS, CL>(S, T, nrows, chunk_len, nchunks, O, *reinterpret_cast<FwSmem<WARPS> *>(fw_raw));
+    fast_fused_block<R, UNROLL, WARPS, CL, V>(S, T, nrows, chunk_len, nchunks, O, *reinterpret_cast<FwSmem<WARPS> *>(fw_raw));
 }
 
 // Fold partials.  exact: nfold = tree depth d; fast: nfold = number of chunks.  Optional second partial set
@@ -248,11 +248,11 @@ static int prove_exact_ranges(ludvm_ctx *ctx, const SrcView &S, const Tgt &T, lo
     return LUDVM_OK;
 }
 
-template <int R, int UNROLL, int WARPS, int CL, class Tgt>
+template <int R, int UNROLL, int WARPS, int CL, int V, class Tgt>
 static int launch_fused_inst(ludvm_ctx *ctx, const SrcView &S, const Tgt &T, int nrows, int chunk_len, int nchunks,
                              const FusedOut &O)
 {
-    auto kern = k_fast_fused<R, UNROLL, WARPS, CL, Tgt>;
+    auto kern = k_fast_fused<R, UNROLL, WARPS, CL, V, Tgt>;
     static bool configured[16] = {};                       // per device; a function attribute is per device
     if (!configured[ctx->device & 15]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FwSmem<WARPS>)));
@@ -274,6 +274,7 @@ static int launch_fused_inst(ludvm_ctx *ctx, const SrcView &S, const Tgt &T, int
     ctx->launches++;
     set_plan(ctx, LUDVM_K_FAST_FUSED, R, nchunks, 1, CL, UNROLL);
     ctx->plan[6] = WARPS;
+    ctx->plan[7] = V;
     return LUDVM_OK;
 }
 
@@ -285,7 +286,8 @@ static int try_launch_fused(ludvm_ctx *ctx, int mode, const SrcView &S, const Tg
                             bool *launched)
 {
     *launched = false;
-    if (mode != LUDVM_FAST_F64 || getenv("LUDVM_NO_FUSED") || getenv("LUDVM_NO_TMA")) return LUDVM_OK;
+    if ((mode != LUDVM_FAST_F64 && mode != LUDVM_FAST12_F64) || getenv("LUDVM_NO_FUSED") || getenv("LUDVM_NO_TMA"))
+        return LUDVM_OK;
     if (S.vc4 != nullptr || S.gstride != 1 || S.n0 != S.n ||
         (((uintptr_t)S.x | (uintptr_t)S.z | (uintptr_t)S.g) & 15) != 0)
         return LUDVM_OK;
@@ -304,20 +306,21 @@ static int try_launch_fused(ludvm_ctx *ctx, int mode, const SrcView &S, const Tg
     const char *ue = getenv("LUDVM_FUSED_UNROLL");
     const int U = ue ? atoi(ue) : 4;
     int rc;
-#define FUSED_CASE(RR, UU)                                                                                          \
-    rc = W == 16 ? launch_fused_inst<RR, UU, 16, 1>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)               \
-       : CL == 2 ? launch_fused_inst<RR, UU, 8, 2>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)                \
-                 : launch_fused_inst<RR, UU, 8, 1>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)
-    if (R == 4 && U == 1) FUSED_CASE(4, 1);
-    else if (R == 4 && U == 2) FUSED_CASE(4, 2);
-#ifdef FW_EXPERIMENT
-    else if (R == 4 && U == 3) FUSED_CASE(4, 3);
-    else if (R == 4 && U == 6) FUSED_CASE(4, 6);
-    else if (R == 4 && U == 8) FUSED_CASE(4, 8);
-#endif
-    else if (R == 4) FUSED_CASE(4, 4);
-    else if (R == 2) FUSED_CASE(2, 4);
-    else FUSED_CASE(1, 8);
+#define FUSED_CASE(RR, UU, VV)                                                                                      \
+    rc = W == 16 ? launch_fused_inst<RR, UU, 16, 1, VV>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)           \
+       : CL == 2 ? launch_fused_inst<RR, UU, 8, 2, VV>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)            \
+                 : launch_fused_inst<RR, UU, 8, 1, VV>(ctx, S, T, (int)nrows, chunk_len, (int)chunks, O)
+    if (mode == LUDVM_FAST12_F64) {   // opt-in 12-slot pair arithmetic
+        if (R == 4 && U == 4) FUSED_CASE(4, 4, 1);
+        else if (R == 4) FUSED_CASE(4, 8, 1);
+        else if (R == 2) FUSED_CASE(2, 4, 1);
+        else FUSED_CASE(1, 8, 1);
+    } else if (R == 4 && U == 1) FUSED_CASE(4, 1, 0);
+    else if (R == 4 && U == 2) FUSED_CASE(4, 2, 0);
+    else if (R == 4 && U == 8) FUSED_CASE(4, 8, 0);
+    else if (R == 4) FUSED_CASE(4, 4, 0);
+    else if (R == 2) FUSED_CASE(2, 4, 0);
+    else FUSED_CASE(1, 8, 0);
 #undef FUSED_CASE
     if (rc) return rc;
     CUDA_TRY(cudaGetLastError());
@@ -332,6 +335,7 @@ static int launch_partials(ludvm_ctx *ctx, int mode, const SrcView &S, const Tgt
                            double **pu, double **pw_, int *nfold)
 {
     const int sm = ctx->sm_count;
+    if (mode == LUDVM_FAST12_F64) mode = LUDVM_FAST_F64;   // outside the fused kernel: the (more accurate) 13-slot pair
     if (mode == LUDVM_EXACT_F64) {
         const int *bad;
         {
@@ -449,7 +453,7 @@ static int stage_in(ludvm_ctx *ctx, int slot, const double *host, size_t n, doub
 
 static int check_mode(int mode)
 {
-    if (mode != LUDVM_EXACT_F64 && mode != LUDVM_FAST_F64 && mode != LUDVM_FAST_F32)
+    if (mode != LUDVM_EXACT_F64 && mode != LUDVM_FAST_F64 && mode != LUDVM_FAST_F32 && mode != LUDVM_FAST12_F64)
         return set_error(LUDVM_E_ARG, "unknown arithmetic mode %d", mode);
     return LUDVM_OK;
 }

@@ -715,7 +715,7 @@ __device__ __forceinline__ const double *cluster_map(const double *p, unsigned r
     return (const double *)out;
 }
 
-template <int R, int UNROLL, int WARPS, int CL, class Tgt>
+template <int R, int UNROLL, int WARPS, int CL, int V, class Tgt>
 __device__ __forceinline__ void fast_fused_block(const SrcView &S, const Tgt &T, int nrows, int chunk_len, int nchunks,
                                                  const FusedOut &O, FwSmem<WARPS> &sm)
 {
@@ -777,7 +777,7 @@ __device__ __forceinline__ void fast_fused_block(const SrcView &S, const Tgt &T,
         for (int j = 0; j < cnt; j++) {
             const double x = b.x[j], z = b.z[j], g = b.g[j];
 #pragma unroll
-            for (int r = 0; r < R; r++) pair_fast(tx[r], tz[r], x, z, g, vc4, au[r], aw[r]);
+            for (int r = 0; r < R; r++) pair_fast_v<V>(tx[r], tz[r], x, z, g, vc4, au[r], aw[r]);
         }
     }
     // chunk partials [warp][component][row] over the front of the warp's own stage memory (all its copies have landed)

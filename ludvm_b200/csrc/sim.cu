@@ -1479,9 +1479,14 @@ __device__ __noinline__ void cta_conv_tiled_fast(const SimDev &S, const Step &st
         }
     }
     __syncthreads();
-    if (nrows > 2 * nth) {
+    // rows per thread = ceil(rows / threads): with 256 threads and <= 684 rows a fixed R = 4 left a third of the row
+    // slots empty (684 / 1024); R = 3 fills 684 / 768
+    if (nrows > 3 * nth) {
         cta_tiled_rows<4>(tx + P, tz + P, sgw, n, S.vc4, tx, tz, nrows, S.pb_u, S.pb_w);
         cta_tiled_rows<4>(tx, tz, sgf, P, S.vc4, tx + P, tz + P, n, S.foil_u, S.foil_w);
+    } else if (nrows > 2 * nth) {
+        cta_tiled_rows<3>(tx + P, tz + P, sgw, n, S.vc4, tx, tz, nrows, S.pb_u, S.pb_w);
+        cta_tiled_rows<3>(tx, tz, sgf, P, S.vc4, tx + P, tz + P, n, S.foil_u, S.foil_w);
     } else if (nrows > nth) {
         cta_tiled_rows<2>(tx + P, tz + P, sgw, n, S.vc4, tx, tz, nrows, S.pb_u, S.pb_w);
         cta_tiled_rows<2>(tx, tz, sgf, P, S.vc4, tx + P, tz + P, n, S.foil_u, S.foil_w);

@@ -64,7 +64,7 @@ def test_selfconv_step_2p20_fast_vs_oracle(cloud, oracle, monkeypatch):
     per-rank launch of the 8-GPU run) and the p2p entry point against the full launch bit for bit."""
     g, x, z = cloud["g"], cloud["x"], cloud["z"]
     u, w, xo, zo, plan = _step(cloud, "fast")
-    assert plan == dict(kernel="fast_fused", rows_per_thread=4, fold=16, tma=True, cluster=2, variant=4, warps=8, range_bad=0), plan
+    assert plan == dict(kernel="fast_fused", rows_per_thread=4, fold=16, tma=True, cluster=2, variant=4, warps=8, range_bad=0, pair_slots=13), plan
     rows = np.sort(np.random.default_rng(7).choice(N, 4096, replace=False))
     uo, wo = oracle.induced_velocity(g, x, z, x[rows], z[rows], VCORE)
     assert np.max(np.abs(u[rows] - uo)) <= 1e-12 * np.max(np.abs(uo))
@@ -76,7 +76,7 @@ def test_selfconv_step_2p20_fast_vs_oracle(cloud, oracle, monkeypatch):
     # the partial-sum path bench.py timed in round 1
     monkeypatch.setenv("LUDVM_NO_FUSED", "1")
     u2, w2, xo2, zo2, plan2 = _step(cloud, "fast")
-    assert plan2 == dict(kernel="fast_tiled_tma", rows_per_thread=4, fold=16, tma=True, cluster=1, variant=0, warps=0, range_bad=0), plan2
+    assert plan2 == dict(kernel="fast_tiled_tma", rows_per_thread=4, fold=16, tma=True, cluster=1, variant=0, warps=0, range_bad=0, pair_slots=13), plan2
     assert biteq(u2, u) and biteq(w2, w) and biteq(xo2, xo) and biteq(zo2, zo)
     us, ws, xs, zs, plans = _step(cloud, "fast", row0=3 * (N // 8), nrows=N // 8)
     assert plans["kernel"] == "fast_tiled_tma" and plans["rows_per_thread"] == 4 and plans["fold"] == 16
@@ -172,7 +172,7 @@ def test_flowfield_quarter_million_points(cloud, oracle, monkeypatch):
     vc4, ctx = VCORE ** 4, cloud["ctx"]
     u, w = ops.flowfield_velocity(g, xw, zw, None, None, None, vc4, x1, z1, mode="fast", ctx=ctx)
     plan = ctx.last_plan()
-    assert plan == dict(kernel="fast_fused", rows_per_thread=4, fold=16, tma=True, cluster=2, variant=4, warps=8, range_bad=0), plan
+    assert plan == dict(kernel="fast_fused", rows_per_thread=4, fold=16, tma=True, cluster=2, variant=4, warps=8, range_bad=0, pair_slots=13), plan
     pts = np.sort(np.random.default_rng(3).choice(512 * 512, 2048, replace=False))
     X, Z = np.meshgrid(x1, z1, indexing="ij")
     uo, wo = oracle.induced_velocity(g, xw, zw, X.ravel()[pts], Z.ravel()[pts], VCORE)
@@ -188,7 +188,7 @@ def test_flowfield_quarter_million_points(cloud, oracle, monkeypatch):
     u2, w2 = ops.flowfield_velocity(g, xw, zw, None, None, None, vc4, x1, z1, mode="fast", ctx=ctx)
     monkeypatch.delenv("LUDVM_NO_FUSED")
     plan2 = ctx.last_plan()
-    assert plan2 == dict(kernel="fast_tiled_tma", rows_per_thread=4, fold=16, tma=True, cluster=1, variant=0, warps=0, range_bad=0), plan2
+    assert plan2 == dict(kernel="fast_tiled_tma", rows_per_thread=4, fold=16, tma=True, cluster=1, variant=0, warps=0, range_bad=0, pair_slots=13), plan2
     assert biteq(u2, u) and biteq(w2, w)
     # with a second (bound-vortex) source set the partial-sum path serves both sets; compare with the sum of two calls
     gb, xb, zb = np.linspace(0.01, 0.02, 80), np.linspace(-1.0, 0.0, 80), np.zeros(80)
@@ -219,3 +219,24 @@ def test_repeated_launches_are_bitwise_stable(cloud, monkeypatch):
         monkeypatch.delenv("LUDVM_NO_FUSED")
         if chunks:
             monkeypatch.delenv("LUDVM_FAST_CHUNKS")
+
+
+def test_fast12_opt_in_mode_within_tolerance(cloud, oracle):
+    """LUDVM_FAST12_F64 (opt-in): the 12-slot pair -- one second-order refinement of the centred MUFU seed.  Per-call
+    results must stay inside BASELINE.json's 1e-12 (relative to sum |terms|); the measured error is reported."""
+    g, x, z = cloud["g"], cloud["x"], cloud["z"]
+    u, w, xo, zo, plan = _step(cloud, "fast12", row0=N // 2, nrows=N // 8)
+    assert plan["kernel"] == "fast_fused" and plan["pair_slots"] == 12 and plan["rows_per_thread"] == 4, plan
+    rows = np.sort(np.random.default_rng(5).choice(N // 8, 1024, replace=False))
+    uo, wo = oracle.induced_velocity(g, x, z, x[N // 2 + rows], z[N // 2 + rows], VCORE)
+    bu, bw = cond_bound_rows(g, x, z, x[N // 2 + rows[:256]], z[N // 2 + rows[:256]], VCORE)
+    eu, ew = np.abs(u[rows[:256]] - uo[:256]) / bu, np.abs(w[rows[:256]] - wo[:256]) / bw
+    assert eu.max() <= 5e-13 and ew.max() <= 5e-13, (eu.max(), ew.max())
+    assert np.max(np.abs(u[rows] - uo)) <= 1e-12 * np.max(np.abs(uo))
+    assert biteq(xo, x[N // 2:N // 2 + N // 8] + DT * u)
+    u13 = _step(cloud, "fast", row0=N // 2, nrows=N // 8)[0]
+    assert not biteq(u13, u) and np.max(np.abs(u13 - u)) <= 1e-12 * np.max(np.abs(u13))
+    # a launch the fused kernel does not take falls back to the 13-slot kernels
+    u_s, _, _, _, plan_s = _step(cloud, "fast12", n=20000)
+    assert plan_s["kernel"] == "fast_tiled_tma" and plan_s["pair_slots"] == 13
+    assert biteq(u_s, _step(cloud, "fast", n=20000)[0])
