@@ -2,7 +2,7 @@
 """bench.py -- benchmarks of the LUDVM vortex-velocity hot path on B200.
 
     python bench.py [--gpus G] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--workload selfconv|flowfield|sweep] [--n N] [--no-extra-legs]
+                    [--workload selfconv|flowfield|sweep] [--nvortices N] [--no-extra-legs]
 
 Workloads (BASELINE.json `configs`):
   selfconv   configs[2], the headline: synthetic all-pairs self-convection of N = 2^20 Vatistas vortices, seed 20260101,
@@ -657,7 +657,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="selfconv", choices=["selfconv", "flowfield", "sweep"])
-    ap.add_argument("--n", type=int, default=1 << 20)
+    ap.add_argument("--n", "--nvortices", dest="n", type=int, default=1 << 20)   # (torchrun's own parser trips over a bare --n)
     ap.add_argument("--transport", default="auto", choices=["auto", "p2p", "nccl"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--ref-step-s", type=float, default=4.0)

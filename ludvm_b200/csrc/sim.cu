@@ -1374,6 +1374,16 @@ __global__ void __launch_bounds__(256, 1) k_sim_coop(SimDev S, int nsteps, unsig
 #else
 #define COOP_T(k) do { } while (0)
 #endif
+    // The loads (LUDVM.py:1035-1090) and the cumulative bound circulation of step i feed nothing inside the loop, so CTA 0 /
+    // CTA 1 evaluate them while the other CTAs already run phase 1 of step i + 1: the barrier after the Euler update no
+    // longer waits for the 4.4 us loads block (profiles/r02g_coop_trace.txt).  What they read -- the convection partials
+    // at the gamma points, gamma_airfoil / g_airfoil row itev, fourier row i -- is not rewritten before phase 3 of the
+    // next step, two barriers later.  Phase 1 therefore runs on CTAs 2 .. nb-2 (CTA nb-1: the circulation sums).
+    auto deferred_tail = [&](int ip) {
+        Step sp{ip, ip - 1, ((volatile int *)S.ilev_arr)[ip]};
+        if (blockIdx.x == 0) phase_finish_loads(S, sp, tab, scr, 0, S.sum_nodes);
+        else if (blockIdx.x == 1) phase_gamma_cumsum(S, sp, threadIdx.x, blockDim.x);
+    };
     for (int i = first; i <= last; i++) {
         Step st{i, i - 1, ((volatile int *)S.ilev_arr)[i]};
         // phase 1: the wake on the gamma points; the last CTA evaluates the two circulation sums instead
@@ -1385,10 +1395,16 @@ __global__ void __launch_bounds__(256, 1) k_sim_coop(SimDev S, int nsteps, unsig
                 S.pre_sums[1] = sL;
             }
         } else {
-            Pool pl = grid_pool();
-            pl.nwarps -= blockDim.x >> 5;
-            pl.nth -= blockDim.x;
-            phase_wake_on_foil(S, st, st.itev, st.ilev, pl);
+            if (blockIdx.x <= 1) {
+                if (i > first) deferred_tail(i - 1);
+            } else {
+                Pool pl = grid_pool();
+                pl.wid -= 2 * (blockDim.x >> 5);  // CTAs 0 and 1 are busy with the previous step's loads / cumulative sums
+                pl.tid -= 2 * blockDim.x;
+                pl.nwarps -= 3 * (blockDim.x >> 5);
+                pl.nth -= 3 * blockDim.x;
+                phase_wake_on_foil(S, st, st.itev, st.ilev, pl);
+            }
         }
         COOP_T(0);
         grid_barrier(bar, epoch, S.counters);
@@ -1401,13 +1417,12 @@ __global__ void __launch_bounds__(256, 1) k_sim_coop(SimDev S, int nsteps, unsig
         COOP_T(4);
         grid_barrier(bar, epoch, S.counters);
         COOP_T(5);
-        if (blockIdx.x == 0) phase_finish_loads(S, st, tab, scr, 0, S.sum_nodes);
-        else if (blockIdx.x == 1) phase_gamma_cumsum(S, st, threadIdx.x, blockDim.x);
-        else phase_finish_update(S, st, (long)(blockIdx.x - 2) * blockDim.x + threadIdx.x, (long)(nb - 2) * blockDim.x, 0);
+        phase_finish_update(S, st, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)nb * blockDim.x, 0);
         COOP_T(6);
         grid_barrier(bar, epoch, S.counters);
         COOP_T(7);
     }
+    if (last >= first && blockIdx.x <= 1) deferred_tail(last);
 #ifdef LUDVM_TRACE
     if (blockIdx.x == 0 && threadIdx.x == 0)
         for (int q = 0; q < 8; q++) g_trace[40 + q] = acc[q];
@@ -2061,7 +2076,7 @@ LUDVM_API int ludvm_sim_create(ludvm_ctx *ctx, const ludvm_sim_params *p, const 
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_coop, 256, s->solve_smem) == cudaSuccess && per_sm >= 1)
             s->coop_grid = ctx->sm_count;
         if (const char *ge = getenv("LUDVM_COOP_GRID"))   // experiments: a smaller persistent grid (>= 3 CTAs)
-            if (s->coop_grid) s->coop_grid = std::max(3, std::min(s->coop_grid, atoi(ge)));
+            if (s->coop_grid) s->coop_grid = std::max(4, std::min(s->coop_grid, atoi(ge)));
         cudaGetLastError();
     }
     CU(cudaStreamSynchronize(ctx->stream));  // the host tables may be freed by the caller after return
@@ -2087,7 +2102,7 @@ LUDVM_API int ludvm_sim_run(ludvm_sim *s, long nsteps)
         return LUDVM_OK;
     }
     // small wakes: the persistent cooperative kernel, all of those steps in one launch
-    if (s->coop_grid >= 3 && !getenv("LUDVM_NO_COOP")) {
+    if (s->coop_grid >= 4 && !getenv("LUDVM_NO_COOP")) {
         // fast mode hands over to the graph path (tiled, overlapped step) earlier than exact mode does
         const long coop_max = s->p.mode == LUDVM_EXACT_F64 ? SIM_COOP_MAX_WAKE : SIM_TILED_MIN_WAKE;
         const long last_small = (coop_max - 2 - (long)s->p.nfree) / 2;   // wake after step i <= 2 i + 2 + nfree

@@ -46,7 +46,7 @@ def test_sharded_self_convection_bitwise_equal_to_one_rank(ngpus):
 def test_bench_line_parity_on_several_gpus(ngpus):
     """bench.py under torchrun at a reduced N: the JSON line's parity objects (self-convection vs oracle + sharded vs
     unsharded, flow-field slab vs oracle, sweep slice vs oracle) must all be ok."""
-    r = _torchrun(ngpus, ["bench.py", "--gpus", str(ngpus), "--steps", "1", "--warmup", "1", "--n", str(1 << 18)])
+    r = _torchrun(ngpus, ["bench.py", "--gpus", str(ngpus), "--steps", "1", "--warmup", "1", "--nvortices", str(1 << 18)])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["n_gpus"] == ngpus
