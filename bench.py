@@ -537,13 +537,12 @@ def flowfield_leg(env, steps, warmup, with_e2e):
                       "vorticity_block_bitwise_vs_oracle_stencil": vort_ok}}
     if with_e2e:   # public host API: host sources/axes in, host u/w out, then the stencil on host fields
         t0 = time.perf_counter()
-        uh, wh = ops.flowfield_velocity(g_h, xw_h, zw_h, None, None, None, vc4, x1_h, z1_h, row0=h0, nrows=ne,
-                                        mode="fast", ctx=ctx)
-        omh = ops.flowfield_vorticity(x1_h[h0:h1], z1_h, uh[None], wh[None], ctx=ctx)
+        uh, wh, omh = ops.flowfield(g_h, xw_h, zw_h, None, None, None, vc4, x1_h, z1_h, row0=h0, nrows=ne, mode="fast",
+                                    ctx=ctx)
         el = env.reduce(time.perf_counter() - t0)
-        out["e2e"] = {"value": pairs / el, "unit": UNIT, "h2d_bytes_per_step": 8 * (3 * FF_NSRC + nx + nz + 2 * ne * nz),
-                      "d2h_bytes_per_step": 8 * 3 * ne * nz, "checksum": float(omh[0, 1, 1]),
-                      "api": "ops.flowfield_velocity + ops.flowfield_vorticity (host numpy buffers)"}
+        out["e2e"] = {"value": pairs / el, "unit": UNIT, "h2d_bytes_per_step": 8 * (3 * FF_NSRC + nx + nz),
+                      "d2h_bytes_per_step": 8 * 3 * ne * nz, "checksum": float(omh[1, 1]),
+                      "api": "ops.flowfield = C ABI ludvm_flowfield(PTR_HOST): host sources and axes in, host u, w, ome out"}
     return out
 
 

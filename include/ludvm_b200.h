@@ -125,6 +125,12 @@ int ludvm_flowfield_velocity(ludvm_ctx *ctx, int mode, const double *ga, const d
                              long na, const double *gb, const double *xb, const double *zb, long nb, double vc4,
                              const double *x1, long nx, const double *z1, long nz, long row0, long nrows,
                              double *u, double *w, int ptr_kind);
+/* Velocity AND vorticity of one snapshot in one call (the body of LUDVM.flowfield's loop, LUDVM.py:1193-1292, for the
+ * rows [row0, row0+nrows) of the grid, nrows >= 2): u, w, ome are [nrows, nz].  With host pointers the fields cross the
+ * bus once.  The stencil is applied to the slab as given (one-sided at its first / last row). */
+int ludvm_flowfield(ludvm_ctx *ctx, int mode, const double *ga, const double *xa, const double *za, long na,
+                    const double *gb, const double *xb, const double *zb, long nb, double vc4, const double *x1, long nx,
+                    const double *z1, long nz, long row0, long nrows, double *u, double *w, double *ome, int ptr_kind);
 /* Vorticity stencil of LUDVM.py:1222-1292 (centred interior, one-sided edges/corners) on [ns, nx, nz] fields. */
 int ludvm_flowfield_vorticity(ludvm_ctx *ctx, const double *x1, long nx, const double *z1, long nz,
                               const double *u, const double *w, long ns, double *ome, int ptr_kind);

@@ -63,6 +63,8 @@ SIGNATURES = {
     "ludvm_flowfield_velocity": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, C.c_long, c_vp, c_vp, c_vp, C.c_long,
                                            C.c_double, c_vp, C.c_long, c_vp, C.c_long, C.c_long, C.c_long,
                                            c_vp, c_vp, C.c_int]),
+    "ludvm_flowfield": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, C.c_long, c_vp, c_vp, c_vp, C.c_long, C.c_double, c_vp,
+                                  C.c_long, c_vp, C.c_long, C.c_long, C.c_long, c_vp, c_vp, c_vp, C.c_int]),
     "ludvm_flowfield_vorticity": (C.c_int, [c_vp, c_vp, C.c_long, c_vp, C.c_long, c_vp, c_vp, C.c_long, c_vp,
                                             C.c_int]),
     "ludvm_sim_create": (C.c_int, [c_vp, C.POINTER(SimParams), C.POINTER(SimTables), C.POINTER(c_vp)]),

@@ -689,6 +689,58 @@ LUDVM_API int ludvm_flowfield_velocity(ludvm_ctx *ctx, int mode, const double *g
     return LUDVM_OK;
 }
 
+// Velocity and vorticity of one snapshot in one call: with host buffers the fields make one trip (u, w, ome out) instead
+// of u, w out, back in for the stencil, and ome out.
+LUDVM_API int ludvm_flowfield(ludvm_ctx *ctx, int mode, const double *ga, const double *xa, const double *za, long na,
+                              const double *gb, const double *xb, const double *zb, long nb, double vc4,
+                              const double *x1, long nx, const double *z1, long nz, long row0, long nrows, double *u,
+                              double *w, double *ome, int ptr_kind)
+{
+    ARG_CHECK(ctx && ome && u && w && x1 && z1);
+    ARG_CHECK(ptr_kind == LUDVM_PTR_HOST || ptr_kind == LUDVM_PTR_DEVICE);
+    ARG_CHECK(nrows >= 2 && nz >= 2 && row0 >= 0 && row0 + nrows <= nx);
+    if (ptr_kind == LUDVM_PTR_DEVICE) {
+        int rc = ludvm_flowfield_velocity(ctx, mode, ga, xa, za, na, gb, xb, zb, nb, vc4, x1, nx, z1, nz, row0, nrows, u, w,
+                                          ptr_kind);
+        if (rc) return rc;
+        return ludvm_flowfield_vorticity(ctx, x1 + row0, nrows, z1, nz, u, w, 1, ome, ptr_kind);
+    }
+    DeviceGuard g(ctx->device);
+    // device-resident u, w, ome and axes in scratch slot 5 / 6; the velocity call stages sources and axes itself (slot 4)
+    const size_t npts = (size_t)nrows * (size_t)nz;
+    void *p, *q;
+    int rc;
+    if ((rc = scratch_reserve(ctx, 5, 3 * npts * sizeof(double), &p))) return rc;
+    if ((rc = scratch_reserve(ctx, 6, ((size_t)nx + nz + 8) * sizeof(double), &q))) return rc;
+    double *du = (double *)p, *dw = du + npts, *dome = dw + npts, *dx1 = (double *)q, *dz1 = dx1 + nx;
+    CUDA_TRY(cudaMemcpyAsync(dx1, x1, (size_t)nx * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(dz1, z1, (size_t)nz * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    // sources: staged by a host-pointer call would also download u, w; stage them here and run on device pointers
+    const size_t nsrc = 3 * (size_t)na + 3 * (size_t)nb;
+    void *sp;
+    if ((rc = scratch_reserve(ctx, 4, (nsrc + 8) * sizeof(double), &sp))) return rc;
+    double *b = (double *)sp;
+    const double *hsrc[6] = {ga, xa, za, gb, xb, zb};
+    const double *dsrc[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < 6; k++) {
+        const size_t n = k < 3 ? (size_t)na : (size_t)nb;
+        if (n == 0) continue;
+        ARG_CHECK(hsrc[k] != nullptr);
+        CUDA_TRY(cudaMemcpyAsync(b, hsrc[k], n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        dsrc[k] = b;
+        b += n;
+    }
+    if ((rc = ludvm_flowfield_velocity(ctx, mode, dsrc[0], dsrc[1], dsrc[2], na, dsrc[3], dsrc[4], dsrc[5], nb, vc4, dx1, nx,
+                                       dz1, nz, row0, nrows, du, dw, LUDVM_PTR_DEVICE)))
+        return rc;
+    if ((rc = ludvm_flowfield_vorticity(ctx, dx1 + row0, nrows, dz1, nz, du, dw, 1, dome, LUDVM_PTR_DEVICE))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(u, du, npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(w, dw, npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaMemcpyAsync(ome, dome, npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    return LUDVM_OK;
+}
+
 LUDVM_API int ludvm_flowfield_vorticity(ludvm_ctx *ctx, const double *x1, long nx, const double *z1, long nz,
                                         const double *u, const double *w, long ns, double *ome, int ptr_kind)
 {

@@ -423,14 +423,14 @@ class LUDVM:
         xs = x1[row0:row0 + nrows]
         x, z = np.meshgrid(xs, z1, indexing='ij')
         ns = len(tsteps)
-        u, w = np.zeros([ns, nrows, len(z1)]), np.zeros([ns, nrows, len(z1)])
+        u, w, ome = (np.zeros([ns, nrows, len(z1)]) for _ in range(3))
         vc4 = float(self.v_core ** 4)
         ap = np.append
         for ii, itev in enumerate(tsteps):
             if self.verbose:
                 print('Flowfield tstep =', itev)
             if itev == 0:     # only the free vortices exist (LUDVM.py:1202-1207)
-                u[ii], w[ii] = ops.flowfield_velocity(self.circulation['FREE'], self.path['FREE'][0, 0],
+                u[ii], w[ii], ome[ii] = ops.flowfield(self.circulation['FREE'], self.path['FREE'][0, 0],
                                                       self.path['FREE'][0, 1], None, None, None, vc4, x1, z1,
                                                       row0=row0, nrows=nrows, mode=self.mode, ctx=self.ctx)
             else:             # index conventions of LUDVM.py:1209-1217 kept
@@ -446,11 +446,11 @@ class LUDVM:
                 zw = ap(ap(self.path['TEV'][hrow, 1, :itev + 1], self.path['LEV'][hrow, 1, :ilev + 1]),
                         self.path['FREE'][itev, 1])
                 gp = self.path['airfoil_gamma_points'][itev - 1]
-                u[ii], w[ii] = ops.flowfield_velocity(g, xw, zw, self.circulation['airfoil'][itev - 1], gp[0], gp[1],
+                u[ii], w[ii], ome[ii] = ops.flowfield(g, xw, zw, self.circulation['airfoil'][itev - 1], gp[0], gp[1],
                                                       vc4, x1, z1, row0=row0, nrows=nrows, mode=self.mode, ctx=self.ctx)
         self.x_ff, self.z_ff = x, z
         self.u_ff, self.w_ff = u, w
-        self.ome_ff = ops.flowfield_vorticity(xs, z1, u, w, ctx=self.ctx)
+        self.ome_ff = ome        # velocity and stencil of a snapshot in one call: the fields cross the bus once
         return None
 
     def animation(self, step=1, ani_interval=10):

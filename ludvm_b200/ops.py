@@ -71,6 +71,23 @@ def flowfield_velocity(ga, xa, za, gb, xb, zb, vc4, x1, z1, row0=0, nrows=None, 
     return u, w
 
 
+def flowfield(ga, xa, za, gb, xb, zb, vc4, x1, z1, row0=0, nrows=None, mode="exact", ctx=None):
+    """Velocity and vorticity of one snapshot on rows [row0, row0+nrows) of the 'ij' mesh x1 x z1 in one call
+    (LUDVM.py:1193-1292), host buffers: returns (u, w, ome), each [nrows, len(z1)]."""
+    ctx = ctx or _lib.default_context()
+    ga, xa, za, x1, z1 = (f64(a) for a in (ga, xa, za, x1, z1))
+    nb = 0 if gb is None else len(gb)
+    if nb:
+        gb, xb, zb = (f64(a) for a in (gb, xb, zb))
+    nrows = x1.size - row0 if nrows is None else nrows
+    u, w, ome = (np.empty((nrows, z1.size)) for _ in range(3))
+    check(load().ludvm_flowfield(ctx.handle, _mode(mode), ptr(ga), ptr(xa), ptr(za), ga.size,
+                                 ptr(gb) if nb else None, ptr(xb) if nb else None, ptr(zb) if nb else None, nb,
+                                 float(vc4), ptr(x1), x1.size, ptr(z1), z1.size, int(row0), int(nrows), ptr(u), ptr(w),
+                                 ptr(ome), PTR_HOST))
+    return u, w, ome
+
+
 def flowfield_velocity_device(ctx, mode, g, xw, zw, vc4, x1, z1, row0, nrows, u, w):
     """Same for one source set with torch CUDA float64 tensors; u, w are [nrows, len(z1)] (asynchronous on ctx's
     stream)."""
