@@ -17,7 +17,7 @@
 //   phase_finish_*       loads Fn, Fs, L, D, T, M; fold partials, forward-Euler update in place, history snapshot
 //                                                                                         (LUDVM.py:1069-1090, 1108-1127)
 // and three drivers run them:
-//   * coop path   -- k_sim_coop: one persistent cooperative grid (one CTA per SM) runs all steps while the wake is
+//   * coop path   -- k_sim_persist: one thread-block cluster (smallest wakes) or one persistent cooperative grid (one CTA per SM) runs all steps while the wake is
 //                    small (latency-bound), grid barriers between the phases, the solve CTA's tables resident in
 //                    shared memory.
 //   * graph path  -- four kernels per step, grid-wide warp pools, K steps captured once in a CUDA graph and replayed
@@ -50,6 +50,9 @@ namespace ludvm {
 #define SIM_TILED_CHUNKS_MAX 64   // partial-sum slots per row of the tiled convection
 #define SIM_EXACT_TILED_MIN_WAKE 8192   // exact mode, graph path: wakes at least this large use k_conv_partials_exact_tiled
 #define SIM_COOP_MAX_WAKE 8192    // wakes up to this size are stepped by the persistent cooperative kernel
+#define SIM_CLUSTER_CTAS 16       // the single-cluster persistent kernel: CTAs (16 = the non-portable maximum) x threads
+#define SIM_CLUSTER_THREADS 512
+#define SIM_CLUSTER_MAX_WAKE 1024 // wakes up to this size are stepped by the single-cluster kernel (LUDVM_CLUSTER_MAX_WAKE)
 #define FINISH_STAGE 4096         // doubles of staging in the loads block of k_finish
 #define SOLVE_SMEM_LIMIT (200 * 1024)   // dynamic shared memory of the solve kernel (bytes)
 #define LUDVM_MAX_PANELS 1024     // Npoints - 1 <= this: 18 doubles per panel of the solve kernel's fixed shared memory
@@ -1355,7 +1358,26 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned l
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(256, 1) k_sim_coop(SimDev S, int nsteps, unsigned long long *bar)
+// One persistent kernel, two ways of keeping its CTAs in step:
+//   CLUSTER = false  a cooperative grid of one CTA per SM with the L2 grid barrier above (wakes up to a few thousand);
+//   CLUSTER = true   ONE thread-block cluster (up to 16 CTAs, co-scheduled on one GPC) whose phase boundary is the hardware
+//                    cluster barrier (barrier.cluster, release/acquire at cluster scope: ~0.2 us instead of ~1.7-3 us).
+//                    A README-size step is four barriers and ~10 us of O(N^2) work spread thin over 148 SMs, so fewer
+//                    CTAs with a cheap barrier win while the wake is small (SIM_CLUSTER_MAX_WAKE).
+// The loads (LUDVM.py:1035-1090) and the cumulative bound circulation of step i feed nothing inside the loop, and the
+// solve of step i + 1 keeps one CTA busy for ~11 us while every other CTA waits: CTA 1 evaluates the loads and CTA 2 the
+// cumulative sums of step i during that window (both have the constant tables / scratch of their own).  What they read --
+// the convection partials at the gamma points, gamma_airfoil / g_airfoil row itev, fourier row i -- is not rewritten
+// before phase 3 of step i + 1, which the barrier after the solve holds back until they are done.
+template <bool CLUSTER>
+__device__ __forceinline__ void persist_barrier(unsigned long long *bar, unsigned long long &k, long long *counters)
+{
+    if (CLUSTER) cluster_sync_all();
+    else grid_barrier(bar, k, counters);
+}
+
+template <bool CLUSTER, int NTH>
+__global__ void __launch_bounds__(NTH, 1) k_sim_persist(SimDev S, int nsteps, unsigned long long *bar)
 {
     extern __shared__ double sm[];
     unsigned long long epoch = 0;
@@ -1363,7 +1385,7 @@ __global__ void __launch_bounds__(256, 1) k_sim_coop(SimDev S, int nsteps, unsig
     const int last = min(S.nt - 1, first + nsteps - 1);
     const int nb = gridDim.x;
     double *const tab = sm, *const scr = sm + TABLE_SMEM_DOUBLES(S.P, S.Nc, S.sinn_smem);
-    if (blockIdx.x == 0) {   // the solve / loads CTA keeps the constant tables in shared memory for the whole launch
+    if (blockIdx.x <= 1) {   // the solve CTA and the loads CTA keep the constant tables in shared memory for the whole launch
         stage_tables(S, StepTables(tab, S));
         tables_wait();
     }
@@ -1374,15 +1396,10 @@ __global__ void __launch_bounds__(256, 1) k_sim_coop(SimDev S, int nsteps, unsig
 #else
 #define COOP_T(k) do { } while (0)
 #endif
-    // The loads (LUDVM.py:1035-1090) and the cumulative bound circulation of step i feed nothing inside the loop, so CTA 0 /
-    // CTA 1 evaluate them while the other CTAs already run phase 1 of step i + 1: the barrier after the Euler update no
-    // longer waits for the 4.4 us loads block (profiles/r02g_coop_trace.txt).  What they read -- the convection partials
-    // at the gamma points, gamma_airfoil / g_airfoil row itev, fourier row i -- is not rewritten before phase 3 of the
-    // next step, two barriers later.  Phase 1 therefore runs on CTAs 2 .. nb-2 (CTA nb-1: the circulation sums).
     auto deferred_tail = [&](int ip) {
         Step sp{ip, ip - 1, ((volatile int *)S.ilev_arr)[ip]};
-        if (blockIdx.x == 0) phase_finish_loads(S, sp, tab, scr, 0, S.sum_nodes);
-        else if (blockIdx.x == 1) phase_gamma_cumsum(S, sp, threadIdx.x, blockDim.x);
+        if (blockIdx.x == 1) phase_finish_loads(S, sp, tab, scr, 0, S.sum_nodes);
+        else if (blockIdx.x == 2) phase_gamma_cumsum(S, sp, threadIdx.x, blockDim.x);
     };
     for (int i = first; i <= last; i++) {
         Step st{i, i - 1, ((volatile int *)S.ilev_arr)[i]};
@@ -1395,34 +1412,29 @@ __global__ void __launch_bounds__(256, 1) k_sim_coop(SimDev S, int nsteps, unsig
                 S.pre_sums[1] = sL;
             }
         } else {
-            if (blockIdx.x <= 1) {
-                if (i > first) deferred_tail(i - 1);
-            } else {
-                Pool pl = grid_pool();
-                pl.wid -= 2 * (blockDim.x >> 5);  // CTAs 0 and 1 are busy with the previous step's loads / cumulative sums
-                pl.tid -= 2 * blockDim.x;
-                pl.nwarps -= 3 * (blockDim.x >> 5);
-                pl.nth -= 3 * blockDim.x;
-                phase_wake_on_foil(S, st, st.itev, st.ilev, pl);
-            }
+            Pool pl = grid_pool();
+            pl.nwarps -= blockDim.x >> 5;
+            pl.nth -= blockDim.x;
+            phase_wake_on_foil(S, st, st.itev, st.ilev, pl);
         }
         COOP_T(0);
-        grid_barrier(bar, epoch, S.counters);
+        persist_barrier<CLUSTER>(bar, epoch, S.counters);
         COOP_T(1);
         if (blockIdx.x == 0) phase_solve<LUDVM_METHOD_FAURE>(S, st, tab, scr, S.pre_sums, false);
+        else if (i > first) deferred_tail(i - 1);
         COOP_T(2);
-        grid_barrier(bar, epoch, S.counters);
+        persist_barrier<CLUSTER>(bar, epoch, S.counters);
         COOP_T(3);
         phase_conv_partials(S, st, grid_pool());
         COOP_T(4);
-        grid_barrier(bar, epoch, S.counters);
+        persist_barrier<CLUSTER>(bar, epoch, S.counters);
         COOP_T(5);
         phase_finish_update(S, st, (long)blockIdx.x * blockDim.x + threadIdx.x, (long)nb * blockDim.x, 0);
         COOP_T(6);
-        grid_barrier(bar, epoch, S.counters);
+        persist_barrier<CLUSTER>(bar, epoch, S.counters);
         COOP_T(7);
     }
-    if (last >= first && blockIdx.x <= 1) deferred_tail(last);
+    if (last >= first) deferred_tail(last);
 #ifdef LUDVM_TRACE
     if (blockIdx.x == 0 && threadIdx.x == 0)
         for (int q = 0; q < 8; q++) g_trace[40 + q] = acc[q];
@@ -1794,6 +1806,7 @@ struct ludvm_sim {
     size_t solve_smem = 0, finish_smem = 0;
     unsigned long long *d_bar = nullptr;  // grid-barrier counter of the cooperative path
     int coop_grid = 0;                    // CTAs of the cooperative kernel (0: path not available on this device)
+    int cluster_ctas = 0;                 // CTAs of the single-cluster kernel (0: not available)
     cudaStream_t cap_stream2 = nullptr;   // second capture stream: the overlapped step's old-wake convection branch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t cap_stream = nullptr;  // private stream used only to record graphs (the context's stream may be
@@ -2072,12 +2085,34 @@ LUDVM_API int ludvm_sim_create(ludvm_ctx *ctx, const ludvm_sim_params *p, const 
     {   // cooperative path: needs cooperative-launch support and one resident CTA per SM
         int coop = 0, per_sm = 0;
         cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
-        if (coop && !cta && cudaFuncSetAttribute(k_sim_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->solve_smem) == cudaSuccess &&
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_coop, 256, s->solve_smem) == cudaSuccess && per_sm >= 1)
+        if (coop && !cta && cudaFuncSetAttribute(k_sim_persist<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->solve_smem) == cudaSuccess &&
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_persist<false, 256>, 256, s->solve_smem) == cudaSuccess && per_sm >= 1)
             s->coop_grid = ctx->sm_count;
-        if (const char *ge = getenv("LUDVM_COOP_GRID"))   // experiments: a smaller persistent grid (>= 3 CTAs)
+        if (const char *ge = getenv("LUDVM_COOP_GRID"))   // experiments: a smaller persistent grid (>= 4 CTAs)
             if (s->coop_grid) s->coop_grid = std::max(4, std::min(s->coop_grid, atoi(ge)));
         cudaGetLastError();
+        // cluster path: one thread-block cluster of SIM_CLUSTER_CTAS CTAs (16 needs the non-portable opt-in), if the
+        // device can co-schedule it with this much shared memory per CTA
+        if (!cta && !getenv("LUDVM_NO_CLUSTER")) {
+            const char *ce = getenv("LUDVM_CLUSTER_CTAS");
+            int want = ce ? atoi(ce) : SIM_CLUSTER_CTAS;
+            want = want >= 16 ? 16 : (want >= 8 ? 8 : 4);
+            const void *kern = (const void *)k_sim_persist<true, SIM_CLUSTER_THREADS>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->solve_smem) == cudaSuccess &&
+                (want <= 8 || cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(want);
+                cfg.blockDim = dim3(SIM_CLUSTER_THREADS);
+                cfg.dynamicSmemBytes = s->solve_smem;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                int nclusters = 0;
+                if (cudaOccupancyMaxActiveClusters(&nclusters, kern, &cfg) == cudaSuccess && nclusters >= 1) s->cluster_ctas = want;
+            }
+            cudaGetLastError();
+        }
     }
     CU(cudaStreamSynchronize(ctx->stream));  // the host tables may be freed by the caller after return
 #undef TRY
@@ -2101,6 +2136,30 @@ LUDVM_API int ludvm_sim_run(ludvm_sim *s, long nsteps)
         s->steps_enqueued += todo;
         return LUDVM_OK;
     }
+    // smallest wakes: ONE thread-block cluster with the hardware cluster barrier between the phases
+    if (s->cluster_ctas >= 4) {
+        const char *me = getenv("LUDVM_CLUSTER_MAX_WAKE");
+        const long cmax = me ? atol(me) : SIM_CLUSTER_MAX_WAKE;
+        const long last_small = (cmax - 2 - (long)s->p.nfree) / 2;
+        long k = std::min(todo, last_small - s->steps_enqueued);
+        if (k > 0) {
+            SimDev dc = s->d;
+            dc.target_warps = s->cluster_ctas * (SIM_CLUSTER_THREADS / 32);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(s->cluster_ctas);
+            cfg.blockDim = dim3(SIM_CLUSTER_THREADS);
+            cfg.dynamicSmemBytes = s->solve_smem;
+            cfg.stream = s->ctx->stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = s->cluster_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, k_sim_persist<true, SIM_CLUSTER_THREADS>, dc, (int)k, (unsigned long long *)nullptr));
+            s->ctx->launches++;
+            s->steps_enqueued += k;
+            todo -= k;
+        }
+    }
     // small wakes: the persistent cooperative kernel, all of those steps in one launch
     if (s->coop_grid >= 4 && !getenv("LUDVM_NO_COOP")) {
         // fast mode hands over to the graph path (tiled, overlapped step) earlier than exact mode does
@@ -2114,7 +2173,7 @@ LUDVM_API int ludvm_sim_run(ludvm_sim *s, long nsteps)
             unsigned long long *bar = s->d_bar;
             void *args[] = {&dc, &ki, &bar};
             CUDA_TRY(cudaMemsetAsync(s->d_bar, 0, COOP_BAR_WORDS * sizeof(unsigned long long), s->ctx->stream));
-            CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_sim_coop, dim3(s->coop_grid), dim3(256), args, s->solve_smem, s->ctx->stream));
+            CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_sim_persist<false, 256>, dim3(s->coop_grid), dim3(256), args, s->solve_smem, s->ctx->stream));
             s->ctx->launches++;
             s->steps_enqueued += k;
             todo -= k;

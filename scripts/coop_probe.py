@@ -1,14 +1,17 @@
-"""Device time of the README-size time loop: persistent cooperative kernel vs CUDA-graph replay (LUDVM_NO_COOP=1)."""
+"""Device time of the README-size time loop: single-cluster kernel (16 / 8 CTAs), persistent cooperative grid, CUDA-graph replay."""
 import ctypes as C, json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ludvm_b200 import LUDVM, _lib
 L = _lib.load()
 README = dict(t0=0, tf=20, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012")
 GRIDS = [int(a) for a in sys.argv[1:]]   # optional: sizes of the persistent grid to try (LUDVM_COOP_GRID)
-for label, env in [("coop", None), ("graph", "1")] + [("coop%d" % g, g) for g in GRIDS]:
-    os.environ.pop("LUDVM_NO_COOP", None); os.environ.pop("LUDVM_COOP_GRID", None)
-    if env == "1": os.environ["LUDVM_NO_COOP"] = env
-    elif env: os.environ["LUDVM_COOP_GRID"] = str(env)
+VARIANTS = [("cluster16", {}), ("cluster8", {"LUDVM_CLUSTER_CTAS": "8"}), ("coop", {"LUDVM_NO_CLUSTER": "1"}),
+            ("graph", {"LUDVM_NO_CLUSTER": "1", "LUDVM_NO_COOP": "1"})] + \
+           [("coop%d" % g, {"LUDVM_NO_CLUSTER": "1", "LUDVM_COOP_GRID": str(g)}) for g in GRIDS]
+for label, env in VARIANTS:
+    for k in ("LUDVM_NO_COOP", "LUDVM_COOP_GRID", "LUDVM_NO_CLUSTER", "LUDVM_CLUSTER_CTAS"):
+        os.environ.pop(k, None)
+    os.environ.update(env)
     for mode in ("exact", "fast"):
         best = 1e9
         for rep in range(4):
