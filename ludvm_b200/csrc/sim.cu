@@ -52,7 +52,10 @@ namespace ludvm {
 #define SIM_COOP_MAX_WAKE 8192    // wakes up to this size are stepped by the persistent cooperative kernel
 #define SIM_CLUSTER_CTAS 16       // the single-cluster persistent kernel: CTAs (16 = the non-portable maximum) x threads
 #define SIM_CLUSTER_THREADS 512
-#define SIM_CLUSTER_MAX_WAKE 1024 // wakes up to this size are stepped by the single-cluster kernel (LUDVM_CLUSTER_MAX_WAKE)
+#define SIM_CLUSTER_MAX_WAKE 512  // wakes up to this size are stepped by the single-cluster kernel (LUDVM_CLUSTER_MAX_WAKE).  README
+                                  // case, us per step over the 400 steps, exact / fast: cluster up to 128: 32.2 / 26.1, 256: 31.1 / 25.3,
+                                  // 384: 30.2 / 24.8, 512: 29.6 / 24.4, all 604: 31.0 / 25.0; cooperative grid alone 33.4 / 26.9
+                                  // (profiles/r02l_coop_probe.txt): past ~500 vortices the O(N^2) phases want more than 16 SMs
 #define FINISH_STAGE 4096         // doubles of staging in the loads block of k_finish
 #define SOLVE_SMEM_LIMIT (200 * 1024)   // dynamic shared memory of the solve kernel (bytes)
 #define LUDVM_MAX_PANELS 1024     // Npoints - 1 <= this: 18 doubles per panel of the solve kernel's fixed shared memory

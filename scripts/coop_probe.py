@@ -4,12 +4,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from ludvm_b200 import LUDVM, _lib
 L = _lib.load()
 README = dict(t0=0, tf=20, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012")
-GRIDS = [int(a) for a in sys.argv[1:]]   # optional: sizes of the persistent grid to try (LUDVM_COOP_GRID)
+GRIDS = [int(a) for a in sys.argv[1:]]   # optional: persistent-grid sizes to try (LUDVM_COOP_GRID); 1000 + w = cluster path up to wake w
 VARIANTS = [("cluster16", {}), ("cluster8", {"LUDVM_CLUSTER_CTAS": "8"}), ("coop", {"LUDVM_NO_CLUSTER": "1"}),
             ("graph", {"LUDVM_NO_CLUSTER": "1", "LUDVM_NO_COOP": "1"})] + \
-           [("coop%d" % g, {"LUDVM_NO_CLUSTER": "1", "LUDVM_COOP_GRID": str(g)}) for g in GRIDS]
+           [("coop%d" % g, {"LUDVM_NO_CLUSTER": "1", "LUDVM_COOP_GRID": str(g)}) for g in GRIDS if g < 1000] + \
+           [("cluster16<=%d" % (g - 1000), {"LUDVM_CLUSTER_MAX_WAKE": str(g - 1000)}) for g in GRIDS if g >= 1000]
 for label, env in VARIANTS:
-    for k in ("LUDVM_NO_COOP", "LUDVM_COOP_GRID", "LUDVM_NO_CLUSTER", "LUDVM_CLUSTER_CTAS"):
+    for k in ("LUDVM_NO_COOP", "LUDVM_COOP_GRID", "LUDVM_NO_CLUSTER", "LUDVM_CLUSTER_CTAS", "LUDVM_CLUSTER_MAX_WAKE"):
         os.environ.pop(k, None)
     os.environ.update(env)
     for mode in ("exact", "fast"):
