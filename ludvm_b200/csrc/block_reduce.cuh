@@ -99,18 +99,31 @@ __device__ __noinline__ void block_fold(const double *__restrict__ pu, const dou
                                         double *__restrict__ out_u, double *__restrict__ out_w)
 {
     const int tid = threadIdx.x, nth = blockDim.x, lane8 = tid & 7, grp = tid >> 3, ngrp = nth >> 3;
-    const int lane = tid & 31, warp = tid >> 5, nwarps = nth >> 5;
     const int nn = exact ? 1 << nfold : nfold, ld = nn | 1;  // odd row pitch: no bank conflicts while staging
     const int per = max(1, cap / ld);
     for (int t0 = 0; t0 < 2 * nr; t0 += per) {
         const int tend = min(t0 + per, 2 * nr), nb = tend - t0;   // see the note in block_trapz
         __syncthreads();
-        for (int f = warp; f < nn; f += nwarps) {
-            const double *pfu = pu + (size_t)f * nrows, *pfw = pw + (size_t)f * nrows;
-#pragma unroll 4
-            for (int tl = lane; tl < nb; tl += 32) {
-                int t = t0 + tl, c = t >= nr, r = t - c * nr;
-                stage[tl * ld + f] = (c ? pfw : pfu)[r];
+        // every thread first issues all of its loads (up to 8 independent ones), then stores: one round trip to L2 for
+        // the whole batch (element e = f * nb + tl: consecutive threads read consecutive rows of one partial index)
+        const int total = nn * nb;
+        for (int e0 = 0; e0 < total; e0 += 8 * nth) {
+            double v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int e = e0 + k * nth + tid;
+                if (e < total) {
+                    const int f = e / nb, tl = e - f * nb, t = t0 + tl, c = t >= nr, r = t - c * nr;
+                    v[k] = (c ? pw : pu)[(size_t)f * nrows + r];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int e = e0 + k * nth + tid;
+                if (e < total) {
+                    const int f = e / nb, tl = e - f * nb;
+                    stage[tl * ld + f] = v[k];
+                }
             }
         }
         __syncthreads();
@@ -161,10 +174,13 @@ __device__ __noinline__ void block_trapz(const double *a0, int amask, int astrid
             for (int j = lane; j < n; j += 32) srow[j] = dx[j] * (a[j + 1] * b[j + 1] + a[j] * b[j]) / 2.0;
         }
         __syncthreads();
-        for (int q = grp; q < nb; q += ngrp) {
-            double v = 0.0 + sum_group(stage + q * P, 0, n);
-            if (lane8 == 0) out[q0 + q] = v;
-
+        // every group of every warp takes the same trips with the same length (a group past the end re-sums the last
+        // integrand and drops the result), so the shuffles may name the whole warp: ~70 cycles less per shuffle than
+        // the per-group masks, ~10 shuffles per sum
+        for (int qb = 0; qb < nb; qb += ngrp) {
+            const int q = qb + grp;
+            double v = 0.0 + sum_group_uniform(stage + min(q, nb - 1) * P, n);
+            if (lane8 == 0 && q < nb) out[q0 + q] = v;
         }
     }
     __syncthreads();
