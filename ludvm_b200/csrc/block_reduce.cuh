@@ -8,6 +8,13 @@
 
 namespace ludvm {
 
+#ifdef LUDVM_TRACE   // clock64 phase traces of the solve CTA (scripts/coop_trace.py); off in the shipped library
+__device__ long long g_trace[64];
+#define TRACE(k) do { if (threadIdx.x == 0 && blockIdx.x == 0) g_trace[k] = clock64(); } while (0)
+#else
+#define TRACE(k) do { } while (0)
+#endif
+
 // np.sum(a[off:off+n]) as numpy's tree, by the calling 8-lane group.
 __device__ __noinline__ double sum_group(const double *a, int off, int n)
 {
@@ -103,7 +110,9 @@ __device__ __noinline__ void block_fold(const double *__restrict__ pu, const dou
     const int per = max(1, cap / ld);
     for (int t0 = 0; t0 < 2 * nr; t0 += per) {
         const int tend = min(t0 + per, 2 * nr), nb = tend - t0;   // see the note in block_trapz
+        TRACE(30);
         __syncthreads();
+        TRACE(31);
         // every thread first issues all of its loads (up to 8 independent ones), then stores: one round trip to L2 for
         // the whole batch (element e = f * nb + tl: consecutive threads read consecutive rows of one partial index)
         const int total = nn * nb;
@@ -126,7 +135,9 @@ __device__ __noinline__ void block_fold(const double *__restrict__ pu, const dou
                 }
             }
         }
+        TRACE(32);
         __syncthreads();
+        TRACE(33);
         if (nn <= 64) {
             for (int tl = tid; tl < nb; tl += nth) {
                 double v = fold_thread(stage + tl * ld, nn, exact);
@@ -142,8 +153,10 @@ __device__ __noinline__ void block_fold(const double *__restrict__ pu, const dou
                 }
             }
         }
+        TRACE(34);
     }
     __syncthreads();
+    TRACE(35);
 }
 
 // Block-wide np.trapz of nq integrands at once:
@@ -165,7 +178,9 @@ __device__ __noinline__ void block_trapz(const double *a0, int amask, int astrid
         // function for a call site with a literal nq it folds `nq - q0` into VIADDMNMX(q0 + (-nq), rows), i.e. the
         // wrong sign, and the batch comes out empty (observed in k_finish: both load integrals stayed 0)
         const int qend = min(q0 + rows, nq), nb = qend - q0;
+        TRACE(36);
         __syncthreads();
+        TRACE(37);
         for (int q = warp; q < nb; q += nwarps) {   // one warp per integrand, lanes along the panels
             const int qq = q0 + q;
             const double *a = a0 + (qq & amask) * astride, *b = b0 + (size_t)(qq >> bshift) * bstride;
@@ -173,7 +188,9 @@ __device__ __noinline__ void block_trapz(const double *a0, int amask, int astrid
 #pragma unroll 4
             for (int j = lane; j < n; j += 32) srow[j] = dx[j] * (a[j + 1] * b[j + 1] + a[j] * b[j]) / 2.0;
         }
+        TRACE(38);
         __syncthreads();
+        TRACE(39);
         // every group of every warp takes the same trips with the same length (a group past the end re-sums the last
         // integrand and drops the result), so the shuffles may name the whole warp: ~70 cycles less per shuffle than
         // the per-group masks, ~10 shuffles per sum

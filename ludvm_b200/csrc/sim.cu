@@ -60,12 +60,6 @@ namespace ludvm {
 #define SOLVE_SMEM_LIMIT (200 * 1024)   // dynamic shared memory of the solve kernel (bytes)
 #define LUDVM_MAX_PANELS 1024     // Npoints - 1 <= this: 18 doubles per panel of the solve kernel's fixed shared memory
 
-#ifdef LUDVM_TRACE
-__device__ long long g_trace[64];
-#define TRACE(k) do { if (threadIdx.x == 0) g_trace[k] = clock64(); } while (0)
-#else
-#define TRACE(k) do { } while (0)
-#endif
 
 struct SimDev {
     int nt, P, Nc, nfree, nv, method, mode, store_history;   // store_history = k >= 1: TEV/LEV rows of steps i % k == 0 are kept
@@ -1569,8 +1563,14 @@ __device__ __noinline__ void cta_finish_update(const SimDev &S, const Step &st)
     phase_finish_update(S, st, threadIdx.x, blockDim.x, 0);
 }
 
+#ifndef SWEEP_CTAS_PER_SM
+#define SWEEP_CTAS_PER_SM 3   // resident one-CTA-per-case drivers per SM.  The driver is a chain of short phases separated by
+                              // block barriers, i.e. latency-bound, so a third resident case pays even though it caps the kernel
+                              // at 80 registers (more spills): 4096-case sweep 0.582 -> 0.564 s fast, 1.008 -> 0.896 s exact
+                              // (profiles/r02o_sweep_occupancy.txt); 4 would need 280 KB of shared memory per SM
+#endif
 template <int THREADS, int METHOD>
-__global__ void __launch_bounds__(THREADS, THREADS <= 256 ? 2 : 1) k_sim_cta(const SimDev *cases, int ncases, int *next_case, int nsteps)
+__global__ void __launch_bounds__(THREADS, THREADS <= 256 ? SWEEP_CTAS_PER_SM : 1) k_sim_cta(const SimDev *cases, int ncases, int *next_case, int nsteps)
 {
     extern __shared__ double sm[];
     __shared__ int s_case;

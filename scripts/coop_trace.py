@@ -24,3 +24,5 @@ for n, a in zip(names, acc):
     print("  %-24s %8.0f cycles  %6.2f us @1.965 GHz" % (n, a, a / 1965.0))
 sol = [tr[k] for k in range(11)]
 print("  solve sub-phases (last step, cycles from entry):", [int(sol[k] - sol[0]) for k in range(1, 11)])
+print("  inside the LAST block_fold / block_trapz call of CTA 0 (cycles between trace points 30..35 / 36..39):",
+      [int(tr[k + 1] - tr[k]) for k in range(30, 35)], [int(tr[k + 1] - tr[k]) for k in range(36, 39)])
