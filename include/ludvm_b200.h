@@ -209,6 +209,8 @@ enum {
 };
 /* Copy a result field to a host buffer of `bytes` bytes (must equal the field's size).  Synchronises. */
 int ludvm_sim_fetch(ludvm_sim *sim, int field, void *dst, size_t bytes);
+/* The same for `nfields` fields at once: all copies are enqueued, then one synchronisation. */
+int ludvm_sim_fetch_many(ludvm_sim *sim, int nfields, const int *fields, void *const *dsts, const size_t *bytes);
 int ludvm_sim_field_bytes(ludvm_sim *sim, int field, size_t *out);
 int ludvm_sim_destroy(ludvm_sim *sim);
 

@@ -371,29 +371,38 @@ class LUDVM:
         return a
 
     def _fetch_results(self, nt, P, Nc, nf, nv):
-        fz = self._fetch
-        self.circulation = {'TEV': fz('G_TEV', nv), 'LEV': fz('G_LEV', nv), 'FREE': self.circulation_freevort,
-                            'bound': fz('G_BOUND', nv), 'airfoil': fz('G_AIRFOIL', (nv, P)),
-                            'gamma_airfoil': fz('GAMMA_AIRFOIL', (nv, P)),
-                            'Gamma_airfoil': fz('GAMMA_INT_AIRFOIL', (nv, P)), 'IC': self._tables['ic']}
+        # every result field in ONE C call (one stream synchronisation instead of one per field)
+        want = [('G_TEV', nv), ('G_LEV', nv), ('G_BOUND', nv), ('G_AIRFOIL', (nv, P)), ('GAMMA_AIRFOIL', (nv, P)),
+                ('GAMMA_INT_AIRFOIL', (nv, P)), ('FOURIER', (nt, 2, Nc)), ('LESP', nt), ('LESP_PREV', nt), ('LEV_SHED', nt),
+                ('FN', nt), ('FS', nt), ('L', nt), ('D', nt), ('T', nt), ('M', nt)]
         if self.store_history:
             hrows = (nt - 1) // self.store_history + 1
-            self.path['TEV'] = fz('PATH_TEV', (hrows, 2, nv))
-            self.path['LEV'] = fz('PATH_LEV', (hrows, 2, nv))
-            self.path['FREE'] = fz('PATH_FREE', (nt, 2, nf))
-            self.history_steps = np.arange(hrows) * self.store_history   # time index of each TEV/LEV path row
+            want += [('PATH_TEV', (hrows, 2, nv)), ('PATH_LEV', (hrows, 2, nv)), ('PATH_FREE', (nt, 2, nf))]
         else:   # only the latest positions exist (the O(nt^2) history is the memory wall at dt=2e-3, tf=40)
-            self.path['TEV_last'] = fz('CUR_TEV', (2, nv))
-            self.path['LEV_last'] = fz('CUR_LEV', (2, nv))
-            self.path['FREE_last'] = fz('CUR_FREE', (2, nf))
-        self.fourier = fz('FOURIER', (nt, 2, Nc))
-        self.LESP, self.LESP_prev, self.LEV_shed = fz('LESP', nt), fz('LESP_PREV', nt), fz('LEV_SHED', nt)
-        self.Fn, self.Fs, self.L, self.D, self.T, self.M = (fz(k, nt) for k in ('FN', 'FS', 'L', 'D', 'T', 'M'))
+            want += [('CUR_TEV', (2, nv)), ('CUR_LEV', (2, nv)), ('CUR_FREE', (2, nf))]
+        got = {name: np.empty(shape) for name, shape in want}
+        got['COUNTERS'], got['RANGE_BAD'] = np.empty(4, dtype=np.int64), np.empty(1, dtype=np.int32)
+        n = len(got)
+        fields = (C.c_int * n)(*[FIELDS[k] for k in got])
+        dsts = (_lib.c_vp * n)(*[a.ctypes.data for a in got.values()])
+        sizes = (C.c_size_t * n)(*[a.nbytes for a in got.values()])
+        check(load().ludvm_sim_fetch_many(self._sim, n, fields, dsts, sizes))
+        self.circulation = {'TEV': got['G_TEV'], 'LEV': got['G_LEV'], 'FREE': self.circulation_freevort,
+                            'bound': got['G_BOUND'], 'airfoil': got['G_AIRFOIL'], 'gamma_airfoil': got['GAMMA_AIRFOIL'],
+                            'Gamma_airfoil': got['GAMMA_INT_AIRFOIL'], 'IC': self._tables['ic']}
+        if self.store_history:
+            self.path['TEV'], self.path['LEV'], self.path['FREE'] = got['PATH_TEV'], got['PATH_LEV'], got['PATH_FREE']
+            self.history_steps = np.arange(hrows) * self.store_history   # time index of each TEV/LEV path row
+        else:
+            self.path['TEV_last'], self.path['LEV_last'], self.path['FREE_last'] = got['CUR_TEV'], got['CUR_LEV'], got['CUR_FREE']
+        self.fourier = got['FOURIER']
+        self.LESP, self.LESP_prev, self.LEV_shed = got['LESP'], got['LESP_PREV'], got['LEV_SHED']
+        self.Fn, self.Fs, self.L, self.D, self.T, self.M = (got[k] for k in ('FN', 'FS', 'L', 'D', 'T', 'M'))
         self.dp = np.zeros([nt, P])                      # never assigned by the reference (LUDVM.py:1059-1064)
         self.BC = np.zeros([nv, self.Npoints])
-        cnt = self._fetch('COUNTERS', 4, np.int64)
+        cnt = got['COUNTERS']
         self.steps_done, self.itev, self.ilev = int(cnt[0]), int(cnt[1]), int(cnt[2])
-        self.range_proof_held = not bool(self._fetch('RANGE_BAD', 1, np.int32)[0])   # exact mode: flag-free arithmetic ran
+        self.range_proof_held = not bool(got['RANGE_BAD'][0])   # exact mode: flag-free arithmetic ran
         if cnt[3] != 0:
             raise _lib.LudvmError("device time loop reported error flags %d (grid barrier timed out)" % int(cnt[3]))
 
