@@ -51,7 +51,9 @@ namespace ludvm {
 #define SIM_EXACT_TILED_MIN_WAKE 8192   // exact mode, graph path: wakes at least this large use k_conv_partials_exact_tiled
 #define SIM_COOP_MAX_WAKE 8192    // wakes up to this size are stepped by the persistent cooperative kernel
 #define SIM_CLUSTER_CTAS 16       // the single-cluster persistent kernel: CTAs (16 = the non-portable maximum) x threads
-#define SIM_CLUSTER_THREADS 512
+#define SIM_CLUSTER_THREADS 256   // 512 threads halve the O(N^2) phases' rounds but cap the kernel at 128 registers and slow the
+                                  // solve by ~3 us: README case 30.4 / 25.7 us per step (exact / fast) against 28.7 / 24.0 with 256
+                                  // (profiles/r02s_coop_probe_1.txt; LUDVM_CLUSTER_THREADS=512 selects the other instantiation)
 #define SIM_CLUSTER_MAX_WAKE 512  // wakes up to this size are stepped by the single-cluster kernel (LUDVM_CLUSTER_MAX_WAKE).  README
                                   // case, us per step over the 400 steps, exact / fast: cluster up to 128: 32.2 / 26.1, 256: 31.1 / 25.3,
                                   // 384: 30.2 / 24.8, 512: 29.6 / 24.4, all 604: 31.0 / 25.0; cooperative grid alone 33.4 / 26.9
@@ -96,15 +98,6 @@ struct SimDev {
     // (by the host for the tables / vc^4, by k_case_init, the solve and the Euler update on the device) it sends every
     // later evaluation through the flagged instantiation.
     int *range_bad;
-    // What the all-pairs phases READ the wake from (wake_view): the global state arrays above (vx = wx, ..., vo1 = nv,
-    // vo2 = 2 nv; set by layout_case), or -- single-cluster kernel -- a replica of the wake in the CTA's own shared
-    // memory, which every CTA of the cluster keeps current through distributed-shared-memory stores (rep_n = cluster size,
-    // rep_x/z/g = this CTA's replica, ga_now = its copy of the step's bound-vortex strengths).  A value another SM has
-    // just written to global memory costs ~2700 cycles to read (profiles/r02p_coop_trace.txt); shared memory ~30.
-    const double *vx, *vz, *vg;
-    int vo1, vo2;
-    double *rep_x, *rep_z, *rep_g, *ga_rep;
-    int rep_n;
 };
 
 __device__ __forceinline__ bool range_safe(const SimDev &S) { return *(volatile const int *)S.range_bad == 0; }
@@ -188,9 +181,9 @@ __device__ __forceinline__ bool step_begin(const SimDev &S, int s, Step &st)
 __device__ __forceinline__ SrcView wake_view(const SimDev &S, int nT, int nL)
 {
     SrcView v;
-    v.x = S.vx; v.z = S.vz; v.g = S.vg; v.vc4 = nullptr; v.vc4s = S.vc4;
+    v.x = S.wx; v.z = S.wz; v.g = S.wg; v.vc4 = nullptr; v.vc4s = S.vc4;
     v.n0 = nT; v.n01 = nT + nL; v.n = nT + nL + S.nfree;
-    v.o1 = S.vo1; v.o2 = S.vo2; v.gstride = 1;
+    v.o1 = S.nv; v.o2 = 2 * S.nv; v.gstride = 1;
     return v;
 }
 
@@ -480,8 +473,8 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *tab, double
         tex = S.te[it * 2];
         tez = S.te[it * 2 + 1];
         if (itev > 0) {
-            pxw = S.vx[itev - 1];
-            pzw = S.vz[itev - 1];
+            pxw = S.wx[itev - 1];
+            pzw = S.wz[itev - 1];
         }
         lc0 = *S.lespcrit_cur;
     }
@@ -590,8 +583,8 @@ __device__ void phase_solve(const SimDev &S, const Step &st, double *tab, double
         // LEV placement (LUDVM.py:784-805), evaluated by every thread
         double lex = S.le[(size_t)i * 2], lez = S.le[(size_t)i * 2 + 1], xl = lex, zl = lez;
         if (ilev > 0 && S.lev_shed[i - 1] != -1.0) {
-            xl = lex + 1.0 / 3 * (S.vx[S.vo1 + ilev - 1] - lex);
-            zl = lez + 1.0 / 3 * (S.vz[S.vo1 + ilev - 1] - lez);
+            xl = lex + 1.0 / 3 * (S.wx[nv + ilev - 1] - lex);
+            zl = lez + 1.0 / 3 * (S.wz[nv + ilev - 1] - lez);
         }
         if (!ramesh) {
             // Faure 2x2 linear system (LUDVM.py:916-961); T1, T2, I1, I2 are unchanged recomputations there
@@ -737,7 +730,7 @@ __device__ __forceinline__ void phase_conv_partials(const SimDev &S, const Step 
     const double *gx = S.gp + ((size_t)st.i * 2 + 0) * P, *gz = S.gp + ((size_t)st.i * 2 + 1) * P;
     TgtGammaWake TA{gx, gz, P, W};
     TgtWake TW{W};
-    SrcView Fo = make_src(S.ga_rep ? S.ga_rep : S.g_airfoil + (size_t)st.itev * S.af_stride, 1, gx, gz, nullptr, S.vc4, P);
+    SrcView Fo = make_src(S.g_airfoil + (size_t)st.itev * S.af_stride, 1, gx, gz, nullptr, S.vc4, P);
     const int nrows = P + W.n;
     long nquadsA = (nrows + 3) >> 2, nquadsW = (W.n + 3) >> 2;
     if (S.mode == LUDVM_EXACT_F64) {
@@ -862,16 +855,11 @@ __device__ __forceinline__ void phase_finish_update(const SimDev &S, const Step 
             uf = S.foil_u[r];
             wf = S.foil_w[r];
         }
-        const int pv = W.phys((int)r);                                   // index in what the phases read (view / replica)
-        const int p = r < nT ? (int)r : (r < nT + nL ? nv + (int)r - nT : 2 * nv + (int)r - nT - nL);   // global state
-        double xn = S.vx[pv] + dt * (uw + uf);
-        double zn = S.vz[pv] + dt * (ww + wf);
+        int p = W.phys((int)r);
+        double xn = S.wx[p] + dt * (uw + uf);
+        double zn = S.wz[p] + dt * (ww + wf);
         S.wx[p] = xn;
         S.wz[p] = zn;
-        for (int c = 0; c < S.rep_n; c++) {   // keep every CTA's replica current (distributed shared memory stores)
-            const_cast<double *>(cluster_map(S.rep_x + pv, (unsigned)c))[0] = xn;
-            const_cast<double *>(cluster_map(S.rep_z + pv, (unsigned)c))[0] = zn;
-        }
         if (exact) range_note(S, xn, zn);
         if (S.store_history) {   // snapshot row i / k of the strided TEV / LEV history; the FREE history is kept in full
             double *hx, *hz;
@@ -1387,74 +1375,37 @@ __device__ __forceinline__ void persist_barrier(unsigned long long *bar, unsigne
     else grid_barrier(bar, k, counters);
 }
 
-// Shared-memory extras of the single-cluster kernel, after the solve's region: the replica of the wake (three arrays of
-// 3 * seg doubles: TEV at 0, LEV at seg, FREE at 2 seg), the step's bound-vortex strengths [P], and -- in CTA 0 -- the
-// landing area of the wake-on-foil partial sums, which the other CTAs write straight into it.
-#define CLUSTER_PA_DOUBLES(P) ((P) > 2048 ? (P) : 2048)   // >= fold x P for every split the 256-warp pool asks for
-#define CLUSTER_EXTRA_DOUBLES(P, seg) (9 * (size_t)(seg) + (size_t)(P) + 2 * (size_t)CLUSTER_PA_DOUBLES(P) + 8)
-
 template <bool CLUSTER, int NTH>
-__global__ void __launch_bounds__(NTH, 1) k_sim_persist(SimDev Sg, int nsteps, unsigned long long *bar, int seg)
+__global__ void __launch_bounds__(NTH, 1) k_sim_persist(SimDev S, int nsteps, unsigned long long *bar)
 {
     extern __shared__ double sm[];
-    __shared__ SimDev s_sim;       // cluster kernel: the descriptor with its view redirected to this CTA's replica
-    __shared__ int s_ilev;         // cluster kernel: ilev at the start of the current step (kept current by CTA 0)
     unsigned long long epoch = 0;
-    const int first = (int)Sg.counters[0] + 1;
-    const int last = min(Sg.nt - 1, first + nsteps - 1);
-    const int nb = gridDim.x, tid = threadIdx.x;
-    double *const tab = sm, *const scr = sm + TABLE_SMEM_DOUBLES(Sg.P, Sg.Nc, Sg.sinn_smem);
-    double *const ext = sm + SOLVE_SMEM_DOUBLES(Sg.P, Sg.Nc, Sg.sum_nodes, Sg.sinn_smem);
-    if (CLUSTER) {
-        {
-            const int *src = reinterpret_cast<const int *>(&Sg);
-            int *dst = reinterpret_cast<int *>(&s_sim);
-            for (int w = tid; w < (int)(sizeof(SimDev) / sizeof(int)); w += NTH) dst[w] = src[w];
-        }
-        __syncthreads();
-        double *rx = ext, *rz = rx + 3 * seg, *rg = rz + 3 * seg, *ga = rg + 3 * seg, *pau = ga + Sg.P;
-        double *paw = pau + CLUSTER_PA_DOUBLES(Sg.P);
-        if (tid == 0) {
-            s_sim.vx = rx; s_sim.vz = rz; s_sim.vg = rg; s_sim.vo1 = seg; s_sim.vo2 = 2 * seg;
-            s_sim.rep_x = rx; s_sim.rep_z = rz; s_sim.rep_g = rg; s_sim.ga_rep = ga; s_sim.rep_n = nb;
-            s_sim.pa_u = const_cast<double *>(cluster_map(pau, 0));   // partial sums of phase 1 land in CTA 0
-            s_sim.pa_w = const_cast<double *>(cluster_map(paw, 0));
-            s_sim.pre_sums = const_cast<double *>(cluster_map(paw + CLUSTER_PA_DOUBLES(Sg.P), 0));   // and the circulation sums
-            s_ilev = Sg.ilev_arr[first < Sg.nt ? first : Sg.nt - 1];
-        }
-        // the wake as it stands: every CTA fills its own replica from the global state
-        const int nT = min(seg, Sg.nv), nF = min(seg, Sg.nfree);
-        for (int k = tid; k < 2 * nT + nF; k += NTH) {
-            const int pg = k < nT ? k : (k < 2 * nT ? Sg.nv + k - nT : 2 * Sg.nv + k - 2 * nT);
-            const int pr = k < nT ? k : (k < 2 * nT ? seg + k - nT : 2 * seg + k - 2 * nT);
-            rx[pr] = Sg.wx[pg]; rz[pr] = Sg.wz[pg]; rg[pr] = Sg.wg[pg];
-        }
-    }
-    const SimDev &S = CLUSTER ? s_sim : Sg;
+    const int first = (int)S.counters[0] + 1;
+    const int last = min(S.nt - 1, first + nsteps - 1);
+    const int nb = gridDim.x;
+    double *const tab = sm, *const scr = sm + TABLE_SMEM_DOUBLES(S.P, S.Nc, S.sinn_smem);
     if (blockIdx.x <= 1) {   // the solve CTA and the loads CTA keep the constant tables in shared memory for the whole launch
-        stage_tables(Sg, StepTables(tab, Sg));
+        stage_tables(S, StepTables(tab, S));
         tables_wait();
     }
     __syncthreads();
-    if (CLUSTER) cluster_sync_all();   // every replica and descriptor is in place before anybody stores into a peer
 #ifdef LUDVM_TRACE
 #define COOP_T(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long t__ = clock64(); acc[k] += t__ - tlast; tlast = t__; } } while (0)
     long long acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tlast = clock64();
 #else
 #define COOP_T(k) do { } while (0)
 #endif
-    auto deferred_tail = [&](int ip, int ilev_ip) {
-        Step sp{ip, ip - 1, ilev_ip};
+    auto deferred_tail = [&](int ip) {
+        Step sp{ip, ip - 1, ((volatile int *)S.ilev_arr)[ip]};
         if (blockIdx.x == 1) phase_finish_loads(S, sp, tab, scr, 0, S.sum_nodes);
         else if (blockIdx.x == 2) phase_gamma_cumsum(S, sp, threadIdx.x, blockDim.x);
     };
-    int ilev_prev = 0;
     for (int i = first; i <= last; i++) {
-        Step st{i, i - 1, CLUSTER ? *(volatile int *)&s_ilev : ((volatile int *)S.ilev_arr)[i]};
+        Step st{i, i - 1, ((volatile int *)S.ilev_arr)[i]};
         // phase 1: the wake on the gamma points; the last CTA evaluates the two circulation sums instead
         if (blockIdx.x == nb - 1) {
-            double sT = block_np_sum(S.vg, st.itev, scr, S.sum_nodes);
-            double sL = block_np_sum(S.vg + S.vo1, st.ilev, scr, S.sum_nodes);
+            double sT = block_np_sum(S.wg, st.itev, scr, S.sum_nodes);
+            double sL = block_np_sum(S.wg + S.nv, st.ilev, scr, S.sum_nodes);
             if (threadIdx.x == 0) {
                 S.pre_sums[0] = sT;
                 S.pre_sums[1] = sL;
@@ -1468,35 +1419,8 @@ __global__ void __launch_bounds__(NTH, 1) k_sim_persist(SimDev Sg, int nsteps, u
         COOP_T(0);
         persist_barrier<CLUSTER>(bar, epoch, S.counters);
         COOP_T(1);
-        if (blockIdx.x == 0) {
-            phase_solve<LUDVM_METHOD_FAURE>(S, st, tab, scr, S.pre_sums, false);
-            if (CLUSTER) {
-                // what the solve decided, into every CTA's replica: the new TEV, the LEV slot (shed, or idle at the
-                // origin), the bound-vortex strengths of this step, and ilev for the next one
-                __syncthreads();
-                const SolveSmem m(scr, S.P, S.Nc);
-                const int P = S.P, nv = S.nv, per = P + 7;
-                for (int idx = tid; idx < nb * per; idx += NTH) {
-                    const unsigned c = (unsigned)(idx / per);
-                    const int k = idx - (int)c * per;
-                    if (k < P) const_cast<double *>(cluster_map(S.ga_rep + k, c))[0] = m.dG[k];
-                    else if (k == P) const_cast<double *>(cluster_map(S.rep_x + st.itev, c))[0] = S.wx[st.itev];
-                    else if (k == P + 1) const_cast<double *>(cluster_map(S.rep_z + st.itev, c))[0] = S.wz[st.itev];
-                    else if (k == P + 2) const_cast<double *>(cluster_map(S.rep_g + st.itev, c))[0] = S.wg[st.itev];
-                    else if (k == P + 3) const_cast<double *>(cluster_map(S.rep_x + seg + st.ilev, c))[0] = S.wx[nv + st.ilev];
-                    else if (k == P + 4) const_cast<double *>(cluster_map(S.rep_z + seg + st.ilev, c))[0] = S.wz[nv + st.ilev];
-                    else if (k == P + 5) const_cast<double *>(cluster_map(S.rep_g + seg + st.ilev, c))[0] = S.wg[nv + st.ilev];
-                    else {
-                        uint64_t a;
-                        asm volatile("mapa.u64 %0, %1, %2;" : "=l"(a) : "l"((uint64_t)&s_ilev), "r"(c));
-                        *reinterpret_cast<volatile int *>(a) = S.ilev_arr[i + 1];
-                    }
-                }
-            }
-        } else if (i > first) {
-            deferred_tail(i - 1, ilev_prev);
-        }
-        ilev_prev = st.ilev;
+        if (blockIdx.x == 0) phase_solve<LUDVM_METHOD_FAURE>(S, st, tab, scr, S.pre_sums, false);
+        else if (i > first) deferred_tail(i - 1);
         COOP_T(2);
         persist_barrier<CLUSTER>(bar, epoch, S.counters);
         COOP_T(3);
@@ -1509,13 +1433,12 @@ __global__ void __launch_bounds__(NTH, 1) k_sim_persist(SimDev Sg, int nsteps, u
         persist_barrier<CLUSTER>(bar, epoch, S.counters);
         COOP_T(7);
     }
-    if (last >= first) deferred_tail(last, ilev_prev);
+    if (last >= first) deferred_tail(last);
 #ifdef LUDVM_TRACE
     if (blockIdx.x == 0 && threadIdx.x == 0)
         for (int q = 0; q < 8; q++) g_trace[40 + q] = acc[q];
 #endif
     if (blockIdx.x == 0 && threadIdx.x == 0) S.counters[0] = last;
-    if (CLUSTER) cluster_sync_all();   // nobody leaves while a peer may still store into its shared memory
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1825,8 +1748,6 @@ static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t
     D.range_bad_init = (t.coords_in_window && vc4_in_safe_window(p.vc4) && !getenv("LUDVM_EXACT_FLAGS")) ? 0 : 1;
     D.range_bad = a.take<int>(1);
     D.wx = a.take<double>(nstate); D.wz = a.take<double>(nstate); D.wg = a.take<double>(nstate);
-    D.vx = D.wx; D.vz = D.wz; D.vg = D.wg; D.vo1 = (int)nv; D.vo2 = 2 * (int)nv;
-    D.rep_x = D.rep_z = D.rep_g = D.ga_rep = nullptr; D.rep_n = 0;
     D.g_bound = a.take<double>(nv);
     const size_t afrows = compact ? 1 : nv;
     D.g_airfoil = a.take<double>(afrows * P);
@@ -1891,8 +1812,7 @@ struct ludvm_sim {
     unsigned long long *d_bar = nullptr;  // grid-barrier counter of the cooperative path
     int coop_grid = 0;                    // CTAs of the cooperative kernel (0: path not available on this device)
     int cluster_ctas = 0;                 // CTAs of the single-cluster kernel (0: not available)
-    int cluster_seg = 0;                  // capacity (vortices per segment) of its shared-memory replica of the wake
-    size_t cluster_smem = 0;              // its dynamic shared memory: the solve's region + replica + landing areas
+    int cluster_threads = SIM_CLUSTER_THREADS;
     cudaStream_t cap_stream2 = nullptr;   // second capture stream: the overlapped step's old-wake convection branch
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t cap_stream = nullptr;  // private stream used only to record graphs (the context's stream may be
@@ -2183,17 +2103,16 @@ LUDVM_API int ludvm_sim_create(ludvm_ctx *ctx, const ludvm_sim_params *p, const 
             const char *ce = getenv("LUDVM_CLUSTER_CTAS");
             int want = ce ? atoi(ce) : SIM_CLUSTER_CTAS;
             want = want >= 16 ? 16 : (want >= 8 ? 8 : 4);
-            const void *kern = (const void *)k_sim_persist<true, SIM_CLUSTER_THREADS>;
-            const char *me = getenv("LUDVM_CLUSTER_MAX_WAKE");
-            s->cluster_seg = (int)std::max<long>(64, me ? atol(me) : SIM_CLUSTER_MAX_WAKE);
-            s->cluster_smem = s->solve_smem + CLUSTER_EXTRA_DOUBLES(p->P, s->cluster_seg) * sizeof(double);
-            if (s->cluster_smem <= 227 * 1024 &&
-                cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->cluster_smem) == cudaSuccess &&
+            const char *te = getenv("LUDVM_CLUSTER_THREADS");
+            s->cluster_threads = (te && atoi(te) == 512) ? 512 : SIM_CLUSTER_THREADS;
+            const void *kern = s->cluster_threads == 512 ? (const void *)k_sim_persist<true, 512>
+                                                         : (const void *)k_sim_persist<true, SIM_CLUSTER_THREADS>;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->solve_smem) == cudaSuccess &&
                 (want <= 8 || cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess)) {
                 cudaLaunchConfig_t cfg = {};
                 cfg.gridDim = dim3(want);
-                cfg.blockDim = dim3(SIM_CLUSTER_THREADS);
-                cfg.dynamicSmemBytes = s->cluster_smem;
+                cfg.blockDim = dim3(s->cluster_threads);
+                cfg.dynamicSmemBytes = s->solve_smem;
                 cudaLaunchAttribute at[1];
                 at[0].id = cudaLaunchAttributeClusterDimension;
                 at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -2228,23 +2147,26 @@ LUDVM_API int ludvm_sim_run(ludvm_sim *s, long nsteps)
     }
     // smallest wakes: ONE thread-block cluster with the hardware cluster barrier between the phases
     if (s->cluster_ctas >= 4) {
-        const long cmax = s->cluster_seg;
+        const char *me = getenv("LUDVM_CLUSTER_MAX_WAKE");
+        const long cmax = me ? atol(me) : SIM_CLUSTER_MAX_WAKE;
         const long last_small = (cmax - 2 - (long)s->p.nfree) / 2;
         long k = std::min(todo, last_small - s->steps_enqueued);
         if (k > 0) {
             SimDev dc = s->d;
-            dc.target_warps = s->cluster_ctas * (SIM_CLUSTER_THREADS / 32);
+            dc.target_warps = s->cluster_ctas * (s->cluster_threads / 32);
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(s->cluster_ctas);
-            cfg.blockDim = dim3(SIM_CLUSTER_THREADS);
-            cfg.dynamicSmemBytes = s->cluster_smem;
+            cfg.blockDim = dim3(s->cluster_threads);
+            cfg.dynamicSmemBytes = s->solve_smem;
             cfg.stream = s->ctx->stream;
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = s->cluster_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
-            CUDA_TRY(cudaLaunchKernelEx(&cfg, k_sim_persist<true, SIM_CLUSTER_THREADS>, dc, (int)k, (unsigned long long *)nullptr,
-                                        s->cluster_seg));
+            if (s->cluster_threads == 512)
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, k_sim_persist<true, 512>, dc, (int)k, (unsigned long long *)nullptr));
+            else
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, k_sim_persist<true, SIM_CLUSTER_THREADS>, dc, (int)k, (unsigned long long *)nullptr));
             s->ctx->launches++;
             s->steps_enqueued += k;
             todo -= k;
@@ -2261,8 +2183,7 @@ LUDVM_API int ludvm_sim_run(ludvm_sim *s, long nsteps)
             dc.target_warps = s->coop_grid * 8;   // one wave of warp tasks over the resident grid
             int ki = (int)k;
             unsigned long long *bar = s->d_bar;
-            int seg0 = 0;
-            void *args[] = {&dc, &ki, &bar, &seg0};
+            void *args[] = {&dc, &ki, &bar};
             CUDA_TRY(cudaMemsetAsync(s->d_bar, 0, COOP_BAR_WORDS * sizeof(unsigned long long), s->ctx->stream));
             CUDA_TRY(cudaLaunchCooperativeKernel((const void *)k_sim_persist<false, 256>, dim3(s->coop_grid), dim3(256), args, s->solve_smem, s->ctx->stream));
             s->ctx->launches++;
