@@ -68,6 +68,7 @@ struct SimDev {
     int target_warps;   // parallelism target used to pick split depths (same value in every phase of a case)
     int sum_nodes;      // doubles of shared-memory staging (block_np_sum tree nodes, block_fold / block_trapz batches)
     int sinn_smem;      // 1: the sin(n theta) table [Nc,P] is copied to shared memory at the head of the solve phase
+    int wof_single;     // 1: phase 1 leaves ONE finished sum per gamma point in pa_u / pa_w (one-CTA driver, fast mode)
     int range_bad_init; // host verdict on the tables and vc^4 (1: outside the range-proof window, or LUDVM_EXACT_FLAGS set)
     int af_stride;      // row stride of the [nv,P] bound-vortex arrays (P, or 0 in compact sweep mode)
     int fourier_rows;   // nt, or 2 in compact sweep mode (row i lives at i % fourier_rows)
@@ -132,8 +133,9 @@ __host__ __device__ __forceinline__ int sim_chunks(int n, int nrows, int target_
 // Phase 1 has only P target rows: its partials per row are capped (2^6 tree nodes / 64 chunks) so that the fold at
 // the head of the solve kernel -- the step's critical path -- stays short; 64 x P/4 warp tasks still cover every SM.
 #define SIM_WOF_MAX_DEPTH 6
-__host__ __device__ __forceinline__ int wof_fold(int mode, int n, int P, int target_warps)
+__host__ __device__ __forceinline__ int wof_fold(int mode, int n, int P, int target_warps, int single = 0)
 {
+    if (single && mode != LUDVM_EXACT_F64) return 1;
     return mode == LUDVM_EXACT_F64 ? min(sim_depth(n, P, target_warps), SIM_WOF_MAX_DEPTH)
                                    : min(sim_chunks(n, P, target_warps), 1 << SIM_WOF_MAX_DEPTH);
 }
@@ -269,7 +271,7 @@ __device__ __forceinline__ void phase_wake_on_foil(const SimDev &S, const Step &
     SrcView W = wake_view(S, nT, nL);
     TgtGamma T{S.gp + ((size_t)st.i * 2 + 0) * S.P, S.gp + ((size_t)st.i * 2 + 1) * S.P};
     long nquads = (S.P + 3) >> 2;
-    const int fold = wof_fold(S.mode, W.n, S.P, S.target_warps);
+    const int fold = wof_fold(S.mode, W.n, S.P, S.target_warps, 0);
     if (S.mode == LUDVM_EXACT_F64) {
         if (range_safe(S))
             for (long t = pl.wid; t < (nquads << fold); t += pl.nwarps)
@@ -392,8 +394,8 @@ struct SolveSmem {  // carve-up of the solve phase's scratch shared memory (afte
 // Fold the phase-1 partials into u1, w1 (block-wide; ends with a barrier).
 __device__ __forceinline__ void fold_wake_on_foil(const SimDev &S, int n1, const SolveSmem &m)
 {
-    block_fold(S.pa_u, S.pa_w, S.P, S.P, wof_fold(S.mode, n1, S.P, S.target_warps), S.mode == LUDVM_EXACT_F64, m.nodes,
-               S.sum_nodes, m.u1, m.w1);
+    block_fold(S.pa_u, S.pa_w, S.P, S.P, wof_fold(S.mode, n1, S.P, S.target_warps, S.wof_single), S.mode == LUDVM_EXACT_F64,
+               m.nodes, S.sum_nodes, m.u1, m.w1);
 }
 
 // Fourier coefficients n0 .. n0+nq-1 of the downwash into A[]: A0 = -1/pi*trapz(W/Uinf), An = 2/pi*trapz(W/Uinf*
@@ -1455,6 +1457,48 @@ __device__ __noinline__ void cta_conv_partials(const SimDev &S, const Step &st)
     phase_conv_partials(S, st, block_pool());
 }
 
+// Fast-mode phase 1 of the one-CTA driver (the wake TEV[:itev] ++ LEV[:ilev] ++ FREE on the P gamma points): the lane-group
+// tasks spend three global loads per pair on 8 warps (19 us per step alone on an SM, a fifth of the driver's step,
+// profiles/r02u_sweep_trace.txt).  Here the wake is staged once in shared memory, the block is cut into blockDim / P
+// slices of the sources, every thread of a slice owns one gamma point, and the slices' partial sums are added in slice
+// order: one finished sum per gamma point (SimDev::wof_single).  Needs P <= blockDim and 3 n + 2 P (blockDim / P) doubles.
+__device__ __noinline__ void cta_wof_tiled_fast(const SimDev &S, const Step &st, double *smt)
+{
+    const int P = S.P, tid = threadIdx.x, nth = blockDim.x;
+    SrcView W = wake_view(S, st.itev, st.ilev);
+    const int n = W.n, nslice = nth / P;
+    const double *gx = S.gp + ((size_t)st.i * 2 + 0) * P, *gz = S.gp + ((size_t)st.i * 2 + 1) * P;
+    double *sx = smt, *sz = sx + n, *sg = sz + n, *pu = sg + n, *pw = pu + nslice * P;
+    __syncthreads();
+    for (int j = tid; j < n; j += nth) {
+        const int p = W.phys(j);
+        sx[j] = S.wx[p]; sz[j] = S.wz[p]; sg[j] = S.wg[p] * LUDVM_INV_TWO_PI;
+    }
+    __syncthreads();
+    const int slice = tid / P, row = tid - slice * P;
+    if (slice < nslice) {
+        const int len = (n + nslice - 1) / nslice, j0 = slice * len, j1 = min(n, j0 + len);
+        const double xp = gx[row], zp = gz[row];
+        double u0 = 0.0, w0 = 0.0, u1 = 0.0, w1 = 0.0;
+        int j = j0;
+#pragma unroll 2
+        for (; j + 1 < j1; j += 2) {
+            pair_fast(xp, zp, sx[j], sz[j], sg[j], S.vc4, u0, w0);
+            pair_fast(xp, zp, sx[j + 1], sz[j + 1], sg[j + 1], S.vc4, u1, w1);
+        }
+        if (j < j1) pair_fast(xp, zp, sx[j], sz[j], sg[j], S.vc4, u0, w0);
+        pu[slice * P + row] = u0 + u1;
+        pw[slice * P + row] = w0 + w1;
+    }
+    __syncthreads();
+    if (tid < P) {
+        double u = 0.0, w = 0.0;
+        for (int q = 0; q < nslice; q++) { u += pu[q * P + tid]; w += pw[q * P + tid]; }
+        S.pa_u[tid] = u;
+        S.pa_w[tid] = w;
+    }
+}
+
 // Fast-mode convection of the one-CTA driver when the whole wake fits in shared memory (parameter sweeps: <= ~800
 // vortices): the lane-group tasks spend 3 loads per pair and are LSU-bound (48 % of the DFMA rate measured); here the
 // wake (x, z, Gamma/2pi) is staged once, every thread keeps R target rows in registers and the sources are broadcast
@@ -1607,7 +1651,8 @@ __global__ void __launch_bounds__(THREADS, THREADS <= 256 ? SWEEP_CTAS_PER_SM : 
             Step st{i, i - 1, S.ilev_arr[i]};
             CTA_T(5);
             if (METHOD == LUDVM_METHOD_FAURE) {
-                cta_wake_on_foil(S, st);
+                if (S.wof_single) cta_wof_tiled_fast(S, st, scr);
+                else cta_wake_on_foil(S, st);
                 __syncthreads();
             }
             CTA_T(0);
@@ -1745,6 +1790,11 @@ static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t
     D.te = t.te; D.detadx_p = t.detadx_p; D.eta_p = t.eta_p; D.x_p = t.x_p; D.theta_p = t.theta_p;
     D.dtheta = t.dtheta; D.cos_tp = t.cos_tp; D.sin_tp = t.sin_tp; D.cosn = t.cosn; D.sinn = t.sinn;
     D.free_g = t.free_g; D.free_xz = t.free_xz;
+    {   // one-CTA driver, fast mode: phase 1 from a shared-memory copy of the wake (cta_wof_tiled_fast)
+        const long nth = CTA_THREADS, nsl = P ? nth / (long)P : 0, nmax = (long)nstate + 2;
+        D.wof_single = (compact && p.mode != LUDVM_EXACT_F64 && p.method == LUDVM_METHOD_FAURE && nsl >= 1 &&
+                        3 * nmax + 2 * (long)P * nsl <= (long)SOLVE_SCRATCH_DOUBLES(P, Nc, sum_nodes) && !getenv("LUDVM_NO_WOF_TILED")) ? 1 : 0;
+    }
     D.range_bad_init = (t.coords_in_window && vc4_in_safe_window(p.vc4) && !getenv("LUDVM_EXACT_FLAGS")) ? 0 : 1;
     D.range_bad = a.take<int>(1);
     D.wx = a.take<double>(nstate); D.wz = a.take<double>(nstate); D.wg = a.take<double>(nstate);
