@@ -1616,7 +1616,7 @@ __device__ __noinline__ void cta_finish_update(const SimDev &S, const Step &st)
                               // (profiles/r02o_sweep_occupancy.txt); 4 would need 280 KB of shared memory per SM
 #endif
 template <int THREADS, int METHOD>
-__global__ void __launch_bounds__(THREADS, THREADS <= 256 ? SWEEP_CTAS_PER_SM : 1) k_sim_cta(const SimDev *cases, int ncases, int *next_case, int nsteps)
+__global__ void __launch_bounds__(THREADS, THREADS <= 128 ? 6 : (THREADS <= 256 ? SWEEP_CTAS_PER_SM : 1)) k_sim_cta(const SimDev *cases, int ncases, int *next_case, int nsteps)
 {
     extern __shared__ double sm[];
     __shared__ int s_case;
@@ -1774,13 +1774,14 @@ static int check_params(const ludvm_sim_params *p, const ludvm_sim_tables *t)
 // Fill the scalar fields and carve the per-case state out of the arena.  `compact` keeps only what a parameter
 // sweep reads back (no [nv,P] bound-vortex histories, two Fourier rows, no vortex path history).
 static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t, Arena &a, int target_warps,
-                        int sum_nodes, bool compact)
+                        int sum_nodes, bool compact, int cta_threads = CTA_THREADS)
 {
     const size_t nt = p.nt, P = p.P, Nc = p.Nc, nf = p.nfree, nv = nt - 1, nstate = 2 * nv + nf;
     D.nt = (int)nt; D.P = (int)P; D.Nc = (int)Nc; D.nfree = (int)nf; D.nv = (int)nv;
     D.method = p.method; D.mode = p.mode; D.store_history = compact ? 0 : std::max(0, p.store_history);
     D.target_warps = target_warps; D.sum_nodes = sum_nodes;
-    D.sinn_smem = Nc * P <= SINN_SMEM_MAX ? 1 : 0;
+    // (the 128-thread sweep driver reads cos/sin(n theta) from global memory: six resident cases per SM need <= 37 KB each)
+    D.sinn_smem = (Nc * P <= SINN_SMEM_MAX && !(compact && cta_threads <= 128)) ? 1 : 0;
     D.af_stride = compact ? 0 : (int)P;
     D.fourier_rows = compact ? 2 : (int)nt;
     D.dt = p.dt; D.Uinf = p.Uinf; D.chord = p.chord; D.rho = p.rho; D.piv = p.piv; D.vc4 = p.vc4; D.ic = p.ic;
@@ -1791,7 +1792,7 @@ static void layout_case(SimDev &D, const ludvm_sim_params &p, const DevTables &t
     D.dtheta = t.dtheta; D.cos_tp = t.cos_tp; D.sin_tp = t.sin_tp; D.cosn = t.cosn; D.sinn = t.sinn;
     D.free_g = t.free_g; D.free_xz = t.free_xz;
     {   // one-CTA driver, fast mode: phase 1 from a shared-memory copy of the wake (cta_wof_tiled_fast)
-        const long nth = CTA_THREADS, nsl = P ? nth / (long)P : 0, nmax = (long)nstate + 2;
+        const long nth = cta_threads, nsl = P ? nth / (long)P : 0, nmax = (long)nstate + 2;
         D.wof_single = (compact && p.mode != LUDVM_EXACT_F64 && p.method == LUDVM_METHOD_FAURE && nsl >= 1 &&
                         3 * nmax + 2 * (long)P * nsl <= (long)SOLVE_SCRATCH_DOUBLES(P, Nc, sum_nodes) && !getenv("LUDVM_NO_WOF_TILED")) ? 1 : 0;
     }
@@ -2079,6 +2080,7 @@ static int set_smem_limits(size_t solve_smem, size_t finish_smem)
         CUDA_TRY(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
         CUDA_TRY(cudaFuncSetAttribute(k_solve_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
         CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<CTA_THREADS, LUDVM_METHOD_FAURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<128, LUDVM_METHOD_FAURE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
         CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<CTA_THREADS, LUDVM_METHOD_RAMESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
         CUDA_TRY(cudaFuncSetAttribute(k_sim_cta<RAMESH_THREADS, LUDVM_METHOD_RAMESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)solve_smem));
     }
@@ -2456,7 +2458,14 @@ LUDVM_API int ludvm_sweep_run(ludvm_ctx *ctx, long ncases, const ludvm_sim_param
     std::map<const double *, DevTables> uploaded;
     std::vector<SimDev> host_cases((size_t)ncases);
     std::vector<DevTables> dts((size_t)ncases);
-    const int target = 2 * (CTA_THREADS / 32), sum_nodes = clamp_sum_nodes(p0.P, p0.Nc, std::max<long>(256, p0.Nc * p0.P));
+    const bool ramesh = p0.method == LUDVM_METHOD_RAMESH;
+    const char *te = getenv("LUDVM_SWEEP_THREADS");
+    // threads per case: 256 (three resident cases per SM) in fast mode; in exact mode 128 threads with the cos/sin(n theta)
+    // tables read from global memory put six cases on an SM and win (4096-case sweep, 256 / 128 threads: fast 0.511 / 0.537 s,
+    // exact 0.899 / 0.832 s; profiles/r02v_sweep_threads.txt).  LUDVM_SWEEP_THREADS overrides.
+    const int want_threads = te ? atoi(te) : (p0.mode == LUDVM_EXACT_F64 ? 128 : CTA_THREADS);
+    const int cta_threads = (!ramesh && want_threads == 128) ? 128 : CTA_THREADS;
+    const int target = 2 * (cta_threads / 32), sum_nodes = clamp_sum_nodes(p0.P, p0.Nc, std::max<long>(256, p0.Nc * p0.P));
     Arena measure;
     for (long c = 0; c < ncases; c++) {
         auto it = uploaded.find(tables[c].gp);
@@ -2466,14 +2475,14 @@ LUDVM_API int ludvm_sweep_run(ludvm_ctx *ctx, long ncases, const ludvm_sim_param
             it = uploaded.emplace(tables[c].gp, dt).first;
         }
         dts[c] = it->second;
-        layout_case(host_cases[c], params[c], dts[c], measure, target, sum_nodes, true);
+        layout_case(host_cases[c], params[c], dts[c], measure, target, sum_nodes, true, cta_threads);
     }
     void *base;
     TRY(dev_malloc(ctx, allocs, measure.off + 256, &base));
     CU(cudaMemsetAsync(base, 0, measure.off + 256, ctx->stream));
     Arena real;
     real.base = (char *)base;
-    for (long c = 0; c < ncases; c++) layout_case(host_cases[c], params[c], dts[c], real, target, sum_nodes, true);
+    for (long c = 0; c < ncases; c++) layout_case(host_cases[c], params[c], dts[c], real, target, sum_nodes, true, cta_threads);
     void *dcases, *dnext;
     TRY(dev_malloc(ctx, allocs, sizeof(SimDev) * (size_t)ncases + 256, &dcases));
     TRY(dev_malloc(ctx, allocs, 256, &dnext));
@@ -2484,11 +2493,12 @@ LUDVM_API int ludvm_sweep_run(ludvm_ctx *ctx, long ncases, const ludvm_sim_param
     size_t smem = solve_smem_bytes(host_cases[0]);
     TRY(set_smem_limits(smem, 0));
     int per_sm = 1;
-    const bool ramesh = p0.method == LUDVM_METHOD_RAMESH;
-    if (ramesh) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_cta<CTA_THREADS, LUDVM_METHOD_RAMESH>, CTA_THREADS, smem));
+    if (cta_threads == 128) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_cta<128, LUDVM_METHOD_FAURE>, 128, smem));
+    else if (ramesh) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_cta<CTA_THREADS, LUDVM_METHOD_RAMESH>, CTA_THREADS, smem));
     else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sim_cta<CTA_THREADS, LUDVM_METHOD_FAURE>, CTA_THREADS, smem));
     int grid = (int)std::min<long>(ncases, (long)ctx->sm_count * std::max(per_sm, 1));
-    if (ramesh) k_sim_cta<CTA_THREADS, LUDVM_METHOD_RAMESH><<<grid, CTA_THREADS, smem, ctx->stream>>>((const SimDev *)dcases, (int)ncases, (int *)dnext, (int)nt);
+    if (cta_threads == 128) k_sim_cta<128, LUDVM_METHOD_FAURE><<<grid, 128, smem, ctx->stream>>>((const SimDev *)dcases, (int)ncases, (int *)dnext, (int)nt);
+    else if (ramesh) k_sim_cta<CTA_THREADS, LUDVM_METHOD_RAMESH><<<grid, CTA_THREADS, smem, ctx->stream>>>((const SimDev *)dcases, (int)ncases, (int *)dnext, (int)nt);
     else k_sim_cta<CTA_THREADS, LUDVM_METHOD_FAURE><<<grid, CTA_THREADS, smem, ctx->stream>>>((const SimDev *)dcases, (int)ncases, (int *)dnext, (int)nt);
     ctx->launches += 2;
     CU(cudaGetLastError());
