@@ -13,6 +13,7 @@ cat $out/${tag}_coop_trace.txt
 # profiler passes last (numbers printed under ncu are never bench values)
 python bench.py --steps 2 --warmup 3 --no-extra-legs > $out/${tag}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file $out/${tag}_launches_bench.csv python bench.py --steps 2 --warmup 3 --no-extra-legs > $out/${tag}_ncu_bench.log 2>&1
+python scripts/run_configs.py --only 1,2,4 --out $out/${tag}_configs.json > $out/${tag}_configs.log 2>&1; tail -4 $out/${tag}_configs.log
 python scripts/ncu_fast_driver.py 1048576 > $out/${tag}_plain_fused.txt 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_fast_fused -s 1 -c 1 -o $out/${tag}_k_fast_fused -f python scripts/ncu_fast_driver.py 1048576 > $out/${tag}_ncu_fused.log 2>&1
 cat $out/${tag}_plain_fused.txt
