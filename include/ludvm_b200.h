@@ -79,7 +79,8 @@ int ludvm_ctx_launch_count(ludvm_ctx *ctx, long long *out);
  * with out[5] = 1: the scan's verdict (0 = every coordinate inside the window, the flag-free instantiation ran;
  * 1 = the flagged instantiation ran; reading it synchronises the context's stream), fused kernel: 1 = 12-slot pair arithmetic. */
 enum { LUDVM_K_NONE = 0, LUDVM_K_EXACT_ROWS = 1, LUDVM_K_EXACT_TILED = 2, LUDVM_K_FAST_ROWS = 3, LUDVM_K_FAST_TILED = 4,
-       LUDVM_K_FAST_TILED_TMA = 5, LUDVM_K_FAST32_TILED = 6, LUDVM_K_FAST32X2_TILED = 7, LUDVM_K_FAST_FUSED = 8 };
+       LUDVM_K_FAST_TILED_TMA = 5, LUDVM_K_FAST32_TILED = 6, LUDVM_K_FAST32X2_TILED = 7, LUDVM_K_FAST_FUSED = 8,
+       LUDVM_K_TREE = 9 /* out[2] = leaf level of the quadtree, out[5] = interpolation order */ };
 int ludvm_ctx_last_plan(ludvm_ctx *ctx, int32_t out[8]);
 
 /*
@@ -114,6 +115,26 @@ int ludvm_selfconv_step(ludvm_ctx *ctx, int mode, const double *gamma, const dou
 int ludvm_selfconv_step_p2p(ludvm_ctx *ctx, int mode, const double *gamma, const double *x, const double *z,
                             const double *vc4_per_source, double vc4, long n, long row0, long nrows, double dt,
                             int npeers, double *const *x_out_peers, double *const *z_out_peers);
+
+/*
+ * O(N log N) far field for clouds with N >> 2^20.  The reference has no counterpart: its
+ * induced_velocity (LUDVM.py:549-570) is all-pairs, and these calls approximate exactly that sum.  A kernel-independent
+ * treecode: quadtree in Morton order over the bounding square, the far field of a cell carried by (order + 1)^2 proxy
+ * vortices at its tensor Chebyshev points (barycentric Lagrange anterpolation, nested over the levels), one-cell
+ * separation lists; near field and proxies are evaluated with the LUDVM_FAST_F64 pair arithmetic.  `order` 2..24
+ * (<= 0: 18) sets the accuracy -- measured against the all-pairs sum, relative to sum |terms|: order 12 ~ 2e-11,
+ * 16 ~ 5e-14, 18 ~ 3e-15 -- and `leaf` the wanted mean number of vortices per leaf cell (<= 0: twice the proxies per
+ * cell).  Results are bitwise reproducible and do not depend on how target rows are split over GPUs.
+ * stats (host pointer, nullable) receives 8 doubles: leaf level, leaf side, pair evaluations done, np * nw, proxies per
+ * cell, device arena bytes, 0, 0; asking for it synchronises the stream.
+ */
+int ludvm_induced_velocity_tree(ludvm_ctx *ctx, const double *gamma, const double *xw, const double *zw, double vc4,
+                                long nw, const double *xp, const double *zp, long np, int order, int leaf, double *u,
+                                double *w, int ptr_kind, double *stats);
+/* ludvm_selfconv_step through the treecode (device pointers): rows [row0, row0 + nrows) of x_out / z_out are written. */
+int ludvm_selfconv_step_tree(ludvm_ctx *ctx, const double *gamma, const double *x, const double *z, double vc4, long n,
+                             long row0, long nrows, double dt, int order, int leaf, double *x_out, double *z_out,
+                             double *u_out, double *w_out, double *stats);
 
 /*
  * Flow-field grid evaluation -- replaces the velocity part of LUDVM.flowfield (LUDVM.py:1193-1220) for one

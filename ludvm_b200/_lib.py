@@ -60,6 +60,10 @@ SIGNATURES = {
                                       C.c_long, C.c_double, c_vp, c_vp, c_vp, c_vp]),
     "ludvm_selfconv_step_p2p": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_long, C.c_long,
                                           C.c_long, C.c_double, C.c_int, C.POINTER(c_vp), C.POINTER(c_vp)]),
+    "ludvm_induced_velocity_tree": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_long, c_vp, c_vp, C.c_long, C.c_int,
+                                              C.c_int, c_vp, c_vp, C.c_int, c_dp]),
+    "ludvm_selfconv_step_tree": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_long, C.c_long, C.c_long, C.c_double,
+                                           C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_dp]),
     "ludvm_flowfield_velocity": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, C.c_long, c_vp, c_vp, c_vp, C.c_long,
                                            C.c_double, c_vp, C.c_long, c_vp, C.c_long, C.c_long, C.c_long,
                                            c_vp, c_vp, C.c_int]),
@@ -144,7 +148,7 @@ class Context:
         return n.value
 
     KERNELS = ("none", "exact_rows", "exact_tiled", "fast_rows", "fast_tiled", "fast_tiled_tma", "fast32_tiled",
-               "fast32x2_tiled", "fast_fused")
+               "fast32x2_tiled", "fast_fused", "tree")
 
     def last_plan(self):
         """The all-pairs kernel the last call chose: dict(kernel, rows_per_thread, fold, tma, cluster, variant)."""

@@ -1,0 +1,691 @@
+// tree.cu -- O(N log N) far field for vortex clouds with N >> 2^20: ludvm_induced_velocity_tree,
+// ludvm_selfconv_step_tree.  The reference has no such path (LUDVM.induced_velocity, LUDVM.py:549-570, is all-pairs); the
+// checker is therefore the all-pairs oracle, and the error against it is a reported quantity, not a bit-parity claim.
+//
+// Method: a kernel-independent treecode (barycentric Lagrange interpolation at Chebyshev points, as in Wang, Krasny &
+// Tlupova's BLTC) over a complete quadtree in Morton order.  The Vatistas kernel 1 / sqrt(r^4 + vc^4) has no harmonic
+// multipole expansion -- its far field is the point vortex plus a series in (vc / r)^4 that is not small at leaf scale
+// (vc / a ~ 0.2-0.6) -- so the far field of a cell is represented by (order + 1)^2 PROXY vortices at the tensor Chebyshev
+// points of the cell, whose strengths are the anterpolated circulations
+//     qhat[k1, k2] = sum_j  l_k1(xi_j) l_k2(zeta_j) Gamma_j
+// (children's proxies are anterpolated again for the parent: the nested form).  A proxy is an ordinary vortex, so the
+// far-field evaluation is the SAME 13-slot fast pair arithmetic as the all-pairs kernels (pair_fast, common.cuh) and
+// runs on the FP64 pipe at the same rate; the only question is how many pairs are left.  Lists are the standard
+// one-cell separation: a target leaf sees its 3x3 neighbour leaves directly and, on every level l = 2 .. L, the children
+// of its parent's neighbours that are not its own neighbours (<= 27 cells), each through its proxies -- or through its
+// own vortices when it holds no more of them than proxies.  Measured error of the representation (scripts/tree_proto.py,
+// numpy model of this file): order 12 -> 2e-11, 16 -> 5e-14, 18 -> 3e-15 of sum |terms|.
+//
+// Everything runs on the context's stream; the only host round trip is the bounding box (32 bytes), which fixes the
+// tree depth.  The order of every sum is fixed (cells sorted by original index, lists walked in slot order), so results
+// are bitwise reproducible from run to run and independent of how the target rows are sharded over GPUs.
+#include "common.cuh"
+
+#include <algorithm>
+#include <cmath>
+
+namespace ludvm {
+
+#define TR_MAX_ORDER 24
+#define TR_MAX_P1 (TR_MAX_ORDER + 1)
+#define TR_MAX_LEVEL 10
+#define TR_MAX_SLOTS (9 + 36 * (TR_MAX_LEVEL - 1))
+#define TE_THREADS 128
+#define TE_TILE 128
+#define TU_THREADS 256
+#define TU_TILE 32
+#define TR_SORT_WARP_MAX 2048   // cells up to this many vortices are ordered by one warp, larger ones by a whole CTA
+
+struct TreeGeom {
+    double x0, z0, side;     // root square [x0, x0 + side) x [z0, z0 + side)
+    double inv_leaf;         // 2^L / side
+    double vc4;
+    int L, P1, P2, pad;
+    double s[TR_MAX_P1];     // Chebyshev points of the second kind on [-1, 1], exactly antisymmetric
+    double bw[TR_MAX_P1];    // barycentric weights
+};
+
+__host__ __device__ __forceinline__ unsigned spread16(unsigned v)
+{
+    v &= 0xFFFFu;
+    v = (v | (v << 8)) & 0x00FF00FFu;
+    v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+__host__ __device__ __forceinline__ unsigned compact16(unsigned v)
+{
+    v &= 0x55555555u;
+    v = (v | (v >> 1)) & 0x33333333u;
+    v = (v | (v >> 2)) & 0x0F0F0F0Fu;
+    v = (v | (v >> 4)) & 0x00FF00FFu;
+    v = (v | (v >> 8)) & 0x0000FFFFu;
+    return v;
+}
+__host__ __device__ __forceinline__ int morton2(int ix, int iz) { return (int)(spread16((unsigned)ix) | (spread16((unsigned)iz) << 1)); }
+// cells of levels 2 .. l-1 precede level l in the proxy array
+__host__ __device__ __forceinline__ long level_offset(int l) { return ((1L << (2 * l)) - 16) / 3; }
+
+// ---------------------------------------------------------------------------------------------------
+// bounding box: order-preserving map double -> uint64, atomicMin / atomicMax
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long dkey(double v)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+static double dkey_inv(unsigned long long k)
+{
+    unsigned long long b = (k >> 63) ? (k & 0x7FFFFFFFFFFFFFFFull) : ~k;
+    double v;
+    memcpy(&v, &b, 8);
+    return v;
+}
+
+// mm[0..3] = min x, max x, min z, max z over both point sets; mm[4..7] the same over set A (the sources) only
+__global__ void __launch_bounds__(256) k_tree_bbox(const double *xa, const double *za, int na, const double *xb,
+                                                   const double *zb, int nb, unsigned long long *mm)
+{
+    unsigned long long lo_x = ~0ull, hi_x = 0, lo_z = ~0ull, hi_z = 0, alo_x = ~0ull, ahi_x = 0, alo_z = ~0ull, ahi_z = 0;
+    const long tot = (long)na + nb;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long)gridDim.x * blockDim.x) {
+        const bool a = i < na;
+        const double x = a ? xa[i] : xb[i - na], z = a ? za[i] : zb[i - na];
+        if (x != x || z != z) continue;
+        const unsigned long long kx = dkey(x), kz = dkey(z);
+        lo_x = min(lo_x, kx); hi_x = max(hi_x, kx); lo_z = min(lo_z, kz); hi_z = max(hi_z, kz);
+        if (a) { alo_x = min(alo_x, kx); ahi_x = max(ahi_x, kx); alo_z = min(alo_z, kz); ahi_z = max(ahi_z, kz); }
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo_x = min(lo_x, __shfl_xor_sync(~0u, lo_x, o)); hi_x = max(hi_x, __shfl_xor_sync(~0u, hi_x, o));
+        lo_z = min(lo_z, __shfl_xor_sync(~0u, lo_z, o)); hi_z = max(hi_z, __shfl_xor_sync(~0u, hi_z, o));
+        alo_x = min(alo_x, __shfl_xor_sync(~0u, alo_x, o)); ahi_x = max(ahi_x, __shfl_xor_sync(~0u, ahi_x, o));
+        alo_z = min(alo_z, __shfl_xor_sync(~0u, alo_z, o)); ahi_z = max(ahi_z, __shfl_xor_sync(~0u, ahi_z, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mm + 0, lo_x); atomicMax(mm + 1, hi_x); atomicMin(mm + 2, lo_z); atomicMax(mm + 3, hi_z);
+        atomicMin(mm + 4, alo_x); atomicMax(mm + 5, ahi_x); atomicMin(mm + 6, alo_z); atomicMax(mm + 7, ahi_z);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Morton keys, counting sort (deterministic: cells ordered by original index)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_tree_keys(const __grid_constant__ TreeGeom G, const double *x, const double *z, int n,
+                                                   int *key, int *slot, int *cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int nc = 1 << G.L;
+    int ix = (int)((x[i] - G.x0) * G.inv_leaf), iz = (int)((z[i] - G.z0) * G.inv_leaf);
+    ix = max(0, min(nc - 1, ix));
+    iz = max(0, min(nc - 1, iz));
+    const int k = morton2(ix, iz);
+    key[i] = k;
+    slot[i] = atomicAdd(cnt + k, 1);   // any free slot of the cell; k_tree_cellsort fixes the order afterwards
+}
+
+// exclusive scan of cnt[0 .. n) into start[0 .. n]; one CTA
+__global__ void __launch_bounds__(1024) k_tree_scan(const int *cnt, int *start, int n)
+{
+    __shared__ int part[1024];
+    const int t = threadIdx.x, chunk = (n + 1023) / 1024, b = min(n, t * chunk), e = min(n, b + chunk);
+    int s = 0;
+    for (int i = b; i < e; i++) s += cnt[i];
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        int v = t >= o ? part[t - o] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    int run = part[t] - s;
+    for (int i = b; i < e; i++) {
+        start[i] = run;
+        run += cnt[i];
+    }
+    if (t == 1023) start[n] = part[1023];
+}
+
+__global__ void __launch_bounds__(256) k_tree_place(const int *key, const int *slot, const int *start, int n, int *tmp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tmp[start[key[i]] + slot[i]] = i;
+}
+
+// perm[start[c] .. start[c+1]) = the cell's original indices in ascending order (rank by counting: the entries are distinct)
+__global__ void __launch_bounds__(256) k_tree_cellsort(const int *tmp, const int *start, int ncell, int *perm)
+{
+    const int lane = threadIdx.x & 31;
+    const long gw = (long)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (long)gridDim.x * 8;
+    for (long c = gw; c < ncell; c += nw) {
+        const int b = start[c], m = start[c + 1] - b;
+        if (m == 0 || m > TR_SORT_WARP_MAX) continue;
+        for (int i = lane; i < m; i += 32) {
+            const int v = tmp[b + i];
+            int r = 0;
+            for (int j = 0; j < m; j++) r += tmp[b + j] < v;
+            perm[b + r] = v;
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_tree_cellsort_big(const int *tmp, const int *start, int ncell, int *perm)
+{
+    __shared__ int tile[1024];
+    for (long c = blockIdx.x; c < ncell; c += gridDim.x) {
+        const int b = start[c], m = start[c + 1] - b;
+        if (m <= TR_SORT_WARP_MAX) continue;
+        for (int i0 = 0; i0 < m; i0 += 256) {
+            const int i = i0 + threadIdx.x;
+            const int v = i < m ? tmp[b + i] : 0;
+            int r = 0;
+            for (int j0 = 0; j0 < m; j0 += 1024) {
+                __syncthreads();
+                for (int j = threadIdx.x; j < 1024; j += 256) tile[j] = j0 + j < m ? tmp[b + j0 + j] : 0x7FFFFFFF;
+                __syncthreads();
+                const int jn = min(1024, m - j0);
+                for (int j = 0; j < jn; j++) r += tile[j] < v;
+            }
+            if (i < m) perm[b + r] = v;
+        }
+    }
+}
+
+// sorted copies of the sources; circulations pre-scaled by 1 / (2 pi) as in every fast kernel
+__global__ void __launch_bounds__(256) k_tree_gather(const int *perm, const double *x, const double *z, const double *g, int n,
+                                                     double *xs, double *zs, double *gs)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = perm[i];
+    xs[i] = x[p];
+    zs[i] = z[p];
+    gs[i] = g[p] * LUDVM_INV_TWO_PI;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// upward pass: proxies of every cell of level l that holds more than P2 vortices
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TU_THREADS) k_tree_up(const __grid_constant__ TreeGeom G, int l, const int *startS,
+                                                        const double *xs, const double *zs, const double *gs, double *qhat)
+{
+    const int c = blockIdx.x, sh = 2 * (G.L - l), tid = threadIdx.x;
+    const int b = startS[(long)c << sh], e = startS[((long)c + 1) << sh];
+    if (e - b <= G.P2) return;
+    __shared__ double Lx[TU_TILE][TR_MAX_P1], Lz[TU_TILE][TR_MAX_P1], gt[TU_TILE];
+    __shared__ int seg_type[4], seg_a[4], seg_pre[5], nseg_s;
+    const int P1 = G.P1, P2 = G.P2;
+    const double h = ldexp(G.side, -(l + 1)), inv_h = 1.0 / h;
+    const double cx = G.x0 + (2.0 * compact16((unsigned)c) + 1.0) * h, cz = G.z0 + (2.0 * compact16((unsigned)c >> 1) + 1.0) * h;
+    if (tid == 0) {
+        int ns = 0, run = 0;
+        if (l == G.L) {
+            seg_type[0] = 0; seg_a[0] = b; seg_pre[0] = 0; run = e - b; ns = 1;
+        } else {
+            for (int ch = 0; ch < 4; ch++) {
+                const long cc = 4L * c + ch;
+                const int cb = startS[cc << (sh - 2)], ce = startS[(cc + 1) << (sh - 2)], n = ce - cb;
+                if (n == 0) continue;
+                seg_pre[ns] = run;
+                if (n > P2) { seg_type[ns] = 1 + ch; seg_a[ns] = (int)cc; run += P2; }
+                else { seg_type[ns] = 0; seg_a[ns] = cb; run += n; }
+                ns++;
+            }
+        }
+        seg_pre[ns] = run;
+        nseg_s = ns;
+    }
+    __syncthreads();
+    const int nseg = nseg_s, total = seg_pre[nseg];
+    const double *qchild = qhat + level_offset(l + 1) * P2;
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int t0 = 0; t0 < total; t0 += TU_TILE) {
+        if (tid < 2 * TU_TILE) {
+            const int tt = tid >> 1, dim = tid & 1, j = t0 + tt;
+            double *row = dim ? Lz[tt] : Lx[tt];
+            if (j < total) {
+                int sg = 0;
+                while (sg + 1 < nseg && seg_pre[sg + 1] <= j) sg++;
+                const int o = j - seg_pre[sg], ty = seg_type[sg];
+                double xi, gval;
+                if (ty == 0) {
+                    const int p = seg_a[sg] + o;
+                    xi = dim ? (zs[p] - cz) * inv_h : (xs[p] - cx) * inv_h;
+                    gval = gs[p];
+                } else {
+                    const int ch = ty - 1, k1 = o / P1, k2 = o - k1 * P1;
+                    xi = dim ? (G.s[k2] + (double)((ch >> 1) * 2 - 1)) * 0.5 : (G.s[k1] + (double)((ch & 1) * 2 - 1)) * 0.5;
+                    gval = qchild[(long)seg_a[sg] * P2 + o];
+                }
+                double sum = 0.0;
+                int hit = -1;
+                for (int k = 0; k < P1; k++) {
+                    double d = xi - G.s[k];
+                    if (d == 0.0) { hit = k; d = 1.0; }
+                    const double t = G.bw[k] / d;
+                    row[k] = t;
+                    sum += t;
+                }
+                const double inv = 1.0 / sum;
+                for (int k = 0; k < P1; k++) row[k] = hit >= 0 ? (k == hit ? 1.0 : 0.0) : row[k] * inv;
+                if (dim == 0) gt[tt] = gval;
+            } else {
+                for (int k = 0; k < P1; k++) row[k] = 0.0;
+                if (dim == 0) gt[tt] = 0.0;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int k = tid + q * TU_THREADS;
+            if (k < P2) {
+                const int k1 = k / P1, k2 = k - k1 * P1;
+                double a = acc[q];
+                for (int tt = 0; tt < TU_TILE; tt++) a = fma(Lx[tt][k1] * gt[tt], Lz[tt][k2], a);
+                acc[q] = a;
+            }
+        }
+        __syncthreads();
+    }
+    double *out = qhat + (level_offset(l) + c) * P2;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+        const int k = tid + q * TU_THREADS;
+        if (k < P2) out[k] = acc[q];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// evaluation: one CTA per target leaf
+// ---------------------------------------------------------------------------------------------------
+struct TreeEval {
+    const int *startS, *startT, *permT;
+    const double *xs, *zs, *gs, *qhat;     // sorted sources, proxies
+    const double *xt, *zt;                 // targets, original order
+    double *u, *w;                         // original order
+    unsigned long long *pairs;             // pair evaluations (diagnostic)
+};
+
+struct TreeSmem {
+    int ent_a[TR_MAX_SLOTS + 32], ent_len[TR_MAX_SLOTS + 32], ent_lvl[TR_MAX_SLOTS + 32], pre[TR_MAX_SLOTS + 33];
+    int nent;
+    double2 sxz[2][TE_TILE];
+    double sg[2][TE_TILE];
+};
+
+// source j of the CTA's flattened list -> (x, z, g / 2 pi)
+__device__ __forceinline__ void tree_fetch(const TreeGeom &G, const TreeEval &A, const TreeSmem &sm, int j, int total,
+                                           double &x, double &z, double &g)
+{
+    if (j >= total) { x = z = g = 0.0; return; }
+    int lo = 0, hi = sm.nent;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (sm.pre[mid] <= j) lo = mid;
+        else hi = mid;
+    }
+    const int o = j - sm.pre[lo], l = sm.ent_lvl[lo], a = sm.ent_a[lo];
+    if (l < 0) {
+        x = A.xs[a + o];
+        z = A.zs[a + o];
+        g = A.gs[a + o];
+    } else {
+        const int k1 = o / G.P1, k2 = o - k1 * G.P1;
+        const double h = ldexp(G.side, -(l + 1));
+        x = fma(h, G.s[k1], G.x0 + (2.0 * compact16((unsigned)a) + 1.0) * h);
+        z = fma(h, G.s[k2], G.z0 + (2.0 * compact16((unsigned)a >> 1) + 1.0) * h);
+        g = A.qhat[(level_offset(l) + a) * G.P2 + o];
+    }
+}
+
+template <int R>
+__device__ __forceinline__ void tree_eval_rows(const TreeGeom &G, const TreeEval &A, TreeSmem &sm, int tb, int te, int total)
+{
+    const int tid = threadIdx.x;
+    const double vc4 = G.vc4;
+    for (int t0 = tb; t0 < te; t0 += TE_THREADS * R) {
+        double xp[R], zp[R], au[R], aw[R];
+        int oi[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            const int t = min(t0 + tid + r * TE_THREADS, te - 1);
+            oi[r] = A.permT[t];
+            xp[r] = A.xt[oi[r]];
+            zp[r] = A.zt[oi[r]];
+            au[r] = aw[r] = 0.0;
+        }
+        const int ntiles = (total + TE_TILE - 1) / TE_TILE;
+        double nx, nz, ng;
+        tree_fetch(G, A, sm, tid, total, nx, nz, ng);
+        __syncthreads();                       // the previous pass has finished reading both buffers
+        sm.sxz[0][tid] = make_double2(nx, nz);
+        sm.sg[0][tid] = ng;
+        __syncthreads();
+        for (int k = 0; k < ntiles; k++) {
+            const int buf = k & 1;
+            if (k + 1 < ntiles) tree_fetch(G, A, sm, (k + 1) * TE_TILE + tid, total, nx, nz, ng);   // in flight during the tile
+            const int len = min(TE_TILE, total - k * TE_TILE);
+#pragma unroll 4
+            for (int j = 0; j < len; j++) {
+                const double2 s = sm.sxz[buf][j];
+                const double gj = sm.sg[buf][j];
+#pragma unroll
+                for (int r = 0; r < R; r++) pair_fast(xp[r], zp[r], s.x, s.y, gj, vc4, au[r], aw[r]);
+            }
+            if (k + 1 < ntiles) {
+                sm.sxz[buf ^ 1][tid] = make_double2(nx, nz);
+                sm.sg[buf ^ 1][tid] = ng;
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            if (t0 + tid + r * TE_THREADS < te) {
+                A.u[oi[r]] = au[r];
+                A.w[oi[r]] = aw[r];
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_constant__ TreeGeom G, const __grid_constant__ TreeEval A)
+{
+    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const int tb = A.startT[c], te = A.startT[c + 1];
+    if (tb == te) return;
+    __shared__ __align__(16) TreeSmem sm;
+    const int L = G.L, P2 = G.P2;
+    const int ix = (int)compact16((unsigned)c), iz = (int)compact16((unsigned)c >> 1);
+    const int nslots = 9 + 36 * (L - 1);
+    // every candidate cell has a fixed slot, so the list order (= the summation order) never depends on scheduling
+    for (int s = tid; s < nslots; s += TE_THREADS) {
+        int a = 0, len = 0, lvl = -1;
+        if (s < 9) {
+            const int jx = ix + s % 3 - 1, jz = iz + s / 3 - 1;
+            if (jx >= 0 && jz >= 0 && jx < (1 << L) && jz < (1 << L)) {
+                const int cc = morton2(jx, jz);
+                a = A.startS[cc];
+                len = A.startS[cc + 1] - a;
+            }
+        } else {
+            const int t = s - 9, l = 2 + t / 36, r = t % 36, pn = r >> 2, ch = r & 3;
+            const int cxl = ix >> (L - l), czl = iz >> (L - l);
+            const int qx = (cxl >> 1) + pn % 3 - 1, qz = (czl >> 1) + pn / 3 - 1;
+            if (qx >= 0 && qz >= 0 && qx < (1 << (l - 1)) && qz < (1 << (l - 1))) {
+                const int jx = 2 * qx + (ch & 1), jz = 2 * qz + (ch >> 1);
+                if (max(abs(jx - cxl), abs(jz - czl)) > 1) {
+                    const int cc = morton2(jx, jz), sh = 2 * (L - l);
+                    const int b = A.startS[(long)cc << sh], n = A.startS[((long)cc + 1) << sh] - b;
+                    if (n > P2) { a = cc; len = P2; lvl = l; }
+                    else { a = b; len = n; }
+                }
+            }
+        }
+        sm.ent_a[s] = a;
+        sm.ent_len[s] = len;
+        sm.ent_lvl[s] = lvl;
+    }
+    __syncthreads();
+    if (tid < 32) {   // drop the empty slots (order kept), then the running offsets
+        int base = 0;
+        for (int s0 = 0; s0 < nslots; s0 += 32) {
+            const int s = s0 + lane;
+            const int a = s < nslots ? sm.ent_a[s] : 0, len = s < nslots ? sm.ent_len[s] : 0, lvl = s < nslots ? sm.ent_lvl[s] : 0;
+            const unsigned m = __ballot_sync(~0u, len > 0);
+            __syncwarp();
+            if (len > 0) {
+                const int pos = base + __popc(m & ((1u << lane) - 1u));
+                sm.ent_a[pos] = a;
+                sm.ent_len[pos] = len;
+                sm.ent_lvl[pos] = lvl;
+            }
+            base += __popc(m);
+            __syncwarp();
+        }
+        const int nent = base;
+        int run = 0;
+        for (int s0 = 0; s0 < nent; s0 += 32) {
+            const int s = s0 + lane;
+            const int v = s < nent ? sm.ent_len[s] : 0;
+            int inc = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(~0u, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (s < nent) sm.pre[s] = run + inc - v;
+            run += __shfl_sync(~0u, inc, 31);
+        }
+        if (lane == 0) {
+            sm.pre[nent] = run;
+            sm.nent = nent;
+        }
+    }
+    __syncthreads();
+    const int total = sm.pre[sm.nent], cnt = te - tb;
+    if (total == 0) {
+        for (int t = tb + tid; t < te; t += TE_THREADS) {
+            A.u[A.permT[t]] = 0.0;
+            A.w[A.permT[t]] = 0.0;
+        }
+        return;
+    }
+    if (tid == 0 && A.pairs) atomicAdd(A.pairs, (unsigned long long)cnt * (unsigned long long)total);
+    if (cnt <= TE_THREADS) tree_eval_rows<1>(G, A, sm, tb, te, total);
+    else if (cnt <= 2 * TE_THREADS) tree_eval_rows<2>(G, A, sm, tb, te, total);
+    else tree_eval_rows<4>(G, A, sm, tb, te, total);
+}
+
+__global__ void __launch_bounds__(256) k_tree_euler(const double *x, const double *z, const double *u, const double *w, double dt,
+                                                    int n, double *xo, double *zo)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    xo[i] = __dadd_rn(x[i], __dmul_rn(dt, u[i]));   // forward Euler, LUDVM.py:1108-1127
+    zo[i] = __dadd_rn(z[i], __dmul_rn(dt, w[i]));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct Arena {
+    char *base;
+    size_t off = 0;
+    template <class T> T *take(size_t n)
+    {
+        T *p = base ? (T *)(base + off) : nullptr;
+        off += (n * sizeof(T) + 255) & ~(size_t)255;
+        return p;
+    }
+};
+
+struct TreeBufs {
+    int *keyS, *slotS, *keyT, *slotT, *cntS, *cntT, *startS, *startT, *tmpS, *permS, *tmpT, *permT;
+    double *xs, *zs, *gs, *qhat;
+    unsigned long long *pairs;
+};
+static size_t tree_layout(Arena &a, TreeBufs &b, long nw, long np, int L, int P2)
+{
+    const size_t ncell = (size_t)1 << (2 * L);
+    b.keyS = a.take<int>(nw); b.slotS = a.take<int>(nw); b.keyT = a.take<int>(np); b.slotT = a.take<int>(np);
+    b.cntS = a.take<int>(ncell + 1); b.cntT = a.take<int>(ncell + 1);
+    b.startS = a.take<int>(ncell + 1); b.startT = a.take<int>(ncell + 1);
+    b.tmpS = a.take<int>(nw); b.permS = a.take<int>(nw); b.tmpT = a.take<int>(np); b.permT = a.take<int>(np);
+    b.xs = a.take<double>(nw); b.zs = a.take<double>(nw); b.gs = a.take<double>(nw);
+    b.qhat = a.take<double>((size_t)level_offset(L + 1) * P2);
+    b.pairs = a.take<unsigned long long>(1);
+    return a.off;
+}
+
+// Velocities of (gamma, xw, zw)[nw] at (xp, zp)[np], device pointers.  stats (host, nullable): [0] leaf level L,
+// [1] leaf side, [2] pair evaluations, [3] np * nw, [4] proxies per cell, [5] arena bytes; reading [2] synchronises.
+static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *xw, const double *zw, double vc4, long nw,
+                                const double *xp, const double *zp, long np_, int order, int leaf, double *u, double *w,
+                                double *stats)
+{
+    if (order <= 0) order = 18;
+    if (order < 2 || order > TR_MAX_ORDER) return set_error(LUDVM_E_ARG, "tree order %d outside 2..%d", order, TR_MAX_ORDER);
+    cudaStream_t st = ctx->stream;
+    void *p;
+    int rc;
+    if ((rc = scratch_reserve(ctx, 9, 256, &p))) return rc;
+    unsigned long long *mm = (unsigned long long *)p;
+    {
+        unsigned long long init[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
+        CUDA_TRY(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
+        const int blocks = (int)std::min<long>((nw + np_ + 1023) / 1024, (long)ctx->sm_count * 8);
+        k_tree_bbox<<<blocks, 256, 0, st>>>(xw, zw, (int)nw, xp, zp, (int)np_, mm);
+        ctx->launches++;
+        unsigned long long out[8];
+        CUDA_TRY(cudaMemcpyAsync(out, mm, sizeof(out), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        for (int k = 0; k < 8; k += 2)
+            if (out[k] > out[k + 1]) return set_error(LUDVM_E_ARG, "tree: no finite coordinates");
+        TreeGeom G = {};
+        const double xlo = dkey_inv(out[0]), xhi = dkey_inv(out[1]), zlo = dkey_inv(out[2]), zhi = dkey_inv(out[3]);
+        const double sxl = dkey_inv(out[4]), sxh = dkey_inv(out[5]), szl = dkey_inv(out[6]), szh = dkey_inv(out[7]);
+        double side = std::max(xhi - xlo, zhi - zlo);
+        side = side * (1.0 + 1e-12) + 1e-300;
+        if (!(side < 1e300)) return set_error(LUDVM_E_ARG, "tree: coordinates not finite");
+        // leaf level from the wanted mean leaf population over the sources' own bounding box.  Per target a leaf costs
+        // 9 x population directly, a level 27 x proxies: the default population is two proxies' worth.
+        const int P1 = order + 1, P2 = P1 * P1;
+        const double pop = leaf > 0 ? (double)leaf : 2.0 * P2;
+        const double area = std::max((sxh - sxl) * (szh - szl), side * side * 1e-12);
+        const double a0 = std::sqrt(pop * area / (double)std::max(1L, nw));
+        int L = (int)std::lround(std::log2(std::max(side / a0, 1.0)));
+        int lcap = 2;                                    // no more than ~16 leaf cells per source vortex
+        while (lcap < TR_MAX_LEVEL && (1L << (2 * (lcap - 1))) < nw) lcap++;
+        L = std::max(2, std::min(std::min(TR_MAX_LEVEL, lcap), L));
+        if (const char *le = getenv("LUDVM_TREE_LEVEL")) L = std::max(2, std::min(TR_MAX_LEVEL, atoi(le)));
+        G.x0 = xlo; G.z0 = zlo; G.side = side; G.inv_leaf = (double)(1 << L) / side; G.vc4 = vc4;
+        G.L = L; G.P1 = P1; G.P2 = P2;
+        for (int k = 0; k < P1; k++) {
+            G.s[k] = std::sin(M_PI * (double)(order - 2 * k) / (double)(2 * order));
+            G.bw[k] = ((k & 1) ? -1.0 : 1.0) * ((k == 0 || k == order) ? 0.5 : 1.0);
+        }
+        if ((order & 1) == 0) G.s[order / 2] = 0.0;
+        for (int k = 0; k < P1 / 2; k++) G.s[order - k] = -G.s[k];
+
+        Arena sizer{nullptr};
+        TreeBufs B;
+        const size_t bytes = tree_layout(sizer, B, nw, np_, L, P2);
+        if ((rc = scratch_reserve(ctx, 8, bytes, &p))) return rc;
+        Arena ar{(char *)p};
+        tree_layout(ar, B, nw, np_, L, P2);
+        const int ncell = 1 << (2 * L);
+        CUDA_TRY(cudaMemsetAsync(B.cntS, 0, (size_t)(ncell + 1) * sizeof(int), st));
+        CUDA_TRY(cudaMemsetAsync(B.cntT, 0, (size_t)(ncell + 1) * sizeof(int), st));
+        CUDA_TRY(cudaMemsetAsync(B.pairs, 0, sizeof(unsigned long long), st));
+        const int sort_blocks = std::min(ceil_div(ncell, 8), ctx->sm_count * 16);
+        const int big_blocks = std::min(ncell, 4096);
+        k_tree_keys<<<ceil_div(nw, 256), 256, 0, st>>>(G, xw, zw, (int)nw, B.keyS, B.slotS, B.cntS);
+        k_tree_scan<<<1, 1024, 0, st>>>(B.cntS, B.startS, ncell);
+        k_tree_place<<<ceil_div(nw, 256), 256, 0, st>>>(B.keyS, B.slotS, B.startS, (int)nw, B.tmpS);
+        k_tree_cellsort<<<sort_blocks, 256, 0, st>>>(B.tmpS, B.startS, ncell, B.permS);
+        k_tree_cellsort_big<<<big_blocks, 256, 0, st>>>(B.tmpS, B.startS, ncell, B.permS);
+        k_tree_gather<<<ceil_div(nw, 256), 256, 0, st>>>(B.permS, xw, zw, g, (int)nw, B.xs, B.zs, B.gs);
+        k_tree_keys<<<ceil_div(np_, 256), 256, 0, st>>>(G, xp, zp, (int)np_, B.keyT, B.slotT, B.cntT);
+        k_tree_scan<<<1, 1024, 0, st>>>(B.cntT, B.startT, ncell);
+        k_tree_place<<<ceil_div(np_, 256), 256, 0, st>>>(B.keyT, B.slotT, B.startT, (int)np_, B.tmpT);
+        k_tree_cellsort<<<sort_blocks, 256, 0, st>>>(B.tmpT, B.startT, ncell, B.permT);
+        k_tree_cellsort_big<<<big_blocks, 256, 0, st>>>(B.tmpT, B.startT, ncell, B.permT);
+        ctx->launches += 11;
+        for (int l = L; l >= 2; l--) {
+            k_tree_up<<<1 << (2 * l), TU_THREADS, 0, st>>>(G, l, B.startS, B.xs, B.zs, B.gs, B.qhat);
+            ctx->launches++;
+        }
+        TreeEval A = {B.startS, B.startT, B.permT, B.xs, B.zs, B.gs, B.qhat, xp, zp, u, w, B.pairs};
+        k_tree_eval<<<ncell, TE_THREADS, 0, st>>>(G, A);
+        ctx->launches++;
+        CUDA_TRY(cudaGetLastError());
+        ctx->plan[0] = LUDVM_K_TREE; ctx->plan[1] = 4; ctx->plan[2] = L; ctx->plan[3] = 0; ctx->plan[4] = 1;
+        ctx->plan[5] = order; ctx->plan[6] = TE_THREADS / 32; ctx->plan[7] = 0;
+        if (stats) {
+            unsigned long long pairs = 0;
+            CUDA_TRY(cudaMemcpyAsync(&pairs, B.pairs, sizeof(pairs), cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+            stats[0] = L; stats[1] = side / (double)(1 << L); stats[2] = (double)pairs; stats[3] = (double)np_ * (double)nw;
+            stats[4] = P2; stats[5] = (double)bytes; stats[6] = stats[7] = 0.0;
+        }
+    }
+    return LUDVM_OK;
+}
+
+}  // namespace ludvm
+
+using namespace ludvm;
+
+LUDVM_API int ludvm_induced_velocity_tree(ludvm_ctx *ctx, const double *gamma, const double *xw, const double *zw, double vc4,
+                                          long nw, const double *xp, const double *zp, long np_, int order, int leaf,
+                                          double *u, double *w, int ptr_kind, double *stats)
+{
+    ARG_CHECK(ctx != nullptr);
+    ARG_CHECK(nw >= 0 && np_ >= 0 && nw < (1L << 30) && np_ < (1L << 30));
+    ARG_CHECK(ptr_kind == LUDVM_PTR_HOST || ptr_kind == LUDVM_PTR_DEVICE);
+    ARG_CHECK(vc4 >= 0.0);
+    if (np_ == 0) return LUDVM_OK;
+    ARG_CHECK(u && w && xp && zp);
+    ARG_CHECK(nw == 0 || (gamma && xw && zw));
+    DeviceGuard g(ctx->device);
+    int rc;
+    const double *dg = gamma, *dxw = xw, *dzw = zw, *dxp = xp, *dzp = zp;
+    double *du = u, *dw = w;
+    if (ptr_kind == LUDVM_PTR_HOST) {
+        const size_t total = 3 * (size_t)nw + 2 * (size_t)np_;
+        void *p;
+        if ((rc = scratch_reserve(ctx, 4, (total + 8) * sizeof(double), &p))) return rc;
+        double *b = (double *)p;
+        const double *h[5] = {gamma, xw, zw, xp, zp};
+        const double **d[5] = {&dg, &dxw, &dzw, &dxp, &dzp};
+        for (int k = 0; k < 5; k++) {
+            const size_t n = k < 3 ? (size_t)nw : (size_t)np_;
+            if (n) CUDA_TRY(cudaMemcpyAsync(b, h[k], n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            *d[k] = b;
+            b += n;
+        }
+        void *o;
+        if ((rc = scratch_reserve(ctx, 5, 2 * (size_t)np_ * sizeof(double), &o))) return rc;
+        du = (double *)o;
+        dw = du + np_;
+    }
+    if (nw == 0) {
+        CUDA_TRY(cudaMemsetAsync(du, 0, (size_t)np_ * sizeof(double), ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(dw, 0, (size_t)np_ * sizeof(double), ctx->stream));
+        if (stats) memset(stats, 0, 8 * sizeof(double));
+    } else if ((rc = tree_velocity_device(ctx, dg, dxw, dzw, vc4, nw, dxp, dzp, np_, order, leaf, du, dw, stats))) {
+        return rc;
+    }
+    if (ptr_kind == LUDVM_PTR_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(u, du, (size_t)np_ * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(w, dw, (size_t)np_ * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    return LUDVM_OK;
+}
+
+LUDVM_API int ludvm_selfconv_step_tree(ludvm_ctx *ctx, const double *gamma, const double *x, const double *z, double vc4, long n,
+                                       long row0, long nrows, double dt, int order, int leaf, double *x_out, double *z_out,
+                                       double *u_out, double *w_out, double *stats)
+{
+    ARG_CHECK(ctx != nullptr);
+    ARG_CHECK(n > 0 && n < (1L << 30) && row0 >= 0 && nrows >= 0 && row0 + nrows <= n);
+    ARG_CHECK(gamma && x && z && x_out && z_out && vc4 >= 0.0);
+    if (nrows == 0) return LUDVM_OK;
+    DeviceGuard g(ctx->device);
+    int rc;
+    double *du = u_out, *dw = w_out;
+    if (!du || !dw) {
+        void *o;
+        if ((rc = scratch_reserve(ctx, 5, 2 * (size_t)nrows * sizeof(double), &o))) return rc;
+        du = (double *)o;
+        dw = du + nrows;
+    }
+    if ((rc = tree_velocity_device(ctx, gamma, x, z, vc4, n, x + row0, z + row0, nrows, order, leaf, du, dw, stats))) return rc;
+    k_tree_euler<<<ceil_div(nrows, 256), 256, 0, ctx->stream>>>(x + row0, z + row0, du, dw, dt, (int)nrows, x_out + row0,
+                                                                z_out + row0);
+    ctx->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LUDVM_OK;
+}
