@@ -457,6 +457,64 @@ def selfconv_leg(env, args):
     return out
 
 
+def tree_leg(env, n, order, steps, warmup, rows_checked, all_pairs_ms=None):
+    """Self-convection step through the O(N log N) treecode (csrc/tree.cu): target rows sharded over the
+    ranks like the all-pairs step, every rank builds the same tree, NCCL all-gather of the positions.  The reference has
+    no treecode: parity is the error of sampled rows against the oracle's ALL-PAIRS sum, relative to sum_j |term_ij|
+    (SURVEY.md 8(d)-3), and the Euler update bitwise."""
+    from ludvm_b200 import ops
+    from ludvm_b200.sharded import ShardedSelfConvection
+    from oracle import ludvm_oracle as oracle
+    torch, world, rank, ctx = env.torch, env.world, env.rank, env.ctx
+    shard, row0 = n // world, rank * (n // world)
+    g_h, x_h, z_h = make_cloud(n)
+    g, x, z = (torch.tensor(a, device=env.dev) for a in (g_h, x_h, z_h))
+    sc = ShardedSelfConvection(g, x.clone(), z.clone(), VCORE, DT, mode="tree", ctx=ctx, transport="nccl", order=order)
+    for _ in range(warmup):
+        sc.step()
+    l0 = ctx.launch_count()
+    ms = env.time_events(sc.step, steps, 0) / steps
+    launches = ctx.launch_count() - l0
+    # parity of one step from the initial cloud: this rank's shard, sampled rows against the oracle
+    xo, zo = torch.empty_like(x), torch.empty_like(z)
+    u, w = (torch.empty(shard, dtype=torch.float64, device=env.dev) for _ in range(2))
+    st = ops.selfconv_step_tree(ctx, g, x, z, VCORE ** 4, DT, xo, zo, row0=row0, nrows=shard, u_out=u, w_out=w, order=order,
+                                return_stats=True)
+    torch.cuda.synchronize()
+    rows = np.sort(np.random.default_rng(11 + rank).choice(shard, max(1, rows_checked // world), replace=False)) + row0
+    uo, wo = oracle.induced_velocity(g_h, x_h, z_h, x_h[rows], z_h[rows], VCORE, nthreads=env.oracle_threads)
+    den = np.empty(len(rows))
+    ga = g.abs()
+    for k0 in range(0, len(rows), 8):                              # sum_j |term_ij| of the checked rows (on the device)
+        rr = torch.as_tensor(rows[k0:k0 + 8], device=env.dev)
+        dx, dz = x[rr, None] - x[None, :], z[rr, None] - z[None, :]
+        r2 = dx * dx + dz * dz
+        den[k0:k0 + 8] = ((ga[None, :] * r2.sqrt() / (r2 * r2 + VCORE ** 4).sqrt()).sum(1) / (2 * np.pi)).cpu().numpy()
+        del dx, dz, r2
+    u_h, w_h = u.cpu().numpy(), w.cpu().numpy()
+    err = float(np.max(np.hypot(u_h[rows - row0] - uo, w_h[rows - row0] - wo) / den))
+    sl = slice(row0, row0 + shard)
+    euler = bool(np.array_equal(xo[sl].cpu().numpy(), x_h[sl] + DT * u_h) and np.array_equal(zo[sl].cpu().numpy(), z_h[sl] + DT * w_h))
+    err = env.reduce(err)
+    euler = env.reduce(1.0 if euler else 0.0, "min") == 1.0
+    evals = env.reduce(st["pair_evaluations"], "sum")
+    out = {"metric": "treecode_selfconv_ms_per_step", "n_vortices": n, "order": order, "ms_per_step": ms, "steps": steps,
+           "gpu_launches": int(launches), "leaf_level": st["leaf_level"], "proxies_per_cell": st["proxies_per_cell"],
+           "pair_evaluations_per_step": evals, "pairs_left_frac": evals / (float(n) * n),
+           "eval_pairs_per_s": evals / (ms * 1e-3), "all_pairs_equivalent_pairs_per_s": float(n) * n / (ms * 1e-3),
+           "build_ms_this_rank": st["build_ms"], "eval_ms_this_rank": st["eval_ms"], "arena_bytes": st["arena_bytes"],
+           "parity": {"ok": bool(err <= 1e-12 and euler), "rows_checked": int(len(rows)) * world,
+                      "max_err_over_sum_abs_terms": err, "tolerance": 1e-12, "euler_update_bitwise": euler,
+                      "checker": "oracle all-pairs sum (the reference has no treecode)"},
+           "note": "approximates the same all-pairs sum; not the headline (value stays the all-pairs fp64 kernel)"}
+    if all_pairs_ms:
+        out["all_pairs_ms_per_step"] = all_pairs_ms
+        out["speedup_vs_all_pairs"] = all_pairs_ms / ms
+    del sc, g, x, z, xo, zo
+    torch.cuda.empty_cache()
+    return out
+
+
 def timesteps_leg(env):
     """LUDVM timesteps/s, README case (BASELINE.json configs[0]), end to end (table upload + result download)."""
     from ludvm_b200 import LUDVM
@@ -612,6 +670,8 @@ def run_ours(args):
         if not args.no_extra_legs:
             out["flowfield"] = flowfield_leg(env, 1, 1, with_e2e=False)
             out["sweep"] = sweep_leg(env, 1, 1)
+            out["tree"] = tree_leg(env, args.n, 18, 3, 2, 512, all_pairs_ms=leg["ms_per_step"])
+            out["tree"]["n_2p24"] = tree_leg(env, 1 << 24, 18, 2, 1, 128)
     elif args.workload == "flowfield":
         sampler = ClockSampler(env.local)
         sampler.start()

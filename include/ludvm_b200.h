@@ -126,7 +126,8 @@ int ludvm_selfconv_step_p2p(ludvm_ctx *ctx, int mode, const double *gamma, const
  * 16 ~ 5e-14, 18 ~ 3e-15 -- and `leaf` the wanted mean number of vortices per leaf cell (<= 0: twice the proxies per
  * cell).  Results are bitwise reproducible and do not depend on how target rows are split over GPUs.
  * stats (host pointer, nullable) receives 8 doubles: leaf level, leaf side, pair evaluations done, np * nw, proxies per
- * cell, device arena bytes, 0, 0; asking for it synchronises the stream.
+ * cell, device arena bytes, ms of tree build + upward pass, ms of the evaluation kernel; asking for it synchronises the
+ * stream.
  */
 int ludvm_induced_velocity_tree(ludvm_ctx *ctx, const double *gamma, const double *xw, const double *zw, double vc4,
                                 long nw, const double *xp, const double *zp, long np, int order, int leaf, double *u,

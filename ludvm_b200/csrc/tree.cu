@@ -340,52 +340,51 @@ __device__ __forceinline__ void tree_fetch(const TreeGeom &G, const TreeEval &A,
     }
 }
 
+// one pass: targets [t0, t1) of the sorted order, t1 - t0 <= R * TE_THREADS, against the CTA's whole list
 template <int R>
-__device__ __forceinline__ void tree_eval_rows(const TreeGeom &G, const TreeEval &A, TreeSmem &sm, int tb, int te, int total)
+__device__ __forceinline__ void tree_eval_rows(const TreeGeom &G, const TreeEval &A, TreeSmem &sm, int t0, int t1, int total)
 {
     const int tid = threadIdx.x;
     const double vc4 = G.vc4;
-    for (int t0 = tb; t0 < te; t0 += TE_THREADS * R) {
-        double xp[R], zp[R], au[R], aw[R];
-        int oi[R];
+    double xp[R], zp[R], au[R], aw[R];
+    int oi[R];
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            const int t = min(t0 + tid + r * TE_THREADS, te - 1);
-            oi[r] = A.permT[t];
-            xp[r] = A.xt[oi[r]];
-            zp[r] = A.zt[oi[r]];
-            au[r] = aw[r] = 0.0;
-        }
-        const int ntiles = (total + TE_TILE - 1) / TE_TILE;
-        double nx, nz, ng;
-        tree_fetch(G, A, sm, tid, total, nx, nz, ng);
-        __syncthreads();                       // the previous pass has finished reading both buffers
-        sm.sxz[0][tid] = make_double2(nx, nz);
-        sm.sg[0][tid] = ng;
-        __syncthreads();
-        for (int k = 0; k < ntiles; k++) {
-            const int buf = k & 1;
-            if (k + 1 < ntiles) tree_fetch(G, A, sm, (k + 1) * TE_TILE + tid, total, nx, nz, ng);   // in flight during the tile
-            const int len = min(TE_TILE, total - k * TE_TILE);
+    for (int r = 0; r < R; r++) {
+        const int t = min(t0 + tid + r * TE_THREADS, t1 - 1);
+        oi[r] = A.permT[t];
+        xp[r] = A.xt[oi[r]];
+        zp[r] = A.zt[oi[r]];
+        au[r] = aw[r] = 0.0;
+    }
+    const int ntiles = (total + TE_TILE - 1) / TE_TILE;
+    double nx, nz, ng;
+    tree_fetch(G, A, sm, tid, total, nx, nz, ng);
+    __syncthreads();                       // the previous pass has finished reading both buffers
+    sm.sxz[0][tid] = make_double2(nx, nz);
+    sm.sg[0][tid] = ng;
+    __syncthreads();
+    for (int k = 0; k < ntiles; k++) {
+        const int buf = k & 1;
+        if (k + 1 < ntiles) tree_fetch(G, A, sm, (k + 1) * TE_TILE + tid, total, nx, nz, ng);   // in flight during the tile
+        const int len = min(TE_TILE, total - k * TE_TILE);
 #pragma unroll 4
-            for (int j = 0; j < len; j++) {
-                const double2 s = sm.sxz[buf][j];
-                const double gj = sm.sg[buf][j];
+        for (int j = 0; j < len; j++) {
+            const double2 s = sm.sxz[buf][j];
+            const double gj = sm.sg[buf][j];
 #pragma unroll
-                for (int r = 0; r < R; r++) pair_fast(xp[r], zp[r], s.x, s.y, gj, vc4, au[r], aw[r]);
-            }
-            if (k + 1 < ntiles) {
-                sm.sxz[buf ^ 1][tid] = make_double2(nx, nz);
-                sm.sg[buf ^ 1][tid] = ng;
-            }
-            __syncthreads();
+            for (int r = 0; r < R; r++) pair_fast(xp[r], zp[r], s.x, s.y, gj, vc4, au[r], aw[r]);
         }
+        if (k + 1 < ntiles) {
+            sm.sxz[buf ^ 1][tid] = make_double2(nx, nz);
+            sm.sg[buf ^ 1][tid] = ng;
+        }
+        __syncthreads();
+    }
 #pragma unroll
-        for (int r = 0; r < R; r++) {
-            if (t0 + tid + r * TE_THREADS < te) {
-                A.u[oi[r]] = au[r];
-                A.w[oi[r]] = aw[r];
-            }
+    for (int r = 0; r < R; r++) {
+        if (t0 + tid + r * TE_THREADS < t1) {
+            A.u[oi[r]] = au[r];
+            A.w[oi[r]] = aw[r];
         }
     }
 }
@@ -395,6 +394,10 @@ __global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_consta
     const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const int tb = A.startT[c], te = A.startT[c + 1];
     if (tb == te) return;
+    // The leaf's targets are cut into row units of TE_THREADS, and the units into passes of <= 4 (rows per thread) as
+    // evenly as possible; passes are spread over blockIdx.y so that a leaf is several work items (wave quantisation).
+    const int units = (te - tb + TE_THREADS - 1) / TE_THREADS, npass = (units + 3) >> 2;
+    if ((int)blockIdx.y >= npass) return;
     __shared__ __align__(16) TreeSmem sm;
     const int L = G.L, P2 = G.P2;
     const int ix = (int)compact16((unsigned)c), iz = (int)compact16((unsigned)c >> 1);
@@ -471,10 +474,16 @@ __global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_consta
         }
         return;
     }
-    if (tid == 0 && A.pairs) atomicAdd(A.pairs, (unsigned long long)cnt * (unsigned long long)total);
-    if (cnt <= TE_THREADS) tree_eval_rows<1>(G, A, sm, tb, te, total);
-    else if (cnt <= 2 * TE_THREADS) tree_eval_rows<2>(G, A, sm, tb, te, total);
-    else tree_eval_rows<4>(G, A, sm, tb, te, total);
+    if (tid == 0 && blockIdx.y == 0 && A.pairs) atomicAdd(A.pairs, (unsigned long long)cnt * (unsigned long long)total);
+    const int base = units / npass, extra = units - base * npass;
+    for (int pass = blockIdx.y; pass < npass; pass += gridDim.y) {
+        const int R = base + (pass < extra ? 1 : 0);
+        const int t0 = tb + (pass * base + min(pass, extra)) * TE_THREADS, t1 = min(te, t0 + R * TE_THREADS);
+        if (R == 1) tree_eval_rows<1>(G, A, sm, t0, t1, total);
+        else if (R == 2) tree_eval_rows<2>(G, A, sm, t0, t1, total);
+        else if (R == 3) tree_eval_rows<3>(G, A, sm, t0, t1, total);
+        else tree_eval_rows<4>(G, A, sm, t0, t1, total);
+    }
 }
 
 __global__ void __launch_bounds__(256) k_tree_euler(const double *x, const double *z, const double *u, const double *w, double dt,
@@ -580,6 +589,11 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
         CUDA_TRY(cudaMemsetAsync(B.pairs, 0, sizeof(unsigned long long), st));
         const int sort_blocks = std::min(ceil_div(ncell, 8), ctx->sm_count * 16);
         const int big_blocks = std::min(ncell, 4096);
+        cudaEvent_t ev0 = nullptr;
+        if (stats) {
+            CUDA_TRY(cudaEventCreate(&ev0));
+            CUDA_TRY(cudaEventRecord(ev0, st));
+        }
         k_tree_keys<<<ceil_div(nw, 256), 256, 0, st>>>(G, xw, zw, (int)nw, B.keyS, B.slotS, B.cntS);
         k_tree_scan<<<1, 1024, 0, st>>>(B.cntS, B.startS, ncell);
         k_tree_place<<<ceil_div(nw, 256), 256, 0, st>>>(B.keyS, B.slotS, B.startS, (int)nw, B.tmpS);
@@ -597,8 +611,16 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
             ctx->launches++;
         }
         TreeEval A = {B.startS, B.startT, B.permT, B.xs, B.zs, B.gs, B.qhat, xp, zp, u, w, B.pairs};
-        k_tree_eval<<<ncell, TE_THREADS, 0, st>>>(G, A);
+        cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+        if (stats) {
+            for (int k = 1; k < 3; k++) CUDA_TRY(cudaEventCreate(&ev[k]));
+            CUDA_TRY(cudaEventRecord(ev[1], st));
+        }
+        int ysplit = 4;
+        if (const char *ye = getenv("LUDVM_TREE_YSPLIT")) ysplit = std::max(1, std::min(64, atoi(ye)));
+        k_tree_eval<<<dim3(ncell, ysplit), TE_THREADS, 0, st>>>(G, A);
         ctx->launches++;
+        if (stats) CUDA_TRY(cudaEventRecord(ev[2], st));
         CUDA_TRY(cudaGetLastError());
         ctx->plan[0] = LUDVM_K_TREE; ctx->plan[1] = 4; ctx->plan[2] = L; ctx->plan[3] = 0; ctx->plan[4] = 1;
         ctx->plan[5] = order; ctx->plan[6] = TE_THREADS / 32; ctx->plan[7] = 0;
@@ -607,7 +629,13 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
             CUDA_TRY(cudaMemcpyAsync(&pairs, B.pairs, sizeof(pairs), cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
             stats[0] = L; stats[1] = side / (double)(1 << L); stats[2] = (double)pairs; stats[3] = (double)np_ * (double)nw;
-            stats[4] = P2; stats[5] = (double)bytes; stats[6] = stats[7] = 0.0;
+            stats[4] = P2; stats[5] = (double)bytes;
+            float ms_build = 0.f, ms_eval = 0.f;
+            cudaEventElapsedTime(&ms_build, ev0, ev[1]);
+            cudaEventElapsedTime(&ms_eval, ev[1], ev[2]);
+            stats[6] = ms_build; stats[7] = ms_eval;
+            cudaEventDestroy(ev0);
+            for (auto &e : ev) if (e) cudaEventDestroy(e);
         }
     }
     return LUDVM_OK;

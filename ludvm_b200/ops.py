@@ -54,7 +54,7 @@ def induced_velocity_tree(circulation, xw, zw, xp, zp, v_core, order=18, leaf=0,
 
 def _tree_stats(s):
     return dict(leaf_level=int(s[0]), leaf_side=s[1], pair_evaluations=s[2], all_pairs=s[3], proxies_per_cell=int(s[4]),
-                arena_bytes=int(s[5]))
+                arena_bytes=int(s[5]), build_ms=s[6], eval_ms=s[7])
 
 
 def induced_velocity_tree_device(ctx, g, xw, zw, xp, zp, vc4, u, w, order=18, leaf=0, return_stats=False):

@@ -45,8 +45,13 @@ def grid_slab(nx, world, rank):
 
 
 class ShardedSelfConvection:
-    def __init__(self, g, x, z, v_core, dt, mode="fast", ctx=None, group=None, kernel=None, transport="auto"):
+    def __init__(self, g, x, z, v_core, dt, mode="fast", ctx=None, group=None, kernel=None, transport="auto", order=18,
+                 leaf=0):
+        """mode: "exact" | "fast" | "fp32" | "fast12" (all-pairs) or "tree" (O(N log N) treecode of csrc/tree.cu with
+        interpolation order `order`: every rank builds the same tree over all sources and evaluates its own target
+        rows; positions are exchanged with NCCL all_gather)."""
         self.group = group
+        self.order, self.leaf = int(order), int(leaf)
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.g = g
@@ -69,8 +74,10 @@ class ShardedSelfConvection:
         self._hdl = None
         if self.world > 1:
             want = transport
+            if mode == "tree" and want == "p2p":
+                raise ValueError("ShardedSelfConvection: the treecode step has no fused peer-store epilogue; use transport='nccl'")
             if want == "auto":
-                want = "p2p" if (kernel is None and x.is_cuda) else "nccl"
+                want = "p2p" if (kernel is None and x.is_cuda and mode != "tree") else "nccl"
             if want == "p2p":
                 try:
                     self._init_p2p(x, z)
@@ -117,6 +124,10 @@ class ShardedSelfConvection:
 
     # -- nccl / single-rank ----------------------------------------------------------------------------------
     def _cuda_kernel(self, g, x, z, vc4, dt, row0, nrows, x_out, z_out):
+        if self.mode == "tree":
+            ops.selfconv_step_tree(self.ctx, g, x, z, vc4, dt, x_out, z_out, row0=row0, nrows=nrows, order=self.order,
+                                   leaf=self.leaf)
+            return
         ops.selfconv_step(self.ctx, self.mode, g, x, z, vc4, dt, x_out, z_out, row0=row0, nrows=nrows)
 
     def step(self):

@@ -16,7 +16,7 @@ ctx = _lib.Context(local, torch.cuda.current_stream().cuda_stream)
 rng = np.random.default_rng(20260101)
 ok = True
 for n, mode, steps, transport in ((65536, "fast", 3, "p2p"), (65536, "fast", 3, "nccl"), (16384, "exact", 2, "p2p"),
-                                  (65536, "fp32", 2, "nccl")):
+                                  (65536, "fp32", 2, "nccl"), (131072, "tree", 2, "nccl")):
     x_h, z_h, g_h = rng.uniform(-20, 0, n), rng.uniform(-4, 4, n), rng.standard_normal(n) * 1e-2
     g, x, z = (torch.tensor(a, device=dev) for a in (g_h, x_h, z_h))
     sc = ShardedSelfConvection(g, x.clone(), z.clone(), 0.065, 0.05, mode=mode, ctx=ctx,
@@ -27,7 +27,10 @@ for n, mode, steps, transport in ((65536, "fast", 3, "p2p"), (65536, "fast", 3, 
     xa, za = x.clone(), z.clone()
     xb, zb = torch.empty_like(x), torch.empty_like(z)
     for _ in range(steps):
-        ops.selfconv_step(ctx, mode, g, xa, za, 0.065 ** 4, 0.05, xb, zb)
+        if mode == "tree":
+            ops.selfconv_step_tree(ctx, g, xa, za, 0.065 ** 4, 0.05, xb, zb, order=18)
+        else:
+            ops.selfconv_step(ctx, mode, g, xa, za, 0.065 ** 4, 0.05, xb, zb)
         xa, xb = xb, xa
         za, zb = zb, za
     torch.cuda.synchronize()

@@ -45,4 +45,4 @@ for lg in [int(a) for a in sys.argv[1:]] or [20]:
             print(json.dumps(dict(n=n, order=order, leaf=leaf, ms=best * 1e3, all_pairs_ms=t_all and t_all * 1e3,
                                   speedup=t_all and t_all / best, pairs_left=st["pair_evaluations"] / st["all_pairs"],
                                   eval_pairs_per_s=st["pair_evaluations"] / best, equivalent_pairs_per_s=float(n) * n / best,
-                                  max_err_over_sum_abs_terms=err, level=st["leaf_level"], arena_mb=st["arena_bytes"] / 2 ** 20)), flush=True)
+                                  max_err_over_sum_abs_terms=err, level=st["leaf_level"], build_ms=st["build_ms"], eval_ms=st["eval_ms"], arena_mb=st["arena_bytes"] / 2 ** 20)), flush=True)

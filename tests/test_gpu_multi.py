@@ -36,11 +36,11 @@ def ngpus():
 
 
 def test_sharded_self_convection_bitwise_equal_to_one_rank(ngpus):
-    """scripts/dist_parity.py: G-rank self-convection (fused peer-store all-gather, NCCL all-gather; fast, exact and fp32
-    modes) equals the single-rank evaluation of the same steps bit for bit on every rank."""
+    """scripts/dist_parity.py: G-rank self-convection (fused peer-store all-gather, NCCL all-gather; fast, exact, fp32
+    and treecode modes) equals the single-rank evaluation of the same steps bit for bit on every rank."""
     r = _torchrun(ngpus, ["scripts/dist_parity.py"])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert r.stdout.count("bitwise_equal_to_single_rank=True") == 4 * ngpus, r.stdout
+    assert r.stdout.count("bitwise_equal_to_single_rank=True") == 5 * ngpus, r.stdout
 
 
 def test_bench_line_parity_on_several_gpus(ngpus):
@@ -53,3 +53,4 @@ def test_bench_line_parity_on_several_gpus(ngpus):
     assert line["parity"]["ok"] and line["parity"]["sharded_2steps_n131072_equals_unsharded_bitwise"] is True, line["parity"]
     assert line["flowfield"]["parity"]["ok"] and line["sweep"]["parity"]["ok"], (line["flowfield"]["parity"], line["sweep"]["parity"])
     assert line["config"]["transport"] in ("p2p", "nccl") and line["gpu_launches"] >= 1
+    assert line["tree"]["parity"]["ok"] and line["tree"]["n_2p24"]["parity"]["ok"], line["tree"]
