@@ -13,7 +13,9 @@
 // runs on the FP64 pipe at the same rate; the only question is how many pairs are left.  Lists are the standard
 // one-cell separation: a target leaf sees its 3x3 neighbour leaves directly and, on every level l = 2 .. L, the children
 // of its parent's neighbours that are not its own neighbours (<= 27 cells), each through its proxies -- or through its
-// own vortices when it holds no more of them than proxies.  Measured error of the representation (scripts/tree_proto.py,
+// own vortices when it holds no more of them than proxies.  On top of that, cells with more than P2 vortices carry a local
+// field at their own Chebyshev points (M2L / L2L / L2P, see "evaluation" below), so that a far list acts on P2 points per
+// cell instead of on every target: the black-box FMM of Fong & Darve with this file's proxies.  Measured error of the representation (scripts/tree_proto.py,
 // numpy model of this file): order 12 -> 2e-11, 16 -> 5e-14, 18 -> 3e-15 of sum |terms|.
 //
 // Everything runs on the context's stream; the only host round trip is the bounding box (32 bytes), which fixes the
@@ -298,14 +300,22 @@ __global__ void __launch_bounds__(TU_THREADS) k_tree_up(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// evaluation: one CTA per target leaf
+// evaluation.  A cell with more than P2 source vortices also carries a LOCAL field: the velocity induced by everything
+// outside its neighbourhood, sampled at its own P2 Chebyshev points (M2L: the far list of the cell's level acting on the
+// points, the same pair arithmetic; L2L: the parent's local field interpolated to the child's points).  A target then
+// takes (a) the local field of its deepest ancestor that has one, interpolated at the target (L2P), (b) the far lists of
+// the levels below that ancestor evaluated directly, and (c) the 3x3 neighbour leaves directly.  Which cells carry a local
+// field depends on the SOURCES only, so a target's sum does not depend on which other targets a rank was given.
+// One launch holds the M2L items of every level (they depend on the upward pass only) and the leaf items.
 // ---------------------------------------------------------------------------------------------------
 struct TreeEval {
-    const int *startS, *startT, *permT;
+    const int *startS, *startT, *permT, *keyT;
     const double *xs, *zs, *gs, *qhat;     // sorted sources, proxies
     const double *xt, *zt;                 // targets, original order
     double *u, *w;                         // original order
+    double *uloc, *wloc;                   // local fields, laid out like qhat
     unsigned long long *pairs;             // pair evaluations (diagnostic)
+    int fmm, np;                           // 0: pure treecode (every far list evaluated at the targets)
 };
 
 struct TreeSmem {
@@ -313,6 +323,43 @@ struct TreeSmem {
     int nent;
     double2 sxz[2][TE_TILE];
     double sg[2][TE_TILE];
+};
+
+// targets of a leaf item: the leaf's points (sorted order t -> original index)
+struct TgtLeafPts {
+    const int *permT;
+    const double *xt, *zt;
+    double *u, *w;
+    __device__ __forceinline__ void load(int t, double &x, double &z) const
+    {
+        const int oi = permT[t];
+        x = xt[oi];
+        z = zt[oi];
+    }
+    __device__ __forceinline__ void store(int t, double uu, double ww) const
+    {
+        const int oi = permT[t];
+        u[oi] = uu;
+        w[oi] = ww;
+    }
+};
+// targets of an M2L item: the cell's own Chebyshev points
+struct TgtNodePts {
+    double cx, cz, h;
+    const double *s;
+    int P1;
+    double *u, *w;
+    __device__ __forceinline__ void load(int k, double &x, double &z) const
+    {
+        const int k1 = k / P1, k2 = k - k1 * P1;
+        x = fma(h, s[k1], cx);
+        z = fma(h, s[k2], cz);
+    }
+    __device__ __forceinline__ void store(int k, double uu, double ww) const
+    {
+        u[k] = uu;
+        w[k] = ww;
+    }
 };
 
 // source j of the CTA's flattened list -> (x, z, g / 2 pi)
@@ -340,89 +387,36 @@ __device__ __forceinline__ void tree_fetch(const TreeGeom &G, const TreeEval &A,
     }
 }
 
-// one pass: targets [t0, t1) of the sorted order, t1 - t0 <= R * TE_THREADS, against the CTA's whole list
-template <int R>
-__device__ __forceinline__ void tree_eval_rows(const TreeGeom &G, const TreeEval &A, TreeSmem &sm, int t0, int t1, int total)
+// Interaction list of cell (cx, cz) of level lc into shared memory: the 3x3 neighbours (near; lc == L) and the far cells
+// of levels lmin .. lmax <= lc (a coarser level's list is the ancestor's).  Every candidate has a fixed slot, so the list
+// order (= the summation order) never depends on scheduling; empty slots are dropped afterwards, order kept.
+__device__ __forceinline__ int tree_build_list(const TreeGeom &G, const TreeEval &A, int cx, int cz, int lc, bool near, int lmin,
+                                               int lmax, TreeSmem &sm)
 {
-    const int tid = threadIdx.x;
-    const double vc4 = G.vc4;
-    double xp[R], zp[R], au[R], aw[R];
-    int oi[R];
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        const int t = min(t0 + tid + r * TE_THREADS, t1 - 1);
-        oi[r] = A.permT[t];
-        xp[r] = A.xt[oi[r]];
-        zp[r] = A.zt[oi[r]];
-        au[r] = aw[r] = 0.0;
-    }
-    const int ntiles = (total + TE_TILE - 1) / TE_TILE;
-    double nx, nz, ng;
-    tree_fetch(G, A, sm, tid, total, nx, nz, ng);
-    __syncthreads();                       // the previous pass has finished reading both buffers
-    sm.sxz[0][tid] = make_double2(nx, nz);
-    sm.sg[0][tid] = ng;
-    __syncthreads();
-    for (int k = 0; k < ntiles; k++) {
-        const int buf = k & 1;
-        if (k + 1 < ntiles) tree_fetch(G, A, sm, (k + 1) * TE_TILE + tid, total, nx, nz, ng);   // in flight during the tile
-        const int len = min(TE_TILE, total - k * TE_TILE);
-#pragma unroll 4
-        for (int j = 0; j < len; j++) {
-            const double2 s = sm.sxz[buf][j];
-            const double gj = sm.sg[buf][j];
-#pragma unroll
-            for (int r = 0; r < R; r++) pair_fast(xp[r], zp[r], s.x, s.y, gj, vc4, au[r], aw[r]);
-        }
-        if (k + 1 < ntiles) {
-            sm.sxz[buf ^ 1][tid] = make_double2(nx, nz);
-            sm.sg[buf ^ 1][tid] = ng;
-        }
-        __syncthreads();
-    }
-#pragma unroll
-    for (int r = 0; r < R; r++) {
-        if (t0 + tid + r * TE_THREADS < t1) {
-            A.u[oi[r]] = au[r];
-            A.w[oi[r]] = aw[r];
-        }
-    }
-}
-
-__global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_constant__ TreeGeom G, const __grid_constant__ TreeEval A)
-{
-    const int c = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    const int tb = A.startT[c], te = A.startT[c + 1];
-    if (tb == te) return;
-    // The leaf's targets are cut into row units of TE_THREADS, and the units into passes of <= 4 (rows per thread) as
-    // evenly as possible; passes are spread over blockIdx.y so that a leaf is several work items (wave quantisation).
-    const int units = (te - tb + TE_THREADS - 1) / TE_THREADS, npass = (units + 3) >> 2;
-    if ((int)blockIdx.y >= npass) return;
-    __shared__ __align__(16) TreeSmem sm;
-    const int L = G.L, P2 = G.P2;
-    const int ix = (int)compact16((unsigned)c), iz = (int)compact16((unsigned)c >> 1);
+    const int tid = threadIdx.x, lane = tid & 31, L = G.L, P2 = G.P2;
     const int nslots = 9 + 36 * (L - 1);
-    // every candidate cell has a fixed slot, so the list order (= the summation order) never depends on scheduling
     for (int s = tid; s < nslots; s += TE_THREADS) {
         int a = 0, len = 0, lvl = -1;
         if (s < 9) {
-            const int jx = ix + s % 3 - 1, jz = iz + s / 3 - 1;
-            if (jx >= 0 && jz >= 0 && jx < (1 << L) && jz < (1 << L)) {
+            const int jx = cx + s % 3 - 1, jz = cz + s / 3 - 1;
+            if (near && jx >= 0 && jz >= 0 && jx < (1 << L) && jz < (1 << L)) {
                 const int cc = morton2(jx, jz);
                 a = A.startS[cc];
                 len = A.startS[cc + 1] - a;
             }
         } else {
             const int t = s - 9, l = 2 + t / 36, r = t % 36, pn = r >> 2, ch = r & 3;
-            const int cxl = ix >> (L - l), czl = iz >> (L - l);
-            const int qx = (cxl >> 1) + pn % 3 - 1, qz = (czl >> 1) + pn / 3 - 1;
-            if (qx >= 0 && qz >= 0 && qx < (1 << (l - 1)) && qz < (1 << (l - 1))) {
-                const int jx = 2 * qx + (ch & 1), jz = 2 * qz + (ch >> 1);
-                if (max(abs(jx - cxl), abs(jz - czl)) > 1) {
-                    const int cc = morton2(jx, jz), sh = 2 * (L - l);
-                    const int b = A.startS[(long)cc << sh], n = A.startS[((long)cc + 1) << sh] - b;
-                    if (n > P2) { a = cc; len = P2; lvl = l; }
-                    else { a = b; len = n; }
+            if (l >= lmin && l <= lmax) {
+                const int cxl = cx >> (lc - l), czl = cz >> (lc - l);
+                const int qx = (cxl >> 1) + pn % 3 - 1, qz = (czl >> 1) + pn / 3 - 1;
+                if (qx >= 0 && qz >= 0 && qx < (1 << (l - 1)) && qz < (1 << (l - 1))) {
+                    const int jx = 2 * qx + (ch & 1), jz = 2 * qz + (ch >> 1);
+                    if (max(abs(jx - cxl), abs(jz - czl)) > 1) {
+                        const int cc = morton2(jx, jz), sh = 2 * (L - l);
+                        const int b = A.startS[(long)cc << sh], n = A.startS[((long)cc + 1) << sh] - b;
+                        if (n > P2) { a = cc; len = P2; lvl = l; }
+                        else { a = b; len = n; }
+                    }
                 }
             }
         }
@@ -431,7 +425,7 @@ __global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_consta
         sm.ent_lvl[s] = lvl;
     }
     __syncthreads();
-    if (tid < 32) {   // drop the empty slots (order kept), then the running offsets
+    if (tid < 32) {
         int base = 0;
         for (int s0 = 0; s0 < nslots; s0 += 32) {
             const int s = s0 + lane;
@@ -466,24 +460,202 @@ __global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_consta
         }
     }
     __syncthreads();
-    const int total = sm.pre[sm.nent], cnt = te - tb;
-    if (total == 0) {
-        for (int t = tb + tid; t < te; t += TE_THREADS) {
-            A.u[A.permT[t]] = 0.0;
-            A.w[A.permT[t]] = 0.0;
-        }
-        return;
+    return sm.pre[sm.nent];
+}
+
+// one pass: targets [t0, t1) of T, t1 - t0 <= R * TE_THREADS, against the CTA's whole list
+template <int R, class Tgt>
+__device__ __forceinline__ void tree_eval_rows(const TreeGeom &G, const TreeEval &A, const Tgt &T, TreeSmem &sm, int t0, int t1,
+                                               int total)
+{
+    const int tid = threadIdx.x;
+    const double vc4 = G.vc4;
+    double xp[R], zp[R], au[R], aw[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        T.load(min(t0 + tid + r * TE_THREADS, t1 - 1), xp[r], zp[r]);
+        au[r] = aw[r] = 0.0;
     }
-    if (tid == 0 && blockIdx.y == 0 && A.pairs) atomicAdd(A.pairs, (unsigned long long)cnt * (unsigned long long)total);
+    const int ntiles = (total + TE_TILE - 1) / TE_TILE;
+    double nx, nz, ng;
+    tree_fetch(G, A, sm, tid, total, nx, nz, ng);
+    __syncthreads();                       // the previous pass has finished reading both buffers
+    sm.sxz[0][tid] = make_double2(nx, nz);
+    sm.sg[0][tid] = ng;
+    __syncthreads();
+    for (int k = 0; k < ntiles; k++) {
+        const int buf = k & 1;
+        if (k + 1 < ntiles) tree_fetch(G, A, sm, (k + 1) * TE_TILE + tid, total, nx, nz, ng);   // in flight during the tile
+        const int len = min(TE_TILE, total - k * TE_TILE);
+#pragma unroll 4
+        for (int j = 0; j < len; j++) {
+            const double2 s = sm.sxz[buf][j];
+            const double gj = sm.sg[buf][j];
+#pragma unroll
+            for (int r = 0; r < R; r++) pair_fast(xp[r], zp[r], s.x, s.y, gj, vc4, au[r], aw[r]);
+        }
+        if (k + 1 < ntiles) {
+            sm.sxz[buf ^ 1][tid] = make_double2(nx, nz);
+            sm.sg[buf ^ 1][tid] = ng;
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++)
+        if (t0 + tid + r * TE_THREADS < t1) T.store(t0 + tid + r * TE_THREADS, au[r], aw[r]);
+}
+
+// The item's targets [tb, te) are cut into row units of TE_THREADS, and the units into passes of <= 4 (rows per thread) as
+// evenly as possible; passes are spread over blockIdx.y so that an item is several CTAs (wave quantisation).
+template <class Tgt>
+__device__ __forceinline__ void tree_eval_item(const TreeGeom &G, const TreeEval &A, const Tgt &T, TreeSmem &sm, int tb, int te,
+                                               int total)
+{
+    const int units = (te - tb + TE_THREADS - 1) / TE_THREADS, npass = (units + 3) >> 2;
     const int base = units / npass, extra = units - base * npass;
     for (int pass = blockIdx.y; pass < npass; pass += gridDim.y) {
         const int R = base + (pass < extra ? 1 : 0);
         const int t0 = tb + (pass * base + min(pass, extra)) * TE_THREADS, t1 = min(te, t0 + R * TE_THREADS);
-        if (R == 1) tree_eval_rows<1>(G, A, sm, t0, t1, total);
-        else if (R == 2) tree_eval_rows<2>(G, A, sm, t0, t1, total);
-        else if (R == 3) tree_eval_rows<3>(G, A, sm, t0, t1, total);
-        else tree_eval_rows<4>(G, A, sm, t0, t1, total);
+        if (total == 0) {
+            for (int t = t0 + threadIdx.x; t < t1; t += TE_THREADS) T.store(t, 0.0, 0.0);
+        } else if (R == 1) tree_eval_rows<1>(G, A, T, sm, t0, t1, total);
+        else if (R == 2) tree_eval_rows<2>(G, A, T, sm, t0, t1, total);
+        else if (R == 3) tree_eval_rows<3>(G, A, T, sm, t0, t1, total);
+        else tree_eval_rows<4>(G, A, T, sm, t0, t1, total);
     }
+}
+
+// deepest level whose ancestor of leaf c carries a local field (more than P2 sources), or 1
+__device__ __forceinline__ int tree_local_level(const TreeGeom &G, const int *startS, int c)
+{
+    for (int l = G.L; l >= 2; l--) {
+        const int sh = 2 * (G.L - l);
+        const long a = (long)(c >> sh);
+        if (startS[(a + 1) << sh] - startS[a << sh] > G.P2) return l;
+    }
+    return 1;
+}
+
+__global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_constant__ TreeGeom G, const __grid_constant__ TreeEval A)
+{
+    __shared__ __align__(16) TreeSmem sm;
+    const int L = G.L, P2 = G.P2;
+    const int nm2l = A.fmm ? (int)level_offset(L + 1) : 0;
+    if ((int)blockIdx.x < nm2l) {
+        // M2L item: cell c of level l
+        int l = 2;
+        while (level_offset(l + 1) <= (long)blockIdx.x) l++;
+        const int c = (int)(blockIdx.x - level_offset(l)), sh = 2 * (L - l);
+        if (A.startS[((long)c + 1) << sh] - A.startS[(long)c << sh] <= P2) return;     // no local field here
+        if (A.startT[((long)c + 1) << sh] == A.startT[(long)c << sh]) return;           // none of this rank's targets below
+        if ((int)blockIdx.y >= (((P2 + TE_THREADS - 1) / TE_THREADS + 3) >> 2)) return;
+        const int cx = (int)compact16((unsigned)c), cz = (int)compact16((unsigned)c >> 1);
+        const int total = tree_build_list(G, A, cx, cz, l, false, l, l, sm);
+        const double h = ldexp(G.side, -(l + 1));
+        const long off = (level_offset(l) + c) * P2;
+        TgtNodePts T{G.x0 + (2.0 * cx + 1.0) * h, G.z0 + (2.0 * cz + 1.0) * h, h, G.s, G.P1, A.uloc + off, A.wloc + off};
+        if (threadIdx.x == 0 && blockIdx.y == 0 && A.pairs) atomicAdd(A.pairs, (unsigned long long)P2 * (unsigned long long)total);
+        tree_eval_item(G, A, T, sm, 0, P2, total);
+        return;
+    }
+    const int c = (int)blockIdx.x - nm2l;
+    const int tb = A.startT[c], te = A.startT[c + 1];
+    if (tb == te) return;
+    if ((int)blockIdx.y >= (((te - tb + TE_THREADS - 1) / TE_THREADS + 3) >> 2)) return;
+    const int lstar = A.fmm ? tree_local_level(G, A.startS, c) : 1;
+    const int total = tree_build_list(G, A, (int)compact16((unsigned)c), (int)compact16((unsigned)c >> 1), L, true, lstar + 1, L, sm);
+    if (threadIdx.x == 0 && blockIdx.y == 0 && A.pairs) atomicAdd(A.pairs, (unsigned long long)(te - tb) * (unsigned long long)total);
+    TgtLeafPts T{A.permT, A.xt, A.zt, A.u, A.w};
+    tree_eval_item(G, A, T, sm, tb, te, total);
+}
+
+// barycentric Lagrange basis l_k(xi), k < P1, into row[]
+__device__ __forceinline__ void tree_basis(const TreeGeom &G, double xi, double *row)
+{
+    double sum = 0.0;
+    int hit = -1;
+    for (int k = 0; k < G.P1; k++) {
+        double d = xi - G.s[k];
+        if (d == 0.0) { hit = k; d = 1.0; }
+        const double t = G.bw[k] / d;
+        row[k] = t;
+        sum += t;
+    }
+    const double inv = 1.0 / sum;
+    for (int k = 0; k < G.P1; k++) row[k] = hit >= 0 ? (k == hit ? 1.0 : 0.0) : row[k] * inv;
+}
+
+// L2L: the parent's local field interpolated to the points of child cell c of level l (l >= 3), added to the child's M2L sums
+__global__ void __launch_bounds__(256) k_tree_l2l(const __grid_constant__ TreeGeom G, int l, const int *startS, const int *startT,
+                                                  double *uloc, double *wloc)
+{
+    const int c = blockIdx.x, sh = 2 * (G.L - l), tid = threadIdx.x, P1 = G.P1, P2 = G.P2;
+    if (startS[((long)c + 1) << sh] - startS[(long)c << sh] <= P2) return;
+    if (startT[((long)c + 1) << sh] == startT[(long)c << sh]) return;
+    __shared__ double Up[TR_MAX_P1 * TR_MAX_P1], Wp[TR_MAX_P1 * TR_MAX_P1], Tu[TR_MAX_P1 * TR_MAX_P1], Tw[TR_MAX_P1 * TR_MAX_P1];
+    __shared__ double Bx[TR_MAX_P1][TR_MAX_P1], Bz[TR_MAX_P1][TR_MAX_P1];
+    const long poff = (level_offset(l - 1) + (c >> 2)) * P2, coff = (level_offset(l) + c) * P2;
+    const int ch = c & 3;
+    for (int k = tid; k < P2; k += 256) {
+        Up[k] = uloc[poff + k];
+        Wp[k] = wloc[poff + k];
+    }
+    if (tid < 2 * P1) {
+        const int k = tid >> 1, dim = tid & 1;
+        const double xi = (G.s[k] + (double)(dim ? (ch >> 1) * 2 - 1 : (ch & 1) * 2 - 1)) * 0.5;
+        tree_basis(G, xi, dim ? Bz[k] : Bx[k]);
+    }
+    __syncthreads();
+    for (int idx = tid; idx < P2; idx += 256) {      // T[m1][k2] = sum_m2 Bz[k2][m2] U[m1][m2]
+        const int m1 = idx / P1, k2 = idx - m1 * P1;
+        double a = 0.0, b = 0.0;
+        for (int m2 = 0; m2 < P1; m2++) {
+            a = fma(Bz[k2][m2], Up[m1 * P1 + m2], a);
+            b = fma(Bz[k2][m2], Wp[m1 * P1 + m2], b);
+        }
+        Tu[idx] = a;
+        Tw[idx] = b;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < P2; idx += 256) {      // child[k1][k2] += sum_m1 Bx[k1][m1] T[m1][k2]
+        const int k1 = idx / P1, k2 = idx - k1 * P1;
+        double a = 0.0, b = 0.0;
+        for (int m1 = 0; m1 < P1; m1++) {
+            a = fma(Bx[k1][m1], Tu[m1 * P1 + k2], a);
+            b = fma(Bx[k1][m1], Tw[m1 * P1 + k2], b);
+        }
+        uloc[coff + idx] += a;
+        wloc[coff + idx] += b;
+    }
+}
+
+// L2P: every target adds the local field of its deepest ancestor that carries one, interpolated at the target
+__global__ void __launch_bounds__(128) k_tree_l2p(const __grid_constant__ TreeGeom G, const __grid_constant__ TreeEval A)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= A.np) return;
+    const int oi = A.permT[t], c = A.keyT[oi];
+    const int l = tree_local_level(G, A.startS, c);
+    if (l < 2) return;
+    const int a = c >> (2 * (G.L - l)), P1 = G.P1;
+    const double h = ldexp(G.side, -(l + 1)), inv_h = 1.0 / h;
+    const double cx = G.x0 + (2.0 * compact16((unsigned)a) + 1.0) * h, cz = G.z0 + (2.0 * compact16((unsigned)a >> 1) + 1.0) * h;
+    double bx[TR_MAX_P1], bz[TR_MAX_P1];
+    tree_basis(G, (A.xt[oi] - cx) * inv_h, bx);
+    tree_basis(G, (A.zt[oi] - cz) * inv_h, bz);
+    const double *U = A.uloc + (level_offset(l) + a) * G.P2, *W = A.wloc + (level_offset(l) + a) * G.P2;
+    double su = 0.0, sw = 0.0;
+    for (int k1 = 0; k1 < P1; k1++) {
+        double tu = 0.0, tw = 0.0;
+        for (int k2 = 0; k2 < P1; k2++) {
+            tu = fma(bz[k2], U[k1 * P1 + k2], tu);
+            tw = fma(bz[k2], W[k1 * P1 + k2], tw);
+        }
+        su = fma(bx[k1], tu, su);
+        sw = fma(bx[k1], tw, sw);
+    }
+    A.u[oi] += su;
+    A.w[oi] += sw;
 }
 
 __global__ void __launch_bounds__(256) k_tree_euler(const double *x, const double *z, const double *u, const double *w, double dt,
@@ -511,10 +683,10 @@ struct Arena {
 
 struct TreeBufs {
     int *keyS, *slotS, *keyT, *slotT, *cntS, *cntT, *startS, *startT, *tmpS, *permS, *tmpT, *permT;
-    double *xs, *zs, *gs, *qhat;
+    double *xs, *zs, *gs, *qhat, *uloc, *wloc;
     unsigned long long *pairs;
 };
-static size_t tree_layout(Arena &a, TreeBufs &b, long nw, long np, int L, int P2)
+static size_t tree_layout(Arena &a, TreeBufs &b, long nw, long np, int L, int P2, bool fmm)
 {
     const size_t ncell = (size_t)1 << (2 * L);
     b.keyS = a.take<int>(nw); b.slotS = a.take<int>(nw); b.keyT = a.take<int>(np); b.slotT = a.take<int>(np);
@@ -523,6 +695,8 @@ static size_t tree_layout(Arena &a, TreeBufs &b, long nw, long np, int L, int P2
     b.tmpS = a.take<int>(nw); b.permS = a.take<int>(nw); b.tmpT = a.take<int>(np); b.permT = a.take<int>(np);
     b.xs = a.take<double>(nw); b.zs = a.take<double>(nw); b.gs = a.take<double>(nw);
     b.qhat = a.take<double>((size_t)level_offset(L + 1) * P2);
+    b.uloc = a.take<double>(fmm ? (size_t)level_offset(L + 1) * P2 : 1);
+    b.wloc = a.take<double>(fmm ? (size_t)level_offset(L + 1) * P2 : 1);
     b.pairs = a.take<unsigned long long>(1);
     return a.off;
 }
@@ -579,10 +753,11 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
 
         Arena sizer{nullptr};
         TreeBufs B;
-        const size_t bytes = tree_layout(sizer, B, nw, np_, L, P2);
+        const bool fmm = !getenv("LUDVM_TREE_NO_FMM");
+        const size_t bytes = tree_layout(sizer, B, nw, np_, L, P2, fmm);
         if ((rc = scratch_reserve(ctx, 8, bytes, &p))) return rc;
         Arena ar{(char *)p};
-        tree_layout(ar, B, nw, np_, L, P2);
+        tree_layout(ar, B, nw, np_, L, P2, fmm);
         const int ncell = 1 << (2 * L);
         CUDA_TRY(cudaMemsetAsync(B.cntS, 0, (size_t)(ncell + 1) * sizeof(int), st));
         CUDA_TRY(cudaMemsetAsync(B.cntT, 0, (size_t)(ncell + 1) * sizeof(int), st));
@@ -610,7 +785,8 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
             k_tree_up<<<1 << (2 * l), TU_THREADS, 0, st>>>(G, l, B.startS, B.xs, B.zs, B.gs, B.qhat);
             ctx->launches++;
         }
-        TreeEval A = {B.startS, B.startT, B.permT, B.xs, B.zs, B.gs, B.qhat, xp, zp, u, w, B.pairs};
+        TreeEval A = {B.startS, B.startT, B.permT, B.keyT, B.xs, B.zs, B.gs, B.qhat, xp, zp, u, w, B.uloc, B.wloc, B.pairs,
+                      fmm ? 1 : 0, (int)np_};
         cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
         if (stats) {
             for (int k = 1; k < 3; k++) CUDA_TRY(cudaEventCreate(&ev[k]));
@@ -618,12 +794,20 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
         }
         int ysplit = 4;
         if (const char *ye = getenv("LUDVM_TREE_YSPLIT")) ysplit = std::max(1, std::min(64, atoi(ye)));
-        k_tree_eval<<<dim3(ncell, ysplit), TE_THREADS, 0, st>>>(G, A);
+        k_tree_eval<<<dim3(ncell + (fmm ? (unsigned)level_offset(L + 1) : 0u), ysplit), TE_THREADS, 0, st>>>(G, A);
         ctx->launches++;
+        if (fmm) {
+            for (int l = 3; l <= L; l++) {
+                k_tree_l2l<<<1 << (2 * l), 256, 0, st>>>(G, l, B.startS, B.startT, B.uloc, B.wloc);
+                ctx->launches++;
+            }
+            k_tree_l2p<<<ceil_div(np_, 128), 128, 0, st>>>(G, A);
+            ctx->launches++;
+        }
         if (stats) CUDA_TRY(cudaEventRecord(ev[2], st));
         CUDA_TRY(cudaGetLastError());
         ctx->plan[0] = LUDVM_K_TREE; ctx->plan[1] = 4; ctx->plan[2] = L; ctx->plan[3] = 0; ctx->plan[4] = 1;
-        ctx->plan[5] = order; ctx->plan[6] = TE_THREADS / 32; ctx->plan[7] = 0;
+        ctx->plan[5] = order; ctx->plan[6] = TE_THREADS / 32; ctx->plan[7] = fmm ? 1 : 0;
         if (stats) {
             unsigned long long pairs = 0;
             CUDA_TRY(cudaMemcpyAsync(&pairs, B.pairs, sizeof(pairs), cudaMemcpyDeviceToHost, st));

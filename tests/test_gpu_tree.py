@@ -53,6 +53,24 @@ def test_tree_self_evaluation_vs_oracle(order, tol, monkeypatch):
     assert st["leaf_level"] == 6 and st["pair_evaluations"] < 0.8 * st["all_pairs"]
 
 
+@pytest.mark.parametrize("level,leaf", [(5, 0), (7, 0)])
+def test_tree_without_local_fields_is_the_same_sum(level, leaf, monkeypatch):
+    """LUDVM_TREE_NO_FMM=1 evaluates every far list at the targets (pure treecode); with local fields (M2L / L2L / L2P, the
+    default) the same lists act on the cells' Chebyshev points first.  Both are within tolerance of the oracle, and of
+    each other."""
+    from ludvm_b200 import ops
+    g, x, z = _cloud(120000, 8)
+    monkeypatch.setenv("LUDVM_TREE_LEVEL", str(level))
+    u1, w1, st1 = ops.induced_velocity_tree(g, x, z, x, z, VC, return_stats=True)
+    monkeypatch.setenv("LUDVM_TREE_NO_FMM", "1")
+    u0, w0, st0 = ops.induced_velocity_tree(g, x, z, x, z, VC, return_stats=True)
+    monkeypatch.delenv("LUDVM_TREE_NO_FMM")
+    den = _sum_abs_terms(g, x, z, x[:300], z[:300], VC ** 4)
+    assert np.max(np.hypot(u1[:300] - u0[:300], w1[:300] - w0[:300]) / den) <= 1e-12
+    assert st1["pair_evaluations"] < st0["pair_evaluations"]
+    _check(g, x, z, x, z, 18, leaf, 1e-12)
+
+
 def test_tree_default_parameters_and_separate_targets():
     g, x, z = _cloud(150000, 2)
     rng = np.random.default_rng(3)
