@@ -557,6 +557,79 @@ __device__ __forceinline__ void fast_tiled_block(const SrcView &S, const Tgt &T,
     }
 }
 
+// Double-buffered form of fast_tiled_block for sources that bulk copies cannot take (the time loop's three-segment wake):
+// every thread fetches its two sources of tile k + 1 into registers BEFORE the pair loop of tile k and stores them to the
+// other buffer afterwards, so the loads are in flight during the FP64 work and one __syncthreads per tile is left
+// (fast_tiled_block: load -> barrier -> compute -> barrier, 16 % of the issue slots waiting at the barrier,
+// profiles/r01c_k_conv_old_tiled_stalls.txt).  Sources are packed (x, z) + Gamma: one LDS.128 + one LDS.64 per source
+// instead of four LDS.64.  Scalar core radius only.
+struct DbTiles {
+    double2 xz[2][FT_TILE];
+    double g[2][FT_TILE];
+};
+template <int R, class Tgt>
+__device__ __forceinline__ void fast_tiled_block_db(const SrcView &S, const Tgt &T, int nrows, int row_block, int c0, int c1,
+                                                    double *__restrict__ pu, double *__restrict__ pw_, DbTiles &sm)
+{
+    constexpr int UNROLL = R <= 2 ? 8 : FT_UNROLL;
+    constexpr int PER = FT_TILE / FT_THREADS;
+    double tx[R], tz[R], au[R], aw[R];
+    const int base = row_block * (FT_THREADS * R) + threadIdx.x;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        T.get(min(base + r * FT_THREADS, nrows - 1), tx[r], tz[r]);
+        au[r] = 0.0;
+        aw[r] = 0.0;
+    }
+    const double vc4 = S.vc4s;
+    double lx[PER], lz[PER], lg[PER];
+    auto fetch = [&](int t0) {
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int s = t0 + threadIdx.x + q * FT_THREADS;
+            const bool ok = s < c1;
+            const int p = ok ? S.phys(s) : 0;
+            lx[q] = ok ? S.x[p] : 0.0;
+            lz[q] = ok ? S.z[p] : 0.0;
+            lg[q] = ok ? S.g[p * S.gstride] * LUDVM_INV_TWO_PI : 0.0;
+        }
+    };
+    auto put = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            sm.xz[buf][threadIdx.x + q * FT_THREADS] = make_double2(lx[q], lz[q]);
+            sm.g[buf][threadIdx.x + q * FT_THREADS] = lg[q];
+        }
+    };
+    const int ntiles = (c1 - c0 + FT_TILE - 1) / FT_TILE;
+    if (ntiles > 0) fetch(c0);
+    __syncthreads();
+    put(0);
+    __syncthreads();
+    for (int k = 0; k < ntiles; k++) {
+        const int buf = k & 1, t0 = c0 + k * FT_TILE;
+        if (k + 1 < ntiles) fetch(t0 + FT_TILE);
+        const int cnt = min(FT_TILE, c1 - t0);
+#pragma unroll UNROLL
+        for (int j = 0; j < cnt; j++) {
+            const double2 s = sm.xz[buf][j];
+            const double g = sm.g[buf][j];
+#pragma unroll
+            for (int r = 0; r < R; r++) pair_fast(tx[r], tz[r], s.x, s.y, g, vc4, au[r], aw[r]);
+        }
+        if (k + 1 < ntiles) put(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int row = base + r * FT_THREADS;
+        if (row < nrows) {
+            pu[row] = au[r];
+            pw_[row] = aw[r];
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // fast tiled, TMA-staged: for one contiguous source segment with a scalar core the x / z / Gamma tiles are brought
 // into shared memory by the copy engine (cp.async.bulk + mbarrier complete_tx, SASS UBLKCP), double-buffered so the

@@ -1006,13 +1006,36 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_conv_partials_tiled(SimDev S,
 // the last wave's worth of time).  Identical in the producer and in k_finish_ov.
 struct TiledGeom {
     int chunk_len, chunks;
-    __host__ __device__ __forceinline__ TiledGeom(int nrows, int nsrc, int R, int slots)
+    // `slots_code` = resident CTA slots, plus (opt-in, A/B runs) a wave range in bits 10-15 / 16-21 for the search below.
+    __host__ __device__ __forceinline__ TiledGeom(int nrows, int nsrc, int R, int slots_code)
     {
         const int rb = (nrows + FT_THREADS * R - 1) / (FT_THREADS * R);
-        int want = (8 * slots + rb - 1) / rb;
-        want = want < 1 ? 1 : (want > SIM_TILED_CHUNKS_MAX ? SIM_TILED_CHUNKS_MAX : want);
-        chunk_len = (((nsrc + want - 1) / want + 63) / 64) * 64;
-        chunks = (nsrc + chunk_len - 1) / chunk_len;
+        const int slots = slots_code & 1023, wmin = (slots_code >> 10) & 63, wmax = (slots_code >> 16) & 63;
+        if (wmin == 0) {
+            int want = (8 * slots + rb - 1) / rb;
+            want = want < 1 ? 1 : (want > SIM_TILED_CHUNKS_MAX ? SIM_TILED_CHUNKS_MAX : want);
+            chunk_len = (((nsrc + want - 1) / want + 63) / 64) * 64;
+            chunks = (nsrc + chunk_len - 1) / chunk_len;
+            return;
+        }
+        // Opt-in (LUDVM_TILED_WAVES=min,max): equal items run in waves over the resident slots, so the kernel should take
+        // waves x (chunk length + a fixed cost per item): try min .. max waves, for each the largest chunk count that
+        // still fits them (chunk lengths in multiples of 16), and keep the cheapest.  Measured on the dt = 2e-3 run
+        // (profiles/r02zd_hires.txt): 4..10 waves 5.86 s against 5.45 s for the rule above -- few, long CTAs free their
+        // first slot late for the solve branch.
+        long best = -1;
+        chunk_len = nsrc > 0 ? nsrc : 1;
+        chunks = 1;
+        for (int W = wmin; W <= wmax; W++) {
+            int c = (int)(((long)W * slots) / rb);
+            c = c < 1 ? 1 : (c > SIM_TILED_CHUNKS_MAX ? SIM_TILED_CHUNKS_MAX : c);
+            int len = (((nsrc + c - 1) / c + 15) / 16) * 16;
+            len = len < 16 ? 16 : len;
+            const int nch = (nsrc + len - 1) / len;
+            const long waves = ((long)rb * nch + slots - 1) / slots;
+            const long t = waves * (long)(len + 48);
+            if (best < 0 || t < best) { best = t; chunk_len = len; chunks = nch < 1 ? 1 : nch; }
+        }
     }
 };
 
@@ -1024,10 +1047,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 4) k_solve_small(SimDev S, int 
     phase_solve<LUDVM_METHOD_FAURE>(S, st, sm, sm + TABLE_SMEM_DOUBLES(S.P, S.Nc, S.sinn_smem), S.pre_sums, true);
 }
 
-template <int R>
+template <int R, bool DB>
 __global__ void __launch_bounds__(FT_THREADS, 2) k_conv_old_tiled(SimDev S, int s, int slots)
 {
-    __shared__ double sx[FT_TILE], sz[FT_TILE], sg[FT_TILE], sv[FT_TILE];
+    __shared__ __align__(16) unsigned char raw[DB ? sizeof(DbTiles) : 4 * FT_TILE * sizeof(double)];
     Step st;
     if (!step_begin(S, s, st)) return;
     SrcView W = wake_view(S, st.itev, st.ilev);
@@ -1040,7 +1063,13 @@ __global__ void __launch_bounds__(FT_THREADS, 2) k_conv_old_tiled(SimDev S, int 
     place_lev(S, st.i, st.ilev, TW.xl, TW.zl);
     int c0 = blockIdx.y * G.chunk_len, c1 = min(W.n, c0 + G.chunk_len);
     size_t po = (size_t)blockIdx.y * nrows;
-    fast_tiled_block<R>(W, TW, nrows, blockIdx.x, c0, c1, S.pb_u + po, S.pb_w + po, sx, sz, sg, sv);
+    if (DB) {
+        fast_tiled_block_db<R>(W, TW, nrows, blockIdx.x, c0, c1, S.pb_u + po, S.pb_w + po, *reinterpret_cast<DbTiles *>(raw));
+    } else {
+        double *sx = reinterpret_cast<double *>(raw);
+        fast_tiled_block<R>(W, TW, nrows, blockIdx.x, c0, c1, S.pb_u + po, S.pb_w + po, sx, sx + FT_TILE, sx + 2 * FT_TILE,
+                            sx + 3 * FT_TILE);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -1934,11 +1963,18 @@ static int bracket_of(long n)
 // Launch geometry of one step for every wake size up to 2^bracket.
 struct StepPlan {
     int g1, g3, g4, g5, R, tchunks, slots, g_wt;
-    bool tiled, ov, tiled_exact, wt;
+    bool tiled, ov, tiled_exact, wt, db;
     dim3 gto;
     dim3 gt;
     dim3 gte;
 };
+
+typedef void (*conv_old_fn)(SimDev, int, int);
+static conv_old_fn conv_old_kernel(int R, bool db)
+{
+    if (db) return R == 4 ? k_conv_old_tiled<4, true> : (R == 2 ? k_conv_old_tiled<2, true> : k_conv_old_tiled<1, true>);
+    return R == 4 ? k_conv_old_tiled<4, false> : (R == 2 ? k_conv_old_tiled<2, false> : k_conv_old_tiled<1, false>);
+}
 
 static StepPlan plan_step(const ludvm_sim *s, int bracket)
 {
@@ -1982,6 +2018,22 @@ static StepPlan plan_step(const ludvm_sim *s, int bracket)
         pl.ov = D.P <= 256 && !getenv("LUDVM_NO_OVERLAP");
         pl.gto = dim3((unsigned)((nw + 3 + FT_THREADS * pl.R - 1) / (FT_THREADS * pl.R)), (unsigned)SIM_TILED_CHUNKS_MAX);
         pl.slots = sm * (pl.R == 1 ? 3 : 2);   // resident CTAs of k_conv_old_tiled<R>: 70 registers -> 3 per SM, 112-120 -> 2
+        // double-buffered tiles (fast_tiled_block_db): opt-in, measured 5.88 s against 5.77 s on the dt = 2e-3 run
+        // (profiles/r02zd_hires.txt) -- with two or three resident CTAs per SM the barrier waits of one CTA are already
+        // covered by the others
+        pl.db = getenv("LUDVM_CONV_DB") != nullptr;
+        {   // resident CTAs of the chosen instantiation, from the occupancy calculator
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, conv_old_kernel(pl.R, pl.db), FT_THREADS, 0) == cudaSuccess &&
+                per_sm > 0)
+                pl.slots = sm * per_sm;
+            else
+                cudaGetLastError();
+        }
+        if (const char *we = getenv("LUDVM_TILED_WAVES")) {   // "min,max": the wave search of TiledGeom (A/B)
+            int a = 0, b = 0;
+            if (sscanf(we, "%d,%d", &a, &b) == 2 && a >= 1 && b >= a && b < 64) pl.slots |= (a << 10) | (b << 16);
+        }
         // warp-task form of the old-wake convection (k_conv_old_wt): 2 CTAs x 8 warps resident per SM
         // (opt-in, LUDVM_CONV_WT=1: measured 5.40-5.58 s against 5.24 s for the thread-staged tiles on the 20 000-step
         // dt = 2e-3 run -- whole-block chunks quantise the task count and a few long tasks free their slots late for
@@ -2019,9 +2071,7 @@ static void enqueue_step_kernel(const ludvm_sim *s, const StepPlan &pl, int whic
             else if (pl.R == 2) k_conv_old_wt<2><<<pl.g_wt, 256, sizeof(WtSmem), cs>>>(D, k, pl.slots);
             else k_conv_old_wt<1><<<pl.g_wt, 256, sizeof(WtSmem), cs>>>(D, k, pl.slots);
         } else if (pl.ov) {
-            if (pl.R == 4) k_conv_old_tiled<4><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.slots);
-            else if (pl.R == 2) k_conv_old_tiled<2><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.slots);
-            else k_conv_old_tiled<1><<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.slots);
+            conv_old_kernel(pl.R, pl.db)<<<pl.gto, FT_THREADS, 0, cs>>>(D, k, pl.slots);
         } else if (pl.R == 4) k_conv_partials_tiled<4><<<pl.gt, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
         else if (pl.R == 2) k_conv_partials_tiled<2><<<pl.gt, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
         else k_conv_partials_tiled<1><<<pl.gt, FT_THREADS, 0, cs>>>(D, k, pl.tchunks);
@@ -2056,9 +2106,13 @@ static int build_graph(ludvm_sim *s, int bracket, int ksteps, cudaGraphExec_t *o
             enqueue_step_kernel(s, pl, 0, k, cs);
             enqueue_step_kernel(s, pl, 2, k, cs2);
             enqueue_step_kernel(s, pl, 1, k, cs);
+            // The new-vortex / bound-vortex terms need the solve, not the old-wake sums, so they could run beside the bulk
+            // kernel instead of after the join (LUDVM_CONV_NEW_EARLY=1): measured no better (5.88 vs 5.84 s).
+            const bool new_after_join = getenv("LUDVM_CONV_NEW_EARLY") == nullptr;
+            if (!new_after_join) enqueue_step_kernel(s, pl, 4, k, cs);
             CUDA_TRY(cudaEventRecord(s->ev_join, cs2));
             CUDA_TRY(cudaStreamWaitEvent(cs, s->ev_join, 0));
-            enqueue_step_kernel(s, pl, 4, k, cs);
+            if (new_after_join) enqueue_step_kernel(s, pl, 4, k, cs);
             enqueue_step_kernel(s, pl, 3, k, cs);
         } else {
             for (int which = 0; which < 4; which++) enqueue_step_kernel(s, pl, which, k, cs);

@@ -158,18 +158,29 @@ __global__ void __launch_bounds__(256) k_tree_place(const int *key, const int *s
 }
 
 // perm[start[c] .. start[c+1]) = the cell's original indices in ascending order (rank by counting: the entries are distinct)
-__global__ void __launch_bounds__(256) k_tree_cellsort(const int *tmp, const int *start, int ncell, int *perm)
+__global__ void __launch_bounds__(256) k_tree_cellsort(const int *__restrict__ tmp, const int *__restrict__ start, int ncell,
+                                                       int *__restrict__ perm)
 {
     const int lane = threadIdx.x & 31;
     const long gw = (long)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (long)gridDim.x * 8;
     for (long c = gw; c < ncell; c += nw) {
         const int b = start[c], m = start[c + 1] - b;
         if (m == 0 || m > TR_SORT_WARP_MAX) continue;
-        for (int i = lane; i < m; i += 32) {
-            const int v = tmp[b + i];
-            int r = 0;
-            for (int j = 0; j < m; j++) r += tmp[b + j] < v;
+        const int *__restrict__ cell = tmp + b;
+        for (int i = lane; i < m; i += 64) {          // two entries per lane and trip: the loads of a trip are independent
+            const int i2 = min(i + 32, m - 1);
+            const int v = cell[i], v2 = cell[i2];
+            int r = 0, r2 = 0, j = 0;
+            for (; j + 8 <= m; j += 8) {
+                int t[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) t[q] = cell[j + q];
+#pragma unroll
+                for (int q = 0; q < 8; q++) { r += t[q] < v; r2 += t[q] < v2; }
+            }
+            for (; j < m; j++) { const int t = cell[j]; r += t < v; r2 += t < v2; }
             perm[b + r] = v;
+            if (i + 32 < m) perm[b + r2] = v2;
         }
     }
 }
@@ -244,14 +255,15 @@ __global__ void __launch_bounds__(TU_THREADS) k_tree_up(const __grid_constant__ 
     const double *qchild = qhat + level_offset(l + 1) * P2;
     double acc[3] = {0.0, 0.0, 0.0};
     for (int t0 = 0; t0 < total; t0 += TU_TILE) {
-        if (tid < 2 * TU_TILE) {
-            const int tt = tid >> 1, dim = tid & 1, j = t0 + tt;
+        {   // barycentric bases of the tile: thread = (pseudo-vortex tt, dimension, quarter of the nodes)
+            const int tt = tid >> 3, dim = (tid >> 2) & 1, part = tid & 3, j = t0 + tt;
             double *row = dim ? Lz[tt] : Lx[tt];
-            if (j < total) {
+            const bool valid = j < total;
+            double xi = 0.0, gval = 0.0;
+            if (valid) {
                 int sg = 0;
                 while (sg + 1 < nseg && seg_pre[sg + 1] <= j) sg++;
                 const int o = j - seg_pre[sg], ty = seg_type[sg];
-                double xi, gval;
                 if (ty == 0) {
                     const int p = seg_a[sg] + o;
                     xi = dim ? (zs[p] - cz) * inv_h : (xs[p] - cx) * inv_h;
@@ -261,22 +273,31 @@ __global__ void __launch_bounds__(TU_THREADS) k_tree_up(const __grid_constant__ 
                     xi = dim ? (G.s[k2] + (double)((ch >> 1) * 2 - 1)) * 0.5 : (G.s[k1] + (double)((ch & 1) * 2 - 1)) * 0.5;
                     gval = qchild[(long)seg_a[sg] * P2 + o];
                 }
-                double sum = 0.0;
-                int hit = -1;
-                for (int k = 0; k < P1; k++) {
+            }
+            double sum = 0.0, tk[(TR_MAX_P1 + 3) / 4];
+            int hit = -1;
+#pragma unroll
+            for (int q = 0; q < (TR_MAX_P1 + 3) / 4; q++) {
+                const int k = part + 4 * q;
+                tk[q] = 0.0;
+                if (valid && k < P1) {
                     double d = xi - G.s[k];
                     if (d == 0.0) { hit = k; d = 1.0; }
-                    const double t = G.bw[k] / d;
-                    row[k] = t;
-                    sum += t;
+                    tk[q] = G.bw[k] / d;
+                    sum += tk[q];
                 }
-                const double inv = 1.0 / sum;
-                for (int k = 0; k < P1; k++) row[k] = hit >= 0 ? (k == hit ? 1.0 : 0.0) : row[k] * inv;
-                if (dim == 0) gt[tt] = gval;
-            } else {
-                for (int k = 0; k < P1; k++) row[k] = 0.0;
-                if (dim == 0) gt[tt] = 0.0;
             }
+            sum += __shfl_xor_sync(~0u, sum, 1);      // the four quarters sit in adjacent lanes (every lane takes part)
+            sum += __shfl_xor_sync(~0u, sum, 2);
+            hit = max(hit, __shfl_xor_sync(~0u, hit, 1));
+            hit = max(hit, __shfl_xor_sync(~0u, hit, 2));
+            const double inv = valid ? 1.0 / sum : 0.0;
+#pragma unroll
+            for (int q = 0; q < (TR_MAX_P1 + 3) / 4; q++) {
+                const int k = part + 4 * q;
+                if (k < P1) row[k] = !valid ? 0.0 : hit >= 0 ? (k == hit ? 1.0 : 0.0) : tk[q] * inv;
+            }
+            if (dim == 0 && part == 0) gt[tt] = gval;
         }
         __syncthreads();
 #pragma unroll
