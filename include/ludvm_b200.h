@@ -137,6 +137,14 @@ int ludvm_selfconv_step_tree(ludvm_ctx *ctx, const double *gamma, const double *
                              long row0, long nrows, double dt, int order, int leaf, double *x_out, double *z_out,
                              double *u_out, double *w_out, double *stats);
 
+/* ludvm_flowfield_velocity (one source set) through the same hierarchical far field: rows [row0, row0 + nrows) of the 'ij'
+ * mesh x1 x z1.  tgt_density = grid points per unit area of the FULL grid, 1 / (dx dz) (not of the slab, so that slabs
+ * reproduce the full-grid values bit for bit): cells holding more than (order+1)^2 grid points carry a local field even
+ * where they hold few sources; 0 decides from the sources alone.  u, w: [nrows, nz] row-major. */
+int ludvm_flowfield_velocity_tree(ludvm_ctx *ctx, const double *ga, const double *xa, const double *za, long na, double vc4,
+                                  const double *x1, long nx, const double *z1, long nz, long row0, long nrows,
+                                  double tgt_density, int order, int leaf, double *u, double *w, int ptr_kind, double *stats);
+
 /*
  * Flow-field grid evaluation -- replaces the velocity part of LUDVM.flowfield (LUDVM.py:1193-1220) for one
  * snapshot: targets are the 'ij' mesh of x1[nx] x z1[nz] (np.arange values passed by the caller), rows

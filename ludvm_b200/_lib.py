@@ -62,6 +62,8 @@ SIGNATURES = {
                                           C.c_long, C.c_double, C.c_int, C.POINTER(c_vp), C.POINTER(c_vp)]),
     "ludvm_induced_velocity_tree": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_long, c_vp, c_vp, C.c_long, C.c_int,
                                               C.c_int, c_vp, c_vp, C.c_int, c_dp]),
+    "ludvm_flowfield_velocity_tree": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_long, C.c_double, c_vp, C.c_long, c_vp, C.c_long,
+                                                C.c_long, C.c_long, C.c_double, C.c_int, C.c_int, c_vp, c_vp, C.c_int, c_dp]),
     "ludvm_selfconv_step_tree": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_double, C.c_long, C.c_long, C.c_long, C.c_double,
                                            C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_dp]),
     "ludvm_flowfield_velocity": (C.c_int, [c_vp, C.c_int, c_vp, c_vp, c_vp, C.c_long, c_vp, c_vp, c_vp, C.c_long,

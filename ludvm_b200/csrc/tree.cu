@@ -36,13 +36,16 @@ namespace ludvm {
 #define TE_TILE 128
 #define TU_THREADS 256
 #define TU_TILE 32
-#define TR_SORT_WARP_MAX 2048   // cells up to this many vortices are ordered by one warp, larger ones by a whole CTA
+#define TR_MAX_LEAF_POP 65536   // refuse clouds that put more than this into one leaf of the deepest tree
+#define TR_SORT_WARP_MAX 96     // cells up to this many vortices are ordered by one warp, larger ones by a whole CTA
 
 struct TreeGeom {
     double x0, z0, side;     // root square [x0, x0 + side) x [z0, z0 + side)
     double inv_leaf;         // 2^L / side
     double vc4;
-    int L, P1, P2, pad;
+    double tdens;            // targets per unit area when they are a uniform grid (0: unknown): cells that hold more than P2
+                             // grid points carry a local field even where they hold few sources
+    int L, P1, P2, generic_up;   // generic_up = 1: children's proxies go through the tile loop of k_tree_up too (A/B)
     double s[TR_MAX_P1];     // Chebyshev points of the second kind on [-1, 1], exactly antisymmetric
     double bw[TR_MAX_P1];    // barycentric weights
 };
@@ -128,13 +131,17 @@ __global__ void __launch_bounds__(256) k_tree_keys(const __grid_constant__ TreeG
     slot[i] = atomicAdd(cnt + k, 1);   // any free slot of the cell; k_tree_cellsort fixes the order afterwards
 }
 
-// exclusive scan of cnt[0 .. n) into start[0 .. n]; one CTA
-__global__ void __launch_bounds__(1024) k_tree_scan(const int *cnt, int *start, int n)
+// exclusive scan of cnt[0 .. n) into start[0 .. n], and the largest count into *maxcnt; one CTA
+__global__ void __launch_bounds__(1024) k_tree_scan(const int *cnt, int *start, int n, int *maxcnt)
 {
     __shared__ int part[1024];
     const int t = threadIdx.x, chunk = (n + 1023) / 1024, b = min(n, t * chunk), e = min(n, b + chunk);
-    int s = 0;
-    for (int i = b; i < e; i++) s += cnt[i];
+    int s = 0, mx = 0;
+    for (int i = b; i < e; i++) {
+        s += cnt[i];
+        mx = max(mx, cnt[i]);
+    }
+    atomicMax(maxcnt, mx);
     part[t] = s;
     __syncthreads();
     for (int o = 1; o < 1024; o <<= 1) {
@@ -184,24 +191,31 @@ __global__ void __launch_bounds__(256) k_tree_cellsort(const int *__restrict__ t
         }
     }
 }
-__global__ void __launch_bounds__(256) k_tree_cellsort_big(const int *tmp, const int *start, int ncell, int *perm)
+__global__ void __launch_bounds__(256) k_tree_cellsort_big(const int *__restrict__ tmp, const int *__restrict__ start, int ncell,
+                                                           int *__restrict__ perm)
 {
     __shared__ int tile[1024];
     for (long c = blockIdx.x; c < ncell; c += gridDim.x) {
         const int b = start[c], m = start[c + 1] - b;
         if (m <= TR_SORT_WARP_MAX) continue;
-        for (int i0 = 0; i0 < m; i0 += 256) {
-            const int i = i0 + threadIdx.x;
-            const int v = i < m ? tmp[b + i] : 0;
-            int r = 0;
+        for (int i0 = 0; i0 < m; i0 += 512) {          // two entries per thread and trip
+            const int i = i0 + threadIdx.x, i2 = i + 256;
+            const int v = i < m ? tmp[b + i] : 0, v2 = i2 < m ? tmp[b + i2] : 0;
+            int r = 0, r2 = 0;
             for (int j0 = 0; j0 < m; j0 += 1024) {
                 __syncthreads();
                 for (int j = threadIdx.x; j < 1024; j += 256) tile[j] = j0 + j < m ? tmp[b + j0 + j] : 0x7FFFFFFF;
                 __syncthreads();
                 const int jn = min(1024, m - j0);
-                for (int j = 0; j < jn; j++) r += tile[j] < v;
+                int j = 0;
+                for (; j + 8 <= jn; j += 8) {
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { const int t = tile[j + q]; r += t < v; r2 += t < v2; }
+                }
+                for (; j < jn; j++) { const int t = tile[j]; r += t < v; r2 += t < v2; }
             }
             if (i < m) perm[b + r] = v;
+            if (i2 < m) perm[b + r2] = v2;
         }
     }
 }
@@ -218,6 +232,22 @@ __global__ void __launch_bounds__(256) k_tree_gather(const int *perm, const doub
     gs[i] = g[p] * LUDVM_INV_TWO_PI;
 }
 
+// barycentric Lagrange basis l_k(xi), k < P1, into row[]
+__device__ __forceinline__ void tree_basis(const TreeGeom &G, double xi, double *row)
+{
+    double sum = 0.0;
+    int hit = -1;
+    for (int k = 0; k < G.P1; k++) {
+        double d = xi - G.s[k];
+        if (d == 0.0) { hit = k; d = 1.0; }
+        const double t = G.bw[k] / d;
+        row[k] = t;
+        sum += t;
+    }
+    const double inv = 1.0 / sum;
+    for (int k = 0; k < G.P1; k++) row[k] = hit >= 0 ? (k == hit ? 1.0 : 0.0) : row[k] * inv;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // upward pass: proxies of every cell of level l that holds more than P2 vortices
 // ---------------------------------------------------------------------------------------------------
@@ -228,12 +258,16 @@ __global__ void __launch_bounds__(TU_THREADS) k_tree_up(const __grid_constant__ 
     const int b = startS[(long)c << sh], e = startS[((long)c + 1) << sh];
     if (e - b <= G.P2) return;
     __shared__ double Lx[TU_TILE][TR_MAX_P1], Lz[TU_TILE][TR_MAX_P1], gt[TU_TILE];
-    __shared__ int seg_type[4], seg_a[4], seg_pre[5], nseg_s;
+    __shared__ int seg_type[4], seg_a[4], seg_pre[5], nseg_s, prox_ch[4], prox_cell[4], nprox_s;
+    __shared__ double Tq[2][TR_MAX_P1][TR_MAX_P1], Qc[TR_MAX_P1 * TR_MAX_P1], Tm[TR_MAX_P1 * TR_MAX_P1];
     const int P1 = G.P1, P2 = G.P2;
     const double h = ldexp(G.side, -(l + 1)), inv_h = 1.0 / h;
     const double cx = G.x0 + (2.0 * compact16((unsigned)c) + 1.0) * h, cz = G.z0 + (2.0 * compact16((unsigned)c >> 1) + 1.0) * h;
+    // Children that carry proxies are anterpolated with the two fixed (P1 x P1) transfer matrices Tq[v][k][m] =
+    // l_k((s_m -+ 1) / 2) -- 2 P1^3 multiply-adds per child instead of P2^2; children (or a leaf's own vortices) that
+    // are plain vortices go through the tile loop below.
     if (tid == 0) {
-        int ns = 0, run = 0;
+        int ns = 0, run = 0, np = 0;
         if (l == G.L) {
             seg_type[0] = 0; seg_a[0] = b; seg_pre[0] = 0; run = e - b; ns = 1;
         } else {
@@ -241,6 +275,7 @@ __global__ void __launch_bounds__(TU_THREADS) k_tree_up(const __grid_constant__ 
                 const long cc = 4L * c + ch;
                 const int cb = startS[cc << (sh - 2)], ce = startS[(cc + 1) << (sh - 2)], n = ce - cb;
                 if (n == 0) continue;
+                if (n > P2 && G.generic_up == 0) { prox_ch[np] = ch; prox_cell[np] = (int)cc; np++; continue; }
                 seg_pre[ns] = run;
                 if (n > P2) { seg_type[ns] = 1 + ch; seg_a[ns] = (int)cc; run += P2; }
                 else { seg_type[ns] = 0; seg_a[ns] = cb; run += n; }
@@ -249,11 +284,42 @@ __global__ void __launch_bounds__(TU_THREADS) k_tree_up(const __grid_constant__ 
         }
         seg_pre[ns] = run;
         nseg_s = ns;
+        nprox_s = np;
+    }
+    if (l < G.L && tid < 2 * P1) {
+        const int v = tid / P1, m = tid - v * P1;
+        double col[TR_MAX_P1];
+        tree_basis(G, (G.s[m] + (double)(2 * v - 1)) * 0.5, col);
+        for (int k = 0; k < P1; k++) Tq[v][k][m] = col[k];
     }
     __syncthreads();
     const int nseg = nseg_s, total = seg_pre[nseg];
     const double *qchild = qhat + level_offset(l + 1) * P2;
     double acc[3] = {0.0, 0.0, 0.0};
+    for (int pc = 0; pc < nprox_s; pc++) {
+        const int vx = prox_ch[pc] & 1, vz = prox_ch[pc] >> 1;
+        const double *q = qchild + (long)prox_cell[pc] * P2;
+        for (int k = tid; k < P2; k += TU_THREADS) Qc[k] = q[k];
+        __syncthreads();
+        for (int idx = tid; idx < P2; idx += TU_THREADS) {       // Tm[k1][m2] = sum_m1 Tq[vx][k1][m1] Q[m1][m2]
+            const int k1 = idx / P1, m2 = idx - k1 * P1;
+            double a = 0.0;
+            for (int m1 = 0; m1 < P1; m1++) a = fma(Tq[vx][k1][m1], Qc[m1 * P1 + m2], a);
+            Tm[idx] = a;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int qq = 0; qq < 3; qq++) {                        // out[k1][k2] += sum_m2 Tm[k1][m2] Tq[vz][k2][m2]
+            const int k = tid + qq * TU_THREADS;
+            if (k < P2) {
+                const int k1 = k / P1, k2 = k - k1 * P1;
+                double a = acc[qq];
+                for (int m2 = 0; m2 < P1; m2++) a = fma(Tm[k1 * P1 + m2], Tq[vz][k2][m2], a);
+                acc[qq] = a;
+            }
+        }
+        __syncthreads();
+    }
     for (int t0 = 0; t0 < total; t0 += TU_TILE) {
         {   // barycentric bases of the tile: thread = (pseudo-vortex tt, dimension, quarter of the nodes)
             const int tt = tid >> 3, dim = (tid >> 2) & 1, part = tid & 3, j = t0 + tt;
@@ -546,14 +612,20 @@ __device__ __forceinline__ void tree_eval_item(const TreeGeom &G, const TreeEval
     }
 }
 
-// deepest level whose ancestor of leaf c carries a local field (more than P2 sources), or 1
+// Does cell c of level l carry a local field?  More than P2 sources -- or, for grid targets of known density, more than P2
+// grid points.  Both are independent of which targets a rank was given, and both hold for the parent when they hold for a child.
+__device__ __forceinline__ bool tree_has_local(const TreeGeom &G, const int *startS, int l, long c)
+{
+    const int sh = 2 * (G.L - l);
+    if (startS[(c + 1) << sh] - startS[c << sh] > G.P2) return true;
+    const double a = ldexp(G.side, -l);
+    return G.tdens * a * a > (double)G.P2;
+}
+// deepest level whose ancestor of leaf c carries a local field, or 1
 __device__ __forceinline__ int tree_local_level(const TreeGeom &G, const int *startS, int c)
 {
-    for (int l = G.L; l >= 2; l--) {
-        const int sh = 2 * (G.L - l);
-        const long a = (long)(c >> sh);
-        if (startS[(a + 1) << sh] - startS[a << sh] > G.P2) return l;
-    }
+    for (int l = G.L; l >= 2; l--)
+        if (tree_has_local(G, startS, l, (long)(c >> (2 * (G.L - l))))) return l;
     return 1;
 }
 
@@ -567,7 +639,7 @@ __global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_consta
         int l = 2;
         while (level_offset(l + 1) <= (long)blockIdx.x) l++;
         const int c = (int)(blockIdx.x - level_offset(l)), sh = 2 * (L - l);
-        if (A.startS[((long)c + 1) << sh] - A.startS[(long)c << sh] <= P2) return;     // no local field here
+        if (!tree_has_local(G, A.startS, l, c)) return;                                   // no local field here
         if (A.startT[((long)c + 1) << sh] == A.startT[(long)c << sh]) return;           // none of this rank's targets below
         if ((int)blockIdx.y >= (((P2 + TE_THREADS - 1) / TE_THREADS + 3) >> 2)) return;
         const int cx = (int)compact16((unsigned)c), cz = (int)compact16((unsigned)c >> 1);
@@ -590,28 +662,12 @@ __global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_consta
     tree_eval_item(G, A, T, sm, tb, te, total);
 }
 
-// barycentric Lagrange basis l_k(xi), k < P1, into row[]
-__device__ __forceinline__ void tree_basis(const TreeGeom &G, double xi, double *row)
-{
-    double sum = 0.0;
-    int hit = -1;
-    for (int k = 0; k < G.P1; k++) {
-        double d = xi - G.s[k];
-        if (d == 0.0) { hit = k; d = 1.0; }
-        const double t = G.bw[k] / d;
-        row[k] = t;
-        sum += t;
-    }
-    const double inv = 1.0 / sum;
-    for (int k = 0; k < G.P1; k++) row[k] = hit >= 0 ? (k == hit ? 1.0 : 0.0) : row[k] * inv;
-}
-
 // L2L: the parent's local field interpolated to the points of child cell c of level l (l >= 3), added to the child's M2L sums
 __global__ void __launch_bounds__(256) k_tree_l2l(const __grid_constant__ TreeGeom G, int l, const int *startS, const int *startT,
                                                   double *uloc, double *wloc)
 {
     const int c = blockIdx.x, sh = 2 * (G.L - l), tid = threadIdx.x, P1 = G.P1, P2 = G.P2;
-    if (startS[((long)c + 1) << sh] - startS[(long)c << sh] <= P2) return;
+    if (!tree_has_local(G, startS, l, c)) return;
     if (startT[((long)c + 1) << sh] == startT[(long)c << sh]) return;
     __shared__ double Up[TR_MAX_P1 * TR_MAX_P1], Wp[TR_MAX_P1 * TR_MAX_P1], Tu[TR_MAX_P1 * TR_MAX_P1], Tw[TR_MAX_P1 * TR_MAX_P1];
     __shared__ double Bx[TR_MAX_P1][TR_MAX_P1], Bz[TR_MAX_P1][TR_MAX_P1];
@@ -706,6 +762,7 @@ struct TreeBufs {
     int *keyS, *slotS, *keyT, *slotT, *cntS, *cntT, *startS, *startT, *tmpS, *permS, *tmpT, *permT;
     double *xs, *zs, *gs, *qhat, *uloc, *wloc;
     unsigned long long *pairs;
+    int *maxcnt;   // [2]: largest leaf population, sources / targets
 };
 static size_t tree_layout(Arena &a, TreeBufs &b, long nw, long np, int L, int P2, bool fmm)
 {
@@ -719,6 +776,7 @@ static size_t tree_layout(Arena &a, TreeBufs &b, long nw, long np, int L, int P2
     b.uloc = a.take<double>(fmm ? (size_t)level_offset(L + 1) * P2 : 1);
     b.wloc = a.take<double>(fmm ? (size_t)level_offset(L + 1) * P2 : 1);
     b.pairs = a.take<unsigned long long>(1);
+    b.maxcnt = a.take<int>(2);
     return a.off;
 }
 
@@ -726,7 +784,7 @@ static size_t tree_layout(Arena &a, TreeBufs &b, long nw, long np, int L, int P2
 // [1] leaf side, [2] pair evaluations, [3] np * nw, [4] proxies per cell, [5] arena bytes; reading [2] synchronises.
 static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *xw, const double *zw, double vc4, long nw,
                                 const double *xp, const double *zp, long np_, int order, int leaf, double *u, double *w,
-                                double *stats)
+                                double *stats, double tdens = 0.0)
 {
     if (order <= 0) order = 18;
     if (order < 2 || order > TR_MAX_ORDER) return set_error(LUDVM_E_ARG, "tree order %d outside 2..%d", order, TR_MAX_ORDER);
@@ -755,7 +813,8 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
         // leaf level from the wanted mean leaf population over the sources' own bounding box.  Per target a leaf costs
         // 9 x population directly, a level 27 x proxies: the default population is two proxies' worth.
         const int P1 = order + 1, P2 = P1 * P1;
-        const double pop = leaf > 0 ? (double)leaf : 2.0 * P2;
+        // (dense grid targets: the near field is what is left per target, so small leaves; M2L does not grow with them)
+        const double pop = leaf > 0 ? (double)leaf : (tdens > 0.0 ? 64.0 : 2.0 * P2);
         const double area = std::max((sxh - sxl) * (szh - szl), side * side * 1e-12);
         const double a0 = std::sqrt(pop * area / (double)std::max(1L, nw));
         int L = (int)std::lround(std::log2(std::max(side / a0, 1.0)));
@@ -763,8 +822,8 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
         while (lcap < TR_MAX_LEVEL && (1L << (2 * (lcap - 1))) < nw) lcap++;
         L = std::max(2, std::min(std::min(TR_MAX_LEVEL, lcap), L));
         if (const char *le = getenv("LUDVM_TREE_LEVEL")) L = std::max(2, std::min(TR_MAX_LEVEL, atoi(le)));
-        G.x0 = xlo; G.z0 = zlo; G.side = side; G.inv_leaf = (double)(1 << L) / side; G.vc4 = vc4;
-        G.L = L; G.P1 = P1; G.P2 = P2;
+        G.x0 = xlo; G.z0 = zlo; G.side = side; G.inv_leaf = (double)(1 << L) / side; G.vc4 = vc4; G.tdens = tdens;
+        G.L = L; G.P1 = P1; G.P2 = P2; G.generic_up = getenv("LUDVM_TREE_GENERIC_UP") ? 1 : 0;
         for (int k = 0; k < P1; k++) {
             G.s[k] = std::sin(M_PI * (double)(order - 2 * k) / (double)(2 * order));
             G.bw[k] = ((k & 1) ? -1.0 : 1.0) * ((k == 0 || k == order) ? 0.5 : 1.0);
@@ -784,24 +843,43 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
         CUDA_TRY(cudaMemsetAsync(B.cntT, 0, (size_t)(ncell + 1) * sizeof(int), st));
         CUDA_TRY(cudaMemsetAsync(B.pairs, 0, sizeof(unsigned long long), st));
         const int sort_blocks = std::min(ceil_div(ncell, 8), ctx->sm_count * 16);
-        const int big_blocks = std::min(ncell, 4096);
+        const int big_blocks = std::min(ncell, ctx->sm_count * 32);
         cudaEvent_t ev0 = nullptr;
         if (stats) {
             CUDA_TRY(cudaEventCreate(&ev0));
             CUDA_TRY(cudaEventRecord(ev0, st));
         }
+        // targets == sources (the self-convection step of the whole cloud): one sort serves both
+        const bool same = xp == xw && zp == zw && np_ == nw;
+        if (same) { B.keyT = B.keyS; B.startT = B.startS; B.permT = B.permS; }
+        CUDA_TRY(cudaMemsetAsync(B.maxcnt, 0, 2 * sizeof(int), st));
         k_tree_keys<<<ceil_div(nw, 256), 256, 0, st>>>(G, xw, zw, (int)nw, B.keyS, B.slotS, B.cntS);
-        k_tree_scan<<<1, 1024, 0, st>>>(B.cntS, B.startS, ncell);
+        k_tree_scan<<<1, 1024, 0, st>>>(B.cntS, B.startS, ncell, B.maxcnt);
+        ctx->launches += 2;
+        if (!same) {
+            k_tree_keys<<<ceil_div(np_, 256), 256, 0, st>>>(G, xp, zp, (int)np_, B.keyT, B.slotT, B.cntT);
+            k_tree_scan<<<1, 1024, 0, st>>>(B.cntT, B.startT, ncell, B.maxcnt + 1);
+            ctx->launches += 2;
+        }
+        // The sources of a cell are ordered by counting (O(population^2) per cell): a leaf of the deepest allowed tree that
+        // still holds this many vortices means the cloud is far too clustered for a uniform-depth tree, and the
+        // all-pairs kernels are the right tool.
+        int maxcnt[2] = {0, 0};
+        CUDA_TRY(cudaMemcpyAsync(maxcnt, B.maxcnt, sizeof(maxcnt), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        if (same) maxcnt[1] = maxcnt[0];
+        if (maxcnt[0] > TR_MAX_LEAF_POP)
+            return set_error(LUDVM_E_UNSUPPORTED, "tree: a leaf cell of level %d holds %d vortices (limit %d): the cloud is too "
+                             "clustered for the uniform-depth tree, use the all-pairs modes", L, maxcnt[0], TR_MAX_LEAF_POP);
         k_tree_place<<<ceil_div(nw, 256), 256, 0, st>>>(B.keyS, B.slotS, B.startS, (int)nw, B.tmpS);
         k_tree_cellsort<<<sort_blocks, 256, 0, st>>>(B.tmpS, B.startS, ncell, B.permS);
-        k_tree_cellsort_big<<<big_blocks, 256, 0, st>>>(B.tmpS, B.startS, ncell, B.permS);
+        if (maxcnt[0] > TR_SORT_WARP_MAX) k_tree_cellsort_big<<<big_blocks, 256, 0, st>>>(B.tmpS, B.startS, ncell, B.permS);
         k_tree_gather<<<ceil_div(nw, 256), 256, 0, st>>>(B.permS, xw, zw, g, (int)nw, B.xs, B.zs, B.gs);
-        k_tree_keys<<<ceil_div(np_, 256), 256, 0, st>>>(G, xp, zp, (int)np_, B.keyT, B.slotT, B.cntT);
-        k_tree_scan<<<1, 1024, 0, st>>>(B.cntT, B.startT, ncell);
-        k_tree_place<<<ceil_div(np_, 256), 256, 0, st>>>(B.keyT, B.slotT, B.startT, (int)np_, B.tmpT);
-        k_tree_cellsort<<<sort_blocks, 256, 0, st>>>(B.tmpT, B.startT, ncell, B.permT);
-        k_tree_cellsort_big<<<big_blocks, 256, 0, st>>>(B.tmpT, B.startT, ncell, B.permT);
-        ctx->launches += 11;
+        ctx->launches += 3 + (maxcnt[0] > TR_SORT_WARP_MAX ? 1 : 0);
+        if (!same) {   // targets: any order inside a cell will do (a target's sum does not involve the other targets)
+            k_tree_place<<<ceil_div(np_, 256), 256, 0, st>>>(B.keyT, B.slotT, B.startT, (int)np_, B.permT);
+            ctx->launches++;
+        }
         for (int l = L; l >= 2; l--) {
             k_tree_up<<<1 << (2 * l), TU_THREADS, 0, st>>>(G, l, B.startS, B.xs, B.zs, B.gs, B.qhat);
             ctx->launches++;
@@ -813,9 +891,12 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
             for (int k = 1; k < 3; k++) CUDA_TRY(cudaEventCreate(&ev[k]));
             CUDA_TRY(cudaEventRecord(ev[1], st));
         }
-        int ysplit = 4;
+        // passes of <= 512 targets of one leaf are spread over blockIdx.y: enough of it for the most crowded leaf
+        const long items = (long)ncell + (fmm ? level_offset(L + 1) : 0);
+        int ysplit = std::max(4, (maxcnt[1] + 4 * TE_THREADS - 1) / (4 * TE_THREADS));
+        ysplit = (int)std::max(1L, std::min<long>(ysplit, (1L << 24) / items));
         if (const char *ye = getenv("LUDVM_TREE_YSPLIT")) ysplit = std::max(1, std::min(64, atoi(ye)));
-        k_tree_eval<<<dim3(ncell + (fmm ? (unsigned)level_offset(L + 1) : 0u), ysplit), TE_THREADS, 0, st>>>(G, A);
+        k_tree_eval<<<dim3((unsigned)items, ysplit), TE_THREADS, 0, st>>>(G, A);
         ctx->launches++;
         if (fmm) {
             for (int l = 3; l <= L; l++) {
@@ -920,5 +1001,65 @@ LUDVM_API int ludvm_selfconv_step_tree(ludvm_ctx *ctx, const double *gamma, cons
                                                                 z_out + row0);
     ctx->launches++;
     CUDA_TRY(cudaGetLastError());
+    return LUDVM_OK;
+}
+
+namespace ludvm {
+// the 'ij' mesh rows [row0, row0 + nrows) of x1 x z1 as explicit target arrays
+__global__ void __launch_bounds__(256) k_tree_grid_points(const double *x1, const double *z1, int nz, int row0, long npts, double *xp,
+                                                          double *zp)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npts) return;
+    const int r = (int)(i / nz), j = (int)(i - (long)r * nz);
+    xp[i] = x1[row0 + r];
+    zp[i] = z1[j];
+}
+}  // namespace ludvm
+
+LUDVM_API int ludvm_flowfield_velocity_tree(ludvm_ctx *ctx, const double *ga, const double *xa, const double *za, long na, double vc4,
+                                            const double *x1, long nx, const double *z1, long nz, long row0, long nrows,
+                                            double tgt_density, int order, int leaf, double *u, double *w, int ptr_kind,
+                                            double *stats)
+{
+    ARG_CHECK(ctx != nullptr);
+    ARG_CHECK(na > 0 && nx > 0 && nz > 0 && row0 >= 0 && nrows >= 0 && row0 + nrows <= nx);
+    ARG_CHECK(na < (1L << 30) && nrows * nz < (1L << 30) && vc4 >= 0.0 && tgt_density >= 0.0);
+    ARG_CHECK(ga && xa && za && x1 && z1 && u && w);
+    ARG_CHECK(ptr_kind == LUDVM_PTR_HOST || ptr_kind == LUDVM_PTR_DEVICE);
+    if (nrows == 0) return LUDVM_OK;
+    DeviceGuard g(ctx->device);
+    const long npts = nrows * nz;
+    int rc;
+    const double *dga = ga, *dxa = xa, *dza = za, *dx1 = x1, *dz1 = z1;
+    double *du = u, *dw = w;
+    if (ptr_kind == LUDVM_PTR_HOST) {
+        void *p;
+        if ((rc = scratch_reserve(ctx, 4, (3 * (size_t)na + (size_t)nx + (size_t)nz + 8) * sizeof(double), &p))) return rc;
+        double *b = (double *)p;
+        const double *h[5] = {ga, xa, za, x1, z1};
+        const double **d[5] = {&dga, &dxa, &dza, &dx1, &dz1};
+        const size_t n[5] = {(size_t)na, (size_t)na, (size_t)na, (size_t)nx, (size_t)nz};
+        for (int k = 0; k < 5; k++) {
+            CUDA_TRY(cudaMemcpyAsync(b, h[k], n[k] * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            *d[k] = b;
+            b += n[k];
+        }
+        void *o;
+        if ((rc = scratch_reserve(ctx, 5, 2 * (size_t)npts * sizeof(double), &o))) return rc;
+        du = (double *)o;
+        dw = du + npts;
+    }
+    void *tp;
+    if ((rc = scratch_reserve(ctx, 6, 2 * (size_t)npts * sizeof(double), &tp))) return rc;
+    double *xp = (double *)tp, *zp = xp + npts;
+    k_tree_grid_points<<<ceil_div(npts, 256), 256, 0, ctx->stream>>>(dx1, dz1, (int)nz, (int)row0, npts, xp, zp);
+    ctx->launches++;
+    if ((rc = tree_velocity_device(ctx, dga, dxa, dza, vc4, na, xp, zp, npts, order, leaf, du, dw, stats, tgt_density))) return rc;
+    if (ptr_kind == LUDVM_PTR_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(u, du, (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(w, dw, (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
     return LUDVM_OK;
 }

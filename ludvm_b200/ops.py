@@ -66,6 +66,37 @@ def induced_velocity_tree_device(ctx, g, xw, zw, xp, zp, vc4, u, w, order=18, le
     return _tree_stats(stats) if return_stats else None
 
 
+def _grid_density(x1, z1):
+    dx = (x1[-1] - x1[0]) / max(len(x1) - 1, 1)
+    dz = (z1[-1] - z1[0]) / max(len(z1) - 1, 1)
+    return 1.0 / (dx * dz) if dx > 0 and dz > 0 else 0.0
+
+
+def flowfield_velocity_tree(g, xw, zw, vc4, x1, z1, row0=0, nrows=None, order=18, leaf=0, ctx=None, return_stats=False):
+    """`flowfield_velocity` for one source set through the hierarchical far field (csrc/tree.cu), host buffers."""
+    ctx = ctx or _lib.default_context()
+    g, xw, zw, x1, z1 = (f64(a) for a in (g, xw, zw, x1, z1))
+    nrows = x1.size - row0 if nrows is None else nrows
+    u, w = np.empty((nrows, z1.size)), np.empty((nrows, z1.size))
+    stats = np.zeros(8)
+    check(load().ludvm_flowfield_velocity_tree(ctx.handle, ptr(g), ptr(xw), ptr(zw), g.size, float(vc4), ptr(x1), x1.size,
+                                               ptr(z1), z1.size, int(row0), int(nrows), _grid_density(x1, z1), int(order),
+                                               int(leaf), ptr(u), ptr(w), PTR_HOST,
+                                               stats.ctypes.data_as(_lib.c_dp) if return_stats else None))
+    return (u, w, _tree_stats(stats)) if return_stats else (u, w)
+
+
+def flowfield_velocity_tree_device(ctx, g, xw, zw, vc4, x1, z1, row0, nrows, u, w, tgt_density, order=18, leaf=0,
+                                   return_stats=False):
+    """Same with torch CUDA float64 tensors; `tgt_density` = grid points per unit area of the full grid."""
+    stats = np.zeros(8)
+    check(load().ludvm_flowfield_velocity_tree(ctx.handle, ptr(g), ptr(xw), ptr(zw), g.numel(), float(vc4), ptr(x1),
+                                               x1.numel(), ptr(z1), z1.numel(), int(row0), int(nrows), float(tgt_density),
+                                               int(order), int(leaf), ptr(u), ptr(w), PTR_DEVICE,
+                                               stats.ctypes.data_as(_lib.c_dp) if return_stats else None))
+    return _tree_stats(stats) if return_stats else None
+
+
 def selfconv_step_tree(ctx, g, x, z, vc4, dt, x_out, z_out, row0=0, nrows=None, u_out=None, w_out=None, order=18, leaf=0,
                        return_stats=False):
     """`selfconv_step` through the treecode (torch CUDA float64 tensors)."""

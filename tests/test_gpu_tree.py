@@ -125,3 +125,56 @@ def test_tree_bitwise_reproducible_and_shard_independent():
     assert np.array_equal(full_x.cpu().numpy(), x + 0.05 * a[0])
     assert ctx.last_plan()["kernel"] == "tree"
     ctx.close()
+
+
+def test_tree_refuses_a_cloud_that_is_one_point_and_handles_crowded_leaves():
+    from ludvm_b200 import _lib, ops
+    from oracle import ludvm_oracle as oracle
+    n = 70000
+    g = np.full(n + 2, 1e-3)
+    x, z = np.full(n + 2, -1.0), np.full(n + 2, 0.25)
+    x[-2:], z[-2:] = (-20.0, 0.0), (-4.0, 4.0)
+    with pytest.raises(_lib.LudvmError, match="too clustered"):
+        ops.induced_velocity_tree(g, x, z, x[-2:], z[-2:], VC)
+    # a tight Gaussian blob inside a sparse background: leaves with thousands of vortices, many passes per leaf
+    rng = np.random.default_rng(12)
+    gb, xb, zb = _cloud(40000, 13)
+    xc, zc = -7.0 + 0.01 * rng.standard_normal(20000), 1.0 + 0.01 * rng.standard_normal(20000)
+    g2, x2, z2 = np.concatenate([gb, 1e-3 * rng.standard_normal(20000)]), np.concatenate([xb, xc]), np.concatenate([zb, zc])
+    u, w, st = ops.induced_velocity_tree(g2, x2, z2, x2, z2, VC, return_stats=True)
+    sel = np.concatenate([rng.choice(40000, 150, replace=False), 40000 + rng.choice(20000, 150, replace=False)])
+    uo, wo = oracle.induced_velocity(g2, x2, z2, x2[sel], z2[sel], VC)
+    den = _sum_abs_terms(g2, x2, z2, x2[sel], z2[sel], VC ** 4)
+    assert np.max(np.hypot(u[sel] - uo, w[sel] - wo) / den) <= 1e-12, st
+
+
+def test_flowfield_grid_through_the_far_field_vs_oracle_and_slabs():
+    """Grid targets: cells holding more than (order+1)^2 grid points carry a local field even away from the sources; the
+    density comes from the full grid, so row slabs reproduce the full-grid values bit for bit."""
+    from ludvm_b200 import ops
+    from oracle import ludvm_oracle as oracle
+    g, x, z = _cloud(60000, 21)
+    x1, z1 = np.arange(-22.0, 2.0, 0.03), np.arange(-9.0, 9.0, 0.03)          # 800 x 600, extends far beyond the sources
+    u, w, st = ops.flowfield_velocity_tree(g, x, z, VC ** 4, x1, z1, return_stats=True)
+    assert u.shape == (len(x1), len(z1)) and st["pair_evaluations"] < 0.1 * st["all_pairs"]
+    rng = np.random.default_rng(5)
+    ii, jj = rng.integers(0, len(x1), 500), rng.integers(0, len(z1), 500)
+    uo, wo = oracle.induced_velocity(g, x, z, x1[ii], z1[jj], VC)
+    den = _sum_abs_terms(g, x, z, x1[ii], z1[jj], VC ** 4)
+    assert np.max(np.hypot(u[ii, jj] - uo, w[ii, jj] - wo) / den) <= 1e-12
+    for r0, nr in ((0, 300), (299, 2), (301, len(x1) - 301)):
+        us, ws = ops.flowfield_velocity_tree(g, x, z, VC ** 4, x1, z1, row0=r0, nrows=nr)
+        assert np.array_equal(us.view(np.uint64), u[r0:r0 + nr].view(np.uint64))
+        assert np.array_equal(ws.view(np.uint64), w[r0:r0 + nr].view(np.uint64))
+
+
+def test_class_flowfield_far_field_order():
+    from ludvm_b200 import LUDVM
+    kw = dict(t0=0, tf=3, dt=5e-2, chord=1, rho=1.225, Uinf=1, Npoints=81, Ncoeffs=30, LESPcrit=0.2, Naca="0012")
+    s = LUDVM(**kw, verbose=False, mode="fast")
+    s.flowfield(xmin=-3.0, xmax=0.5, zmin=-1.0, zmax=1.0, dr=0.02, tsteps=[0, 30, 59])
+    ua, wa, oa = s.u_ff.copy(), s.w_ff.copy(), s.ome_ff.copy()
+    s.flowfield(xmin=-3.0, xmax=0.5, zmin=-1.0, zmax=1.0, dr=0.02, tsteps=[0, 30, 59], far_field_order=18)
+    scale = np.max(np.abs(ua))
+    assert np.max(np.abs(s.u_ff - ua)) <= 1e-11 * scale and np.max(np.abs(s.w_ff - wa)) <= 1e-11 * scale
+    assert np.max(np.abs(s.ome_ff - oa)) <= 1e-8 * np.max(np.abs(oa))
