@@ -593,6 +593,33 @@ def flowfield_leg(env, steps, warmup, with_e2e):
            "parity": {"ok": bool(eu <= 1e-12 and ew <= 1e-12 and vort_ok), "points_checked": 256 * env.world,
                       "max_err_u_over_max_ref": eu, "max_err_w_over_max_ref": ew, "tolerance": 1e-12,
                       "vorticity_block_bitwise_vs_oracle_stencil": vort_ok}}
+    # the same slab through the hierarchical far field (csrc/tree.cu), reported separately: not pairs/s, an approximation
+    # of the same sums whose error against the oracle is part of the figure
+    ut, wt = torch.empty_like(u), torch.empty_like(w)
+    dens = 1.0 / (FF_DR * FF_DR)
+
+    def tree_step():
+        ops.flowfield_velocity_tree_device(ctx, g, xw, zw, vc4, x1, z1, h0, ne, ut, wt, dens, order=18)
+        check(load().ludvm_flowfield_vorticity(ctx.handle, ptr(x1s), ne, ptr(z1), nz, ptr(ut), ptr(wt), 1, ptr(ome), PTR_DEVICE))
+    tms = env.time_events(tree_step, 2, 1) / 2
+    st = ops.flowfield_velocity_tree_device(ctx, g, xw, zw, vc4, x1, z1, h0, ne, ut, wt, dens, order=18, return_stats=True)
+    torch.cuda.synchronize()
+    ut_h, wt_h = ut.cpu().numpy(), wt.cpu().numpy()
+    den = np.empty(len(ii))
+    ga = g.abs()
+    for k0 in range(0, len(ii), 32):
+        xs_, zs_ = x1[torch.as_tensor(ii[k0:k0 + 32], device=env.dev)], z1[torch.as_tensor(jj[k0:k0 + 32], device=env.dev)]
+        dx, dz = xs_[:, None] - xw[None, :], zs_[:, None] - zw[None, :]
+        r2 = dx * dx + dz * dz
+        den[k0:k0 + 32] = ((ga[None, :] * r2.sqrt() / (r2 * r2 + vc4).sqrt()).sum(1) / (2 * np.pi)).cpu().numpy()
+    terr = env.reduce(float(np.max(np.hypot(ut_h[ii - h0, jj] - uo, wt_h[ii - h0, jj] - wo) / den)))
+    evals = env.reduce(st["pair_evaluations"], "sum")
+    out["far_field"] = {"metric": "fmm_flowfield_ms_per_step", "order": 18, "ms_per_step": tms, "all_pairs_ms_per_step": ms,
+                        "speedup_vs_all_pairs": ms / tms, "pair_evaluations_per_step": evals,
+                        "pairs_left_frac": evals / pairs, "leaf_level": st["leaf_level"],
+                        "parity": {"ok": bool(terr <= 1e-12), "points_checked": 256 * env.world,
+                                   "max_err_over_sum_abs_terms": terr, "tolerance": 1e-12,
+                                   "checker": "oracle all-pairs sum (the reference has no far-field method)"}}
     if with_e2e:   # public host API: host sources/axes in, host u/w out, then the stencil on host fields
         t0 = time.perf_counter()
         uh, wh, omh = ops.flowfield(g_h, xw_h, zw_h, None, None, None, vc4, x1_h, z1_h, row0=h0, nrows=ne, mode="fast",

@@ -784,8 +784,11 @@ static size_t tree_layout(Arena &a, TreeBufs &b, long nw, long np, int L, int P2
 // [1] leaf side, [2] pair evaluations, [3] np * nw, [4] proxies per cell, [5] arena bytes; reading [2] synchronises.
 static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *xw, const double *zw, double vc4, long nw,
                                 const double *xp, const double *zp, long np_, int order, int leaf, double *u, double *w,
-                                double *stats, double tdens = 0.0)
+                                double *stats, double tdens = 0.0, const double *box_x = nullptr, const double *box_z = nullptr,
+                                int nbox = 0)
 {
+    // (box_x, box_z)[nbox]: points that span the targets' bounding box, used for it in place of the targets themselves --
+    // a slab of a grid passes the full grid's corners, so that every slab builds the tree of the full grid
     if (order <= 0) order = 18;
     if (order < 2 || order > TR_MAX_ORDER) return set_error(LUDVM_E_ARG, "tree order %d outside 2..%d", order, TR_MAX_ORDER);
     cudaStream_t st = ctx->stream;
@@ -797,7 +800,8 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
         unsigned long long init[8] = {~0ull, 0, ~0ull, 0, ~0ull, 0, ~0ull, 0};
         CUDA_TRY(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, st));
         const int blocks = (int)std::min<long>((nw + np_ + 1023) / 1024, (long)ctx->sm_count * 8);
-        k_tree_bbox<<<blocks, 256, 0, st>>>(xw, zw, (int)nw, xp, zp, (int)np_, mm);
+        if (nbox > 0) k_tree_bbox<<<blocks, 256, 0, st>>>(xw, zw, (int)nw, box_x, box_z, nbox, mm);
+        else k_tree_bbox<<<blocks, 256, 0, st>>>(xw, zw, (int)nw, xp, zp, (int)np_, mm);
         ctx->launches++;
         unsigned long long out[8];
         CUDA_TRY(cudaMemcpyAsync(out, mm, sizeof(out), cudaMemcpyDeviceToHost, st));
@@ -1006,10 +1010,13 @@ LUDVM_API int ludvm_selfconv_step_tree(ludvm_ctx *ctx, const double *gamma, cons
 
 namespace ludvm {
 // the 'ij' mesh rows [row0, row0 + nrows) of x1 x z1 as explicit target arrays
-__global__ void __launch_bounds__(256) k_tree_grid_points(const double *x1, const double *z1, int nz, int row0, long npts, double *xp,
-                                                          double *zp)
+__global__ void __launch_bounds__(256) k_tree_grid_points(const double *x1, int nx, const double *z1, int nz, int row0, long npts,
+                                                          double *xp, double *zp, double *box)
 {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {   // corners of the FULL grid: box[0..1] = x, box[2..3] = z
+        box[0] = x1[0]; box[1] = x1[nx - 1]; box[2] = z1[0]; box[3] = z1[nz - 1];
+    }
     if (i >= npts) return;
     const int r = (int)(i / nz), j = (int)(i - (long)r * nz);
     xp[i] = x1[row0 + r];
@@ -1051,11 +1058,12 @@ LUDVM_API int ludvm_flowfield_velocity_tree(ludvm_ctx *ctx, const double *ga, co
         dw = du + npts;
     }
     void *tp;
-    if ((rc = scratch_reserve(ctx, 6, 2 * (size_t)npts * sizeof(double), &tp))) return rc;
-    double *xp = (double *)tp, *zp = xp + npts;
-    k_tree_grid_points<<<ceil_div(npts, 256), 256, 0, ctx->stream>>>(dx1, dz1, (int)nz, (int)row0, npts, xp, zp);
+    if ((rc = scratch_reserve(ctx, 6, (2 * (size_t)npts + 4) * sizeof(double), &tp))) return rc;
+    double *xp = (double *)tp, *zp = xp + npts, *box = zp + npts;
+    k_tree_grid_points<<<ceil_div(npts, 256), 256, 0, ctx->stream>>>(dx1, (int)nx, dz1, (int)nz, (int)row0, npts, xp, zp, box);
     ctx->launches++;
-    if ((rc = tree_velocity_device(ctx, dga, dxa, dza, vc4, na, xp, zp, npts, order, leaf, du, dw, stats, tgt_density))) return rc;
+    if ((rc = tree_velocity_device(ctx, dga, dxa, dza, vc4, na, xp, zp, npts, order, leaf, du, dw, stats, tgt_density, box, box + 2, 2)))
+        return rc;
     if (ptr_kind == LUDVM_PTR_HOST) {
         CUDA_TRY(cudaMemcpyAsync(u, du, (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaMemcpyAsync(w, dw, (size_t)npts * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
