@@ -17,4 +17,10 @@ python scripts/run_configs.py --only 1,2,4 --out $out/${tag}_configs.json > $out
 python scripts/ncu_fast_driver.py 1048576 > $out/${tag}_plain_fused.txt 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_fast_fused -s 1 -c 1 -o $out/${tag}_k_fast_fused -f python scripts/ncu_fast_driver.py 1048576 > $out/${tag}_ncu_fused.log 2>&1
 cat $out/${tag}_plain_fused.txt
+# far-field path: probe (time / pairs left / error), launch list and one full capture of the evaluation kernel
+PROBE_ORDERS=12,14,16,18 python scripts/tree_probe.py 18 20 22 24 > $out/${tag}_tree_probe.txt 2>&1; cut -c1-200 $out/${tag}_tree_probe.txt
+python scripts/ff_tree_probe.py > $out/${tag}_ff_tree_probe.txt 2>&1
+python scripts/tree_ncu_driver.py 20 18 > $out/${tag}_plain_tree.txt 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $out/${tag}_tree_launches.csv python scripts/tree_ncu_driver.py 20 18 > /dev/null 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_tree_eval -s 1 -c 1 -o $out/${tag}_k_tree_eval -f python scripts/tree_ncu_driver.py 20 18 > $out/${tag}_ncu_tree.log 2>&1
 ls -la $out | tail -14
