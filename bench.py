@@ -466,8 +466,11 @@ def tree_leg(env, n, order, steps, warmup, rows_checked, all_pairs_ms=None):
     from ludvm_b200.sharded import ShardedSelfConvection
     from oracle import ludvm_oracle as oracle
     torch, world, rank, ctx = env.torch, env.world, env.rank, env.ctx
+    from ludvm_b200.sharded import morton_order
     shard, row0 = n // world, rank * (n // world)
     g_h, x_h, z_h = make_cloud(n)
+    perm = morton_order(x_h, z_h)          # the same cloud relabelled along the Z-order curve: row shards compact in space
+    g_h, x_h, z_h = (np.ascontiguousarray(a[perm]) for a in (g_h, x_h, z_h))
     g, x, z = (torch.tensor(a, device=env.dev) for a in (g_h, x_h, z_h))
     sc = ShardedSelfConvection(g, x.clone(), z.clone(), VCORE, DT, mode="tree", ctx=ctx, transport="nccl", order=order)
     for _ in range(warmup):
