@@ -505,6 +505,7 @@ def tree_leg(env, n, order, steps, warmup, rows_checked, all_pairs_ms=None):
            "gpu_launches": int(launches), "leaf_level": st["leaf_level"], "proxies_per_cell": st["proxies_per_cell"],
            "pair_evaluations_per_step": evals, "pairs_left_frac": evals / (float(n) * n),
            "eval_pairs_per_s": evals / (ms * 1e-3), "all_pairs_equivalent_pairs_per_s": float(n) * n / (ms * 1e-3),
+           "frac_of_dfma_rate_whole_step": evals / (ms * 1e-3) / world * SLOTS_PER_PAIR / ctx.fp64_fma_rate(100.0),
            "build_ms_this_rank": st["build_ms"], "eval_ms_this_rank": st["eval_ms"], "arena_bytes": st["arena_bytes"],
            "parity": {"ok": bool(err <= 1e-12 and euler), "rows_checked": int(len(rows)) * world,
                       "max_err_over_sum_abs_terms": err, "tolerance": 1e-12, "euler_update_bitwise": euler,

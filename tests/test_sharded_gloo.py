@@ -155,3 +155,39 @@ def test_slab_and_case_partitions(oracle, world):
             _, _, ome = _ff_eval(oracle, g, xw, zw, x1[h0:h1], z1)
             assert np.array_equal(ome[r0 - h0:r1 - h0], oms[r0:r1])
     assert rows[0][0] == 0 and rows[-1][1] == FF_NX and all(a[1] == b[0] for a, b in zip(rows, rows[1:]))
+
+
+def test_morton_order_is_a_permutation_that_makes_row_shards_compact():
+    """sharded.morton_order (used to relabel a cloud before a sharded far-field run): a permutation; the first eighth of
+    the relabelled cloud covers about an eighth of the area instead of all of it."""
+    from ludvm_b200.sharded import morton_order
+    rng = np.random.default_rng(3)
+    x, z = rng.uniform(-20, 0, 40000), rng.uniform(-4, 4, 40000)
+    p = morton_order(x, z)
+    assert sorted(p.tolist()) == list(range(40000))
+    xs, zs = x[p][:5000], z[p][:5000]
+    assert np.ptp(xs) * np.ptp(zs) < 0.3 * 160.0
+    assert np.ptp(x[:5000]) * np.ptp(z[:5000]) > 0.9 * 160.0
+
+
+def test_far_field_model_matches_direct_summation():
+    """scripts/tree_proto.py is the numpy model of csrc/tree.cu's representation (same tree, lists and nested Chebyshev
+    proxies): against direct summation it must show the orders' accuracy that DESIGN.md section 4b quotes."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location(
+        "tree_proto", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "scripts", "tree_proto.py"))
+    tp = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tp)
+    rng = np.random.default_rng(5)
+    n = 6000
+    g, x, z = rng.standard_normal(n) * 1e-2, rng.uniform(-20, 0, n), rng.uniform(-4, 4, n)
+    vc4 = 0.065 ** 4
+    sel = rng.choice(n, 200, replace=False)
+    ud, wd = tp.direct(x[sel], z[sel], x, z, g, vc4)
+    den = np.array([np.sum(np.abs(g) * np.hypot(x[i] - x, z[i] - z) / np.sqrt(((x[i] - x) ** 2 + (z[i] - z) ** 2) ** 2 + vc4))
+                    for i in sel])
+    for order, tol in ((8, 1e-6), (14, 1e-10)):
+        u, w, st = tp.tree_velocity(g, x, z, x[sel], z[sel], vc4, p=order, leaf=16, L=5)
+        assert st["proxy_cells"] > 0
+        assert np.max(np.hypot(u - ud, w - wd) / den) <= tol
