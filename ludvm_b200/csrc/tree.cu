@@ -403,6 +403,7 @@ struct TreeEval {
     double *uloc, *wloc;                   // local fields, laid out like qhat
     unsigned long long *pairs;             // pair evaluations (diagnostic)
     int fmm, np;                           // 0: pure treecode (every far list evaluated at the targets)
+    int gemm;                              // 1: proxy cells of the M2L lists are applied by k_tree_m2l_gemm, not here
 };
 
 struct TreeSmem {
@@ -478,7 +479,7 @@ __device__ __forceinline__ void tree_fetch(const TreeGeom &G, const TreeEval &A,
 // of levels lmin .. lmax <= lc (a coarser level's list is the ancestor's).  Every candidate has a fixed slot, so the list
 // order (= the summation order) never depends on scheduling; empty slots are dropped afterwards, order kept.
 __device__ __forceinline__ int tree_build_list(const TreeGeom &G, const TreeEval &A, int cx, int cz, int lc, bool near, int lmin,
-                                               int lmax, TreeSmem &sm)
+                                               int lmax, TreeSmem &sm, bool skip_proxies = false)
 {
     const int tid = threadIdx.x, lane = tid & 31, L = G.L, P2 = G.P2;
     const int nslots = 9 + 36 * (L - 1);
@@ -501,7 +502,7 @@ __device__ __forceinline__ int tree_build_list(const TreeGeom &G, const TreeEval
                     if (max(abs(jx - cxl), abs(jz - czl)) > 1) {
                         const int cc = morton2(jx, jz), sh = 2 * (L - l);
                         const int b = A.startS[(long)cc << sh], n = A.startS[((long)cc + 1) << sh] - b;
-                        if (n > P2) { a = cc; len = P2; lvl = l; }
+                        if (n > P2) { a = cc; len = skip_proxies ? 0 : P2; lvl = l; }
                         else { a = b; len = n; }
                     }
                 }
@@ -643,7 +644,7 @@ __global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_consta
         if (A.startT[((long)c + 1) << sh] == A.startT[(long)c << sh]) return;           // none of this rank's targets below
         if ((int)blockIdx.y >= (((P2 + TE_THREADS - 1) / TE_THREADS + 3) >> 2)) return;
         const int cx = (int)compact16((unsigned)c), cz = (int)compact16((unsigned)c >> 1);
-        const int total = tree_build_list(G, A, cx, cz, l, false, l, l, sm);
+        const int total = tree_build_list(G, A, cx, cz, l, false, l, l, sm, A.gemm != 0);
         const double h = ldexp(G.side, -(l + 1));
         const long off = (level_offset(l) + c) * P2;
         TgtNodePts T{G.x0 + (2.0 * cx + 1.0) * h, G.z0 + (2.0 * cz + 1.0) * h, h, G.s, G.P1, A.uloc + off, A.wloc + off};
@@ -660,6 +661,181 @@ __global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_consta
     if (threadIdx.x == 0 && blockIdx.y == 0 && A.pairs) atomicAdd(A.pairs, (unsigned long long)(te - tb) * (unsigned long long)total);
     TgtLeafPts T{A.permT, A.xt, A.zt, A.u, A.w};
     tree_eval_item(G, A, T, sm, tb, te, total);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// M2L between proxy cells as matrix products.  The proxies of a cell sit at fixed points of the cell, so the velocity
+// that the P2 proxies of cell B induce at the P2 points of cell A of the same level depends on the cells' offset
+// (dx, dz) in [-3, 3]^2 only: U_A += Mu[l][off] q_B, W_A += Mw[l][off] q_B with two P2 x P2 matrices per level and offset
+// (per level: the core radius does not scale with the cells).  An entry costs one DFMA per component instead of the 13
+// slots + MUFU of a pair evaluation, and a matrix is shared by every pair of cells with that offset: a CTA owns a
+// (TM_TI points) x (TM_TC cells) tile of the local fields of one level, walks the 40 offsets and the P2 proxies with
+// register-tiled outer products, tiles of the matrices and of the proxy strengths prefetched into registers while the
+// previous ones are consumed.  Lists entries that are plain vortices (cells with <= P2 of them) stay with k_tree_eval.
+// The order of the sums is fixed (offsets, then proxies, ascending), whatever tile a cell lands in.
+// ---------------------------------------------------------------------------------------------------
+#define TM_NOFF 49
+#define TM_TI 32
+#define TM_TC 64
+#define TM_JC 16
+
+// matrices [level - 2][off][j][i], i fastest
+__global__ void __launch_bounds__(128) k_tree_m2l_mats(const __grid_constant__ TreeGeom G, double *Mu, double *Mw)
+{
+    const int j = blockIdx.x, off = blockIdx.y, l = 2 + blockIdx.z, P1 = G.P1, P2 = G.P2;
+    const int dx = off % 7 - 3, dz = off / 7 - 3;
+    if (max(abs(dx), abs(dz)) <= 1) return;
+    const double h = ldexp(G.side, -(l + 1));
+    const int j1 = j / P1, j2 = j - j1 * P1;
+    const double xs = fma(h, G.s[j1], 2.0 * h * dx), zs = fma(h, G.s[j2], 2.0 * h * dz);   // relative to A's centre
+    const size_t base = (((size_t)(l - 2) * TM_NOFF + off) * P2 + j) * P2;
+    for (int i = threadIdx.x; i < P2; i += blockDim.x) {
+        const int i1 = i / P1, i2 = i - i1 * P1;
+        double u = 0.0, w = 0.0;
+        pair_fast(h * G.s[i1], h * G.s[i2], xs, zs, 1.0, G.vc4, u, w);
+        Mu[base + i] = u;
+        Mw[base + i] = w;
+    }
+}
+
+// Cells of every level that carry a local field and have targets of this rank beneath them, one list per level and per
+// parity (ax & 1, az & 1) of the cell in its parent: cells of one parity share the 27 valid offsets of the 49, so a tile
+// of them does no wasted products.  Any order inside a list: a cell's result does not depend on its neighbours in it.
+__global__ void __launch_bounds__(256) k_tree_alist(const __grid_constant__ TreeGeom G, const int *startS, const int *startT,
+                                                    int *alist, int *acount)
+{
+    const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= level_offset(G.L + 1)) return;
+    int l = 2;
+    while (level_offset(l + 1) <= b) l++;
+    const long c = b - level_offset(l);
+    const int sh = 2 * (G.L - l);
+    if (!tree_has_local(G, startS, l, c)) return;
+    if (startT[(c + 1) << sh] == startT[c << sh]) return;
+    const int par = (int)(c & 3);                                     // Morton: bit 0 = ax & 1, bit 1 = az & 1
+    alist[level_offset(l) + ((long)par << (2 * (l - 1))) + atomicAdd(acount + 4 * l + par, 1)] = (int)c;
+}
+
+__global__ void __launch_bounds__(256, 2) k_tree_m2l_gemm(const __grid_constant__ TreeGeom G, const int *startS, const int *alist,
+                                                          const int *acount, const double *Mu, const double *Mw,
+                                                          const double *qhat, double *uloc, double *wloc)
+{
+    // blockIdx.y -> (level, parity, cell tile): level l owns 4 x ceil(4^(l-1) / TM_TC) tiles
+    const int P2 = G.P2, tid = threadIdx.x;
+    int l = 2, tile = blockIdx.y, ntp;
+    for (;; l++) {
+        ntp = (int)(((1L << (2 * (l - 1))) + TM_TC - 1) / TM_TC);
+        if (tile < 4 * ntp) break;
+        tile -= 4 * ntp;
+    }
+    const int par = tile / ntp;
+    tile -= par * ntp;
+    const int nA = acount[4 * l + par];
+    if (tile * TM_TC >= nA) return;
+    const long abase = level_offset(l) + ((long)par << (2 * (l - 1)));
+    const int i0 = blockIdx.x * TM_TI;
+    __shared__ int Acell[TM_TC], Bcell[TM_TC];
+    __shared__ __align__(16) double sMu[TM_JC][TM_TI], sMw[TM_JC][TM_TI], sQ[TM_JC][TM_TC + 2];   // (+2: the stores of a
+                                                                        // strength tile walk down a column of sQ)
+    const int ti = tid & 15, tc = tid >> 4;              // thread tile: points i0 + 2 ti + {0, 1}, cells 4 tc + {0..3}
+    double au[2][4], aw[2][4];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) au[a][b] = aw[a][b] = 0.0;
+    if (tid < TM_TC) Acell[tid] = tile * TM_TC + tid < nA ? alist[abase + tile * TM_TC + tid] : -1;
+    const double *Ml_u = Mu + (size_t)(l - 2) * TM_NOFF * P2 * P2, *Ml_w = Mw + (size_t)(l - 2) * TM_NOFF * P2 * P2;
+    const double *ql = qhat + level_offset(l) * P2;
+    const int sh = 2 * (G.L - l), nc = 1 << l;
+    // loader roles: matrices -- element e = tid + 256 q (q < 2) of a TM_JC x TM_TI tile (i fastest); strengths -- element
+    // e = tid + 256 q (q < 4) of a TM_TC x TM_JC tile (j fastest inside a cell)
+    for (int off = 0; off < TM_NOFF; off++) {
+        const int dx = off % 7 - 3, dz = off / 7 - 3;
+        if (max(abs(dx), abs(dz)) <= 1) continue;
+        // B's parent must be a neighbour of A's parent: dx in [-2 - px, 3 - px] for the parity px of A, likewise dz
+        if (dx < -2 - (par & 1) || dx > 3 - (par & 1) || dz < -2 - (par >> 1) || dz > 3 - (par >> 1)) continue;
+        __syncthreads();                                   // the previous offset's tiles and Bcell are no longer read
+        if (tid < TM_TC) {
+            int bcell = -1;
+            const int a = Acell[tid];
+            if (a >= 0) {
+                const int ax = (int)compact16((unsigned)a), az = (int)compact16((unsigned)a >> 1), bx = ax + dx, bz = az + dz;
+                if (bx >= 0 && bz >= 0 && bx < nc && bz < nc && abs((bx >> 1) - (ax >> 1)) <= 1 && abs((bz >> 1) - (az >> 1)) <= 1) {
+                    const long bc = morton2(bx, bz);
+                    if (startS[(bc + 1) << sh] - startS[bc << sh] > P2) bcell = (int)bc;
+                }
+            }
+            Bcell[tid] = bcell;
+        }
+        const int any = __syncthreads_or(tid < TM_TC && Bcell[tid] >= 0);
+        if (!any) continue;
+        const double *Mo_u = Ml_u + (size_t)off * P2 * P2, *Mo_w = Ml_w + (size_t)off * P2 * P2;
+        double pmu[2], pmw[2], pq[4];
+        auto fetch = [&](int j0) {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int e = tid + 256 * q, jj = e / TM_TI, ii = e - jj * TM_TI, j = j0 + jj, i = i0 + ii;
+                const bool ok = j < P2 && i < P2;
+                pmu[q] = ok ? Mo_u[(size_t)j * P2 + i] : 0.0;
+                pmw[q] = ok ? Mo_w[(size_t)j * P2 + i] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int e = tid + 256 * q, cc = e / TM_JC, jj = e - cc * TM_JC, j = j0 + jj, bcell = Bcell[cc];
+                pq[q] = (bcell >= 0 && j < P2) ? ql[(size_t)bcell * P2 + j] : 0.0;
+            }
+        };
+        auto put = [&]() {
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int e = tid + 256 * q, jj = e / TM_TI, ii = e - jj * TM_TI;
+                sMu[jj][ii] = pmu[q];
+                sMw[jj][ii] = pmw[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int e = tid + 256 * q, cc = e / TM_JC, jj = e - cc * TM_JC;
+                sQ[jj][cc] = pq[q];
+            }
+        };
+        fetch(0);
+        for (int j0 = 0; j0 < P2; j0 += TM_JC) {
+            __syncthreads();                               // the previous chunk has been consumed
+            put();
+            __syncthreads();
+            if (j0 + TM_JC < P2) fetch(j0 + TM_JC);        // in flight during the products
+#pragma unroll
+            for (int jj = 0; jj < TM_JC; jj++) {
+                const double2 mu = *reinterpret_cast<const double2 *>(&sMu[jj][2 * ti]);
+                const double2 mw = *reinterpret_cast<const double2 *>(&sMw[jj][2 * ti]);
+                const double2 qa = *reinterpret_cast<const double2 *>(&sQ[jj][4 * tc]);
+                const double2 qb = *reinterpret_cast<const double2 *>(&sQ[jj][4 * tc + 2]);
+                const double q4[4] = {qa.x, qa.y, qb.x, qb.y};
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    au[0][b] = fma(mu.x, q4[b], au[0][b]);
+                    au[1][b] = fma(mu.y, q4[b], au[1][b]);
+                    aw[0][b] = fma(mw.x, q4[b], aw[0][b]);
+                    aw[1][b] = fma(mw.y, q4[b], aw[1][b]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int b = 0; b < 4; b++) {
+        const int a = Acell[4 * tc + b];
+        if (a < 0) continue;
+        const size_t o = (size_t)(level_offset(l) + a) * P2;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const int i = i0 + 2 * ti + k;
+            if (i < P2) {
+                uloc[o + i] += au[k][b];       // (k_tree_eval stored the list's plain-vortex part, or zero, before)
+                wloc[o + i] += aw[k][b];
+            }
+        }
+    }
 }
 
 // L2L: the parent's local field interpolated to the points of child cell c of level l (l >= 3), added to the child's M2L sums
@@ -761,10 +937,12 @@ struct Arena {
 struct TreeBufs {
     int *keyS, *slotS, *keyT, *slotT, *cntS, *cntT, *startS, *startT, *tmpS, *permS, *tmpT, *permT;
     double *xs, *zs, *gs, *qhat, *uloc, *wloc;
+    double *Mu, *Mw;   // M2L matrices [L - 1][TM_NOFF][P2][P2]
+    int *alist, *acount;
     unsigned long long *pairs;
     int *maxcnt;   // [2]: largest leaf population, sources / targets
 };
-static size_t tree_layout(Arena &a, TreeBufs &b, long nw, long np, int L, int P2, bool fmm)
+static size_t tree_layout(Arena &a, TreeBufs &b, long nw, long np, int L, int P2, bool fmm, bool gemm)
 {
     const size_t ncell = (size_t)1 << (2 * L);
     b.keyS = a.take<int>(nw); b.slotS = a.take<int>(nw); b.keyT = a.take<int>(np); b.slotT = a.take<int>(np);
@@ -775,6 +953,10 @@ static size_t tree_layout(Arena &a, TreeBufs &b, long nw, long np, int L, int P2
     b.qhat = a.take<double>((size_t)level_offset(L + 1) * P2);
     b.uloc = a.take<double>(fmm ? (size_t)level_offset(L + 1) * P2 : 1);
     b.wloc = a.take<double>(fmm ? (size_t)level_offset(L + 1) * P2 : 1);
+    b.Mu = a.take<double>(gemm ? (size_t)(L - 1) * TM_NOFF * P2 * P2 : 1);
+    b.Mw = a.take<double>(gemm ? (size_t)(L - 1) * TM_NOFF * P2 * P2 : 1);
+    b.alist = a.take<int>(gemm ? (size_t)level_offset(L + 1) : 1);
+    b.acount = a.take<int>(64);
     b.pairs = a.take<unsigned long long>(1);
     b.maxcnt = a.take<int>(2);
     return a.off;
@@ -838,10 +1020,11 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
         Arena sizer{nullptr};
         TreeBufs B;
         const bool fmm = !getenv("LUDVM_TREE_NO_FMM");
-        const size_t bytes = tree_layout(sizer, B, nw, np_, L, P2, fmm);
+        const bool gemm = fmm && !getenv("LUDVM_TREE_NO_GEMM");
+        const size_t bytes = tree_layout(sizer, B, nw, np_, L, P2, fmm, gemm);
         if ((rc = scratch_reserve(ctx, 8, bytes, &p))) return rc;
         Arena ar{(char *)p};
-        tree_layout(ar, B, nw, np_, L, P2, fmm);
+        tree_layout(ar, B, nw, np_, L, P2, fmm, gemm);
         const int ncell = 1 << (2 * L);
         CUDA_TRY(cudaMemsetAsync(B.cntS, 0, (size_t)(ncell + 1) * sizeof(int), st));
         CUDA_TRY(cudaMemsetAsync(B.cntT, 0, (size_t)(ncell + 1) * sizeof(int), st));
@@ -889,7 +1072,7 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
             ctx->launches++;
         }
         TreeEval A = {B.startS, B.startT, B.permT, B.keyT, B.xs, B.zs, B.gs, B.qhat, xp, zp, u, w, B.uloc, B.wloc, B.pairs,
-                      fmm ? 1 : 0, (int)np_};
+                      fmm ? 1 : 0, (int)np_, gemm ? 1 : 0};
         cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
         if (stats) {
             for (int k = 1; k < 3; k++) CUDA_TRY(cudaEventCreate(&ev[k]));
@@ -902,6 +1085,16 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
         if (const char *ye = getenv("LUDVM_TREE_YSPLIT")) ysplit = std::max(1, std::min(64, atoi(ye)));
         k_tree_eval<<<dim3((unsigned)items, ysplit), TE_THREADS, 0, st>>>(G, A);
         ctx->launches++;
+        if (gemm) {
+            CUDA_TRY(cudaMemsetAsync(B.acount, 0, 64 * sizeof(int), st));
+            k_tree_m2l_mats<<<dim3(P2, TM_NOFF, L - 1), 128, 0, st>>>(G, B.Mu, B.Mw);
+            k_tree_alist<<<ceil_div(level_offset(L + 1), 256), 256, 0, st>>>(G, B.startS, B.startT, B.alist, B.acount);
+            long tiles = 0;
+            for (int l = 2; l <= L; l++) tiles += 4 * (((1L << (2 * (l - 1))) + TM_TC - 1) / TM_TC);
+            k_tree_m2l_gemm<<<dim3((P2 + TM_TI - 1) / TM_TI, (unsigned)tiles), 256, 0, st>>>(G, B.startS, B.alist, B.acount, B.Mu,
+                                                                                             B.Mw, B.qhat, B.uloc, B.wloc);
+            ctx->launches += 3;
+        }
         if (fmm) {
             for (int l = 3; l <= L; l++) {
                 k_tree_l2l<<<1 << (2 * l), 256, 0, st>>>(G, l, B.startS, B.startT, B.uloc, B.wloc);
