@@ -673,6 +673,10 @@ __global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_consta
 // register-tiled outer products, tiles of the matrices and of the proxy strengths prefetched into registers while the
 // previous ones are consumed.  Lists entries that are plain vortices (cells with <= P2 of them) stay with k_tree_eval.
 // The order of the sums is fixed (offsets, then proxies, ascending), whatever tile a cell lands in.
+// The kernel is bound by the L2 -> SM traffic of its tiles, not by the FP64 pipe (a 32 x 64 tile does 4 DFMA per byte
+// loaded; 2^20 vortices: 1.15e10 DFMA in 2.8 ms = 24 % of the DFMA rate).  Measured and dropped: 4 x 4 thread tiles with
+// 64 x 32 or 64 x 64 CTA tiles (fewer LDS per DFMA, but 160 registers: 3.2 / 4.1 ms; profiles/r03f_*).  What it wants is
+// the matrix tile multicast to a cluster of CTAs that work on different cells (cp.async.bulk multicast): not built.
 // ---------------------------------------------------------------------------------------------------
 #define TM_NOFF 49
 #define TM_TI 32
