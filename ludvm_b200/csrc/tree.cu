@@ -673,10 +673,13 @@ __global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_consta
 // register-tiled outer products, tiles of the matrices and of the proxy strengths prefetched into registers while the
 // previous ones are consumed.  Lists entries that are plain vortices (cells with <= P2 of them) stay with k_tree_eval.
 // The order of the sums is fixed (offsets, then proxies, ascending), whatever tile a cell lands in.
-// The kernel is bound by the L2 -> SM traffic of its tiles, not by the FP64 pipe (a 32 x 64 tile does 4 DFMA per byte
-// loaded; 2^20 vortices: 1.15e10 DFMA in 2.8 ms = 24 % of the DFMA rate).  Measured and dropped: 4 x 4 thread tiles with
-// 64 x 32 or 64 x 64 CTA tiles (fewer LDS per DFMA, but 160 registers: 3.2 / 4.1 ms; profiles/r03f_*).  What it wants is
-// the matrix tile multicast to a cluster of CTAs that work on different cells (cp.async.bulk multicast): not built.
+// The kernel is bound by shared-memory bandwidth, not by the FP64 pipe (ncu, profiles/r03g_k_tree_m2l_gemm_*: l1tex 85 %
+// busy, FP64 45 %, top stall short scoreboard): a 2 x 4 thread tile reads 64 bytes of operands per 16 DFMA = 4 bytes
+// per DFMA, and the SM returns 128 bytes per clock for 64 FP64 lanes, i.e. 2 bytes per DFMA at full rate.  2^20 vortices:
+// 1.15e10 DFMA in 2.8 ms.  Measured and dropped (profiles/r03f_*, r03h_*, r03i_*): 4 x 4 thread tiles (3 bytes per DFMA)
+// as 64 x 32 CTA tiles with 128 threads, 64 x 64 with 256 threads at one or two CTAs per SM: 3.2 / 4.8 / 3.5 ms; a lane
+// map with fewer wavefronts per LDS: no change (the limit is bytes returned, not wavefronts).  What it wants is the FP64
+// tensor-core path (mma.sync m8n8k4.f64 with warp-level register reuse): not built.
 // ---------------------------------------------------------------------------------------------------
 #define TM_NOFF 49
 #define TM_TI 32
@@ -836,134 +839,6 @@ __global__ void __launch_bounds__(256, 2) k_tree_m2l_gemm(const __grid_constant_
             const int i = i0 + 2 * ti + k;
             if (i < P2) {
                 uloc[o + i] += au[k][b];       // (k_tree_eval stored the list's plain-vortex part, or zero, before)
-                wloc[o + i] += aw[k][b];
-            }
-        }
-    }
-}
-
-// Variant with 4 (points) x 4 (cells) thread tiles: THREADS = (TI / 4) x (TC / 4); a warp covers 8 point groups x 4 cell
-// groups, so a matrix fragment is shared by 4 lanes and a strength fragment by 8: 6 LDS wavefronts per 32 DFMA instead of
-// 6 per 16 (the 2 x 4 version above is bound by the shared-memory pipe: l1tex 85 % busy, FP64 45 %).
-template <int THREADS, int TI, int TC, int JC, int MINB>
-__global__ void __launch_bounds__(THREADS, MINB) k_tree_m2l_gemm44(const __grid_constant__ TreeGeom G, const int *startS,
-                                                                   const int *alist, const int *acount, const double *Mu,
-                                                                   const double *Mw, const double *qhat, double *uloc, double *wloc)
-{
-    static_assert(THREADS == (TI / 4) * (TC / 4), "thread tile is 4 x 4");
-    constexpr int MPT = JC * TI / THREADS, QPT = JC * TC / THREADS;
-    const int P2 = G.P2, tid = threadIdx.x;
-    int l = 2, tile = blockIdx.y, ntp;
-    for (;; l++) {
-        ntp = (int)(((1L << (2 * (l - 1))) + TC - 1) / TC);
-        if (tile < 4 * ntp) break;
-        tile -= 4 * ntp;
-    }
-    const int par = tile / ntp;
-    tile -= par * ntp;
-    const int nA = acount[4 * l + par];
-    if (tile * TC >= nA) return;
-    const long abase = level_offset(l) + ((long)par << (2 * (l - 1)));
-    const int i0 = blockIdx.x * TI;
-    __shared__ int Acell[TC], Bcell[TC];
-    __shared__ __align__(16) double sMu[JC][TI], sMw[JC][TI], sQ[JC][TC + 2];
-    const int warp = tid >> 5, lane = tid & 31;
-    const int ig = (warp % (TI / 32)) * 8 + (lane & 7), cg = (warp / (TI / 32)) * 4 + (lane >> 3);
-    double au[4][4], aw[4][4];
-#pragma unroll
-    for (int a = 0; a < 4; a++)
-#pragma unroll
-        for (int b = 0; b < 4; b++) au[a][b] = aw[a][b] = 0.0;
-    for (int t = tid; t < TC; t += THREADS) Acell[t] = tile * TC + t < nA ? alist[abase + tile * TC + t] : -1;
-    const double *Ml_u = Mu + (size_t)(l - 2) * TM_NOFF * P2 * P2, *Ml_w = Mw + (size_t)(l - 2) * TM_NOFF * P2 * P2;
-    const double *ql = qhat + level_offset(l) * P2;
-    const int sh = 2 * (G.L - l), nc = 1 << l;
-    __syncthreads();
-    for (int off = 0; off < TM_NOFF; off++) {
-        const int dx = off % 7 - 3, dz = off / 7 - 3;
-        if (max(abs(dx), abs(dz)) <= 1) continue;
-        if (dx < -2 - (par & 1) || dx > 3 - (par & 1) || dz < -2 - (par >> 1) || dz > 3 - (par >> 1)) continue;
-        __syncthreads();
-        int mine = 0;
-        for (int t = tid; t < TC; t += THREADS) {
-            int bcell = -1;
-            const int a = Acell[t];
-            if (a >= 0) {
-                const int ax = (int)compact16((unsigned)a), az = (int)compact16((unsigned)a >> 1), bx = ax + dx, bz = az + dz;
-                if (bx >= 0 && bz >= 0 && bx < nc && bz < nc) {
-                    const long bc = morton2(bx, bz);
-                    if (startS[(bc + 1) << sh] - startS[bc << sh] > P2) bcell = (int)bc;
-                }
-            }
-            Bcell[t] = bcell;
-            mine |= bcell >= 0;
-        }
-        if (!__syncthreads_or(mine)) continue;
-        const double *Mo_u = Ml_u + (size_t)off * P2 * P2, *Mo_w = Ml_w + (size_t)off * P2 * P2;
-        double pmu[MPT], pmw[MPT], pq[QPT];
-        auto fetch = [&](int j0) {
-#pragma unroll
-            for (int q = 0; q < MPT; q++) {
-                const int e = tid + THREADS * q, jj = e / TI, ii = e - jj * TI, j = j0 + jj, i = i0 + ii;
-                const bool ok = j < P2 && i < P2;
-                pmu[q] = ok ? Mo_u[(size_t)j * P2 + i] : 0.0;
-                pmw[q] = ok ? Mo_w[(size_t)j * P2 + i] : 0.0;
-            }
-#pragma unroll
-            for (int q = 0; q < QPT; q++) {
-                const int e = tid + THREADS * q, cc = e / JC, jj = e - cc * JC, j = j0 + jj, bcell = Bcell[cc];
-                pq[q] = (bcell >= 0 && j < P2) ? ql[(size_t)bcell * P2 + j] : 0.0;
-            }
-        };
-        auto put = [&]() {
-#pragma unroll
-            for (int q = 0; q < MPT; q++) {
-                const int e = tid + THREADS * q, jj = e / TI, ii = e - jj * TI;
-                sMu[jj][ii] = pmu[q];
-                sMw[jj][ii] = pmw[q];
-            }
-#pragma unroll
-            for (int q = 0; q < QPT; q++) {
-                const int e = tid + THREADS * q, cc = e / JC, jj = e - cc * JC;
-                sQ[jj][cc] = pq[q];
-            }
-        };
-        fetch(0);
-        for (int j0 = 0; j0 < P2; j0 += JC) {
-            __syncthreads();
-            put();
-            __syncthreads();
-            if (j0 + JC < P2) fetch(j0 + JC);
-#pragma unroll
-            for (int jj = 0; jj < JC; jj++) {
-                const double2 m0 = *reinterpret_cast<const double2 *>(&sMu[jj][4 * ig]);
-                const double2 m1 = *reinterpret_cast<const double2 *>(&sMu[jj][4 * ig + 2]);
-                const double2 n0 = *reinterpret_cast<const double2 *>(&sMw[jj][4 * ig]);
-                const double2 n1 = *reinterpret_cast<const double2 *>(&sMw[jj][4 * ig + 2]);
-                const double2 qa = *reinterpret_cast<const double2 *>(&sQ[jj][4 * cg]);
-                const double2 qb = *reinterpret_cast<const double2 *>(&sQ[jj][4 * cg + 2]);
-                const double mu[4] = {m0.x, m0.y, m1.x, m1.y}, mw[4] = {n0.x, n0.y, n1.x, n1.y}, q4[4] = {qa.x, qa.y, qb.x, qb.y};
-#pragma unroll
-                for (int a = 0; a < 4; a++)
-#pragma unroll
-                    for (int b = 0; b < 4; b++) {
-                        au[a][b] = fma(mu[a], q4[b], au[a][b]);
-                        aw[a][b] = fma(mw[a], q4[b], aw[a][b]);
-                    }
-            }
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-        const int a = Acell[4 * cg + b];
-        if (a < 0) continue;
-        const size_t o = (size_t)(level_offset(l) + a) * P2;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int i = i0 + 4 * ig + k;
-            if (i < P2) {
-                uloc[o + i] += au[k][b];
                 wloc[o + i] += aw[k][b];
             }
         }
@@ -1223,14 +1098,6 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
             k_tree_alist<<<ceil_div(level_offset(L + 1), 256), 256, 0, st>>>(G, B.startS, B.startT, B.alist, B.acount);
             long tiles = 0;
             for (int l = 2; l <= L; l++) tiles += 4 * (((1L << (2 * (l - 1))) + TM_TC - 1) / TM_TC);
-            const char *ve = getenv("LUDVM_TREE_GEMM44");
-            if (ve) {   // 4 x 4 thread tiles, 64 points x 64 cells per CTA (A/B)
-                long t44 = 0;
-                for (int l = 2; l <= L; l++) t44 += 4 * (((1L << (2 * (l - 1))) + 63) / 64);
-                const dim3 grid((P2 + 63) / 64, (unsigned)t44);
-                if (atoi(ve) == 1) k_tree_m2l_gemm44<256, 64, 64, 8, 2><<<grid, 256, 0, st>>>(G, B.startS, B.alist, B.acount, B.Mu, B.Mw, B.qhat, B.uloc, B.wloc);
-                else k_tree_m2l_gemm44<256, 64, 64, 8, 1><<<grid, 256, 0, st>>>(G, B.startS, B.alist, B.acount, B.Mu, B.Mw, B.qhat, B.uloc, B.wloc);
-            } else
             k_tree_m2l_gemm<<<dim3((P2 + TM_TI - 1) / TM_TI, (unsigned)tiles), 256, 0, st>>>(G, B.startS, B.alist, B.acount, B.Mu,
                                                                                              B.Mw, B.qhat, B.uloc, B.wloc);
             ctx->launches += 3;
