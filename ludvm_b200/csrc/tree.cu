@@ -845,6 +845,138 @@ __global__ void __launch_bounds__(256, 2) k_tree_m2l_gemm(const __grid_constant_
     }
 }
 
+// The same products on the FP64 tensor cores (mma.sync.m8n8k4.f64; Blackwell's tcgen05 has no FP64 kind, so this is the
+// FP64 tensor path of sm_100a).  CTA tile 64 points x 64 cells, 8 warps as 4 (points) x 2 (cells), warp tile 16 x 32 =
+// 2 x 4 MMA tiles per component: per k-step of 4 proxies a thread reads 8 doubles of fragments for 16 MMAs (4096 FMA per
+// warp), 0.5 bytes of shared memory per FMA where the CUDA-core version above needs 4.  Fragment layout (PTX ISA, m8n8k4
+// .f64): A[row = lane >> 2][k = lane & 3], B[k = lane & 3][col = lane >> 2], C[row = lane >> 2][col = 2 (lane & 3) + {0, 1}].
+// Row strides of 68 doubles make the fragment loads conflict-free (stride = 4 mod 16 bank pairs).
+#define TD_TI 64
+#define TD_TC 64
+#define TD_JC 16
+#define TD_LD 68
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 2) k_tree_m2l_dmma(const __grid_constant__ TreeGeom G, const int *startS, const int *alist,
+                                                          const int *acount, const double *Mu, const double *Mw,
+                                                          const double *qhat, double *uloc, double *wloc)
+{
+    const int P2 = G.P2, tid = threadIdx.x;
+    int l = 2, tile = blockIdx.y, ntp;
+    for (;; l++) {
+        ntp = (int)(((1L << (2 * (l - 1))) + TD_TC - 1) / TD_TC);
+        if (tile < 4 * ntp) break;
+        tile -= 4 * ntp;
+    }
+    const int par = tile / ntp;
+    tile -= par * ntp;
+    const int nA = acount[4 * l + par];
+    if (tile * TD_TC >= nA) return;
+    const long abase = level_offset(l) + ((long)par << (2 * (l - 1)));
+    const int i0 = blockIdx.x * TD_TI;
+    __shared__ int Acell[TD_TC], Bcell[TD_TC];
+    __shared__ __align__(16) double sMu[TD_JC][TD_LD], sMw[TD_JC][TD_LD], sQ[TD_JC][TD_LD];
+    const int warp = tid >> 5, lane = tid & 31;
+    const int iw = (warp & 3) * 16, cw = (warp >> 2) * 32;      // warp tile origin
+    const int fr = lane >> 2, fk = lane & 3;                    // fragment row / k index of this lane
+    double cu[2][4][2], cv[2][4][2];
+#pragma unroll
+    for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) cu[a][b][0] = cu[a][b][1] = cv[a][b][0] = cv[a][b][1] = 0.0;
+    if (tid < TD_TC) Acell[tid] = tile * TD_TC + tid < nA ? alist[abase + tile * TD_TC + tid] : -1;
+    const double *Ml_u = Mu + (size_t)(l - 2) * TM_NOFF * P2 * P2, *Ml_w = Mw + (size_t)(l - 2) * TM_NOFF * P2 * P2;
+    const double *ql = qhat + level_offset(l) * P2;
+    const int sh = 2 * (G.L - l), nc = 1 << l;
+    for (int off = 0; off < TM_NOFF; off++) {
+        const int dx = off % 7 - 3, dz = off / 7 - 3;
+        if (max(abs(dx), abs(dz)) <= 1) continue;
+        if (dx < -2 - (par & 1) || dx > 3 - (par & 1) || dz < -2 - (par >> 1) || dz > 3 - (par >> 1)) continue;
+        __syncthreads();
+        if (tid < TD_TC) {
+            int bcell = -1;
+            const int a = Acell[tid];
+            if (a >= 0) {
+                const int ax = (int)compact16((unsigned)a), az = (int)compact16((unsigned)a >> 1), bx = ax + dx, bz = az + dz;
+                if (bx >= 0 && bz >= 0 && bx < nc && bz < nc) {
+                    const long bc = morton2(bx, bz);
+                    if (startS[(bc + 1) << sh] - startS[bc << sh] > P2) bcell = (int)bc;
+                }
+            }
+            Bcell[tid] = bcell;
+        }
+        if (!__syncthreads_or(tid < TD_TC && Bcell[tid] >= 0)) continue;
+        const double *Mo_u = Ml_u + (size_t)off * P2 * P2, *Mo_w = Ml_w + (size_t)off * P2 * P2;
+        double pmu[4], pmw[4], pq[4];     // TD_JC x 64 elements of each tile / 256 threads
+        auto fetch = [&](int j0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int e = tid + 256 * q, jj = e >> 6, ii = e & 63, j = j0 + jj, i = i0 + ii;
+                const bool ok = j < P2 && i < P2;
+                pmu[q] = ok ? Mo_u[(size_t)j * P2 + i] : 0.0;
+                pmw[q] = ok ? Mo_w[(size_t)j * P2 + i] : 0.0;
+                const int cc = e / TD_JC, kj = e - cc * TD_JC, bcell = Bcell[cc];
+                pq[q] = (bcell >= 0 && j0 + kj < P2) ? ql[(size_t)bcell * P2 + j0 + kj] : 0.0;
+            }
+        };
+        auto put = [&]() {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int e = tid + 256 * q, jj = e >> 6, ii = e & 63;
+                sMu[jj][ii] = pmu[q];
+                sMw[jj][ii] = pmw[q];
+                const int cc = e / TD_JC, kj = e - cc * TD_JC;
+                sQ[kj][cc] = pq[q];
+            }
+        };
+        fetch(0);
+        for (int j0 = 0; j0 < P2; j0 += TD_JC) {
+            __syncthreads();
+            put();
+            __syncthreads();
+            if (j0 + TD_JC < P2) fetch(j0 + TD_JC);
+#pragma unroll
+            for (int k0 = 0; k0 < TD_JC; k0 += 4) {
+                double a_u[2], a_w[2], b[4];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++) {
+                    a_u[mt] = sMu[k0 + fk][iw + mt * 8 + fr];
+                    a_w[mt] = sMw[k0 + fk][iw + mt * 8 + fr];
+                }
+#pragma unroll
+                for (int nt = 0; nt < 4; nt++) b[nt] = sQ[k0 + fk][cw + nt * 8 + fr];
+#pragma unroll
+                for (int mt = 0; mt < 2; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) {
+                        dmma_m8n8k4(cu[mt][nt][0], cu[mt][nt][1], a_u[mt], b[nt]);
+                        dmma_m8n8k4(cv[mt][nt][0], cv[mt][nt][1], a_w[mt], b[nt]);
+                    }
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int a = Acell[cw + nt * 8 + 2 * fk + e];
+            if (a < 0) continue;
+            const size_t o = (size_t)(level_offset(l) + a) * P2;
+#pragma unroll
+            for (int mt = 0; mt < 2; mt++) {
+                const int i = i0 + iw + mt * 8 + fr;
+                if (i < P2) {
+                    uloc[o + i] += cu[mt][nt][e];
+                    wloc[o + i] += cv[mt][nt][e];
+                }
+            }
+        }
+}
+
 // L2L: the parent's local field interpolated to the points of child cell c of level l (l >= 3), added to the child's M2L sums
 __global__ void __launch_bounds__(256) k_tree_l2l(const __grid_constant__ TreeGeom G, int l, const int *startS, const int *startT,
                                                   double *uloc, double *wloc)
@@ -1098,6 +1230,12 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
             k_tree_alist<<<ceil_div(level_offset(L + 1), 256), 256, 0, st>>>(G, B.startS, B.startT, B.alist, B.acount);
             long tiles = 0;
             for (int l = 2; l <= L; l++) tiles += 4 * (((1L << (2 * (l - 1))) + TM_TC - 1) / TM_TC);
+            if (!getenv("LUDVM_TREE_NO_DMMA")) {   // FP64 tensor cores (default); the CUDA-core kernel stays for A/B
+                long td = 0;
+                for (int l = 2; l <= L; l++) td += 4 * (((1L << (2 * (l - 1))) + TD_TC - 1) / TD_TC);
+                k_tree_m2l_dmma<<<dim3((P2 + TD_TI - 1) / TD_TI, (unsigned)td), 256, 0, st>>>(G, B.startS, B.alist, B.acount, B.Mu, B.Mw,
+                                                                                            B.qhat, B.uloc, B.wloc);
+            } else
             k_tree_m2l_gemm<<<dim3((P2 + TM_TI - 1) / TM_TI, (unsigned)tiles), 256, 0, st>>>(G, B.startS, B.alist, B.acount, B.Mu,
                                                                                              B.Mw, B.qhat, B.uloc, B.wloc);
             ctx->launches += 3;
