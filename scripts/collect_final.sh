@@ -9,5 +9,5 @@ PROBE_ORDERS=12,14,16,18 python scripts/tree_probe.py 18 20 22 24 > $out/${tag}_
 python scripts/ff_tree_probe.py > $out/${tag}_ff_tree_probe.txt 2>&1; cut -c1-200 $out/${tag}_ff_tree_probe.txt | head -3
 python scripts/tree_ncu_driver.py 20 18 > $out/${tag}_plain_tree.txt 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 24 --csv --log-file $out/${tag}_tree_launches.csv python scripts/tree_ncu_driver.py 20 18 > /dev/null 2>&1
-ncu --set full --clock-control none --import-source on -k regex:k_tree_m2l_gemm -s 1 -c 1 -o $out/${tag}_k_tree_m2l_gemm -f python scripts/tree_ncu_driver.py 20 18 > $out/${tag}_ncu_gemm.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_tree_m2l_dmma -s 1 -c 1 -o $out/${tag}_k_tree_m2l_dmma -f python scripts/tree_ncu_driver.py 20 18 > $out/${tag}_ncu_gemm.log 2>&1
 ls -la $out | tail -8
