@@ -15,7 +15,9 @@
 // of its parent's neighbours that are not its own neighbours (<= 27 cells), each through its proxies -- or through its
 // own vortices when it holds no more of them than proxies.  On top of that, cells with more than P2 vortices carry a local
 // field at their own Chebyshev points (M2L / L2L / L2P, see "evaluation" below), so that a far list acts on P2 points per
-// cell instead of on every target: the black-box FMM of Fong & Darve with this file's proxies.  Measured error of the representation (scripts/tree_proto.py,
+// cell instead of on every target: the black-box FMM of Fong & Darve with this file's proxies; between two cells that both
+// carry proxies that action is a fixed matrix per level and offset, applied on the FP64 tensor cores (k_tree_m2l_dmma).
+// Measured error of the representation (scripts/tree_proto.py,
 // numpy model of this file): order 12 -> 2e-11, 16 -> 5e-14, 18 -> 3e-15 of sum |terms|.
 //
 // Everything runs on the context's stream; the only host round trip is the bounding box (32 bytes), which fixes the
