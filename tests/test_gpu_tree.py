@@ -178,3 +178,17 @@ def test_class_flowfield_far_field_order():
     scale = np.max(np.abs(ua))
     assert np.max(np.abs(s.u_ff - ua)) <= 1e-11 * scale and np.max(np.abs(s.w_ff - wa)) <= 1e-11 * scale
     assert np.max(np.abs(s.ome_ff - oa)) <= 1e-8 * np.max(np.abs(oa))
+
+
+@pytest.mark.parametrize("knob", ["LUDVM_TREE_NO_DMMA", "LUDVM_TREE_NO_GEMM", "LUDVM_TREE_GENERIC_UP"])
+def test_tree_alternative_kernels_give_the_same_sums(knob, monkeypatch):
+    """The A/B knobs select other kernels for the same mathematics -- the CUDA-core matrix M2L instead of the tensor-core
+    one, pair evaluations instead of matrices, the tile loop instead of transfer matrices in the upward pass -- and must
+    stay within the tolerance of the default path (they differ in summation order only)."""
+    from ludvm_b200 import ops
+    g, x, z = _cloud(200000, 31)
+    u1, w1 = ops.induced_velocity_tree(g, x, z, x, z, VC)
+    monkeypatch.setenv(knob, "1")
+    u0, w0 = ops.induced_velocity_tree(g, x, z, x, z, VC)
+    den = _sum_abs_terms(g, x, z, x[:400], z[:400], VC ** 4)
+    assert np.max(np.hypot(u1[:400] - u0[:400], w1[:400] - w0[:400]) / den) <= 1e-13
