@@ -12,7 +12,12 @@ def _mode(mode):
 def induced_velocity(circulation, xw, zw, xp, zp, v_core, viscous=True, mode="exact", ctx=None, vc4_per_source=None):
     """LUDVM.induced_velocity (LUDVM.py:549-570) on the GPU with host (numpy) buffers.
 
-    `v_core` is the core radius (the reference reads `self.v_core`); `viscous=False` uses point vortices."""
+    `v_core` is the core radius (the reference reads `self.v_core`); `viscous=False` uses point vortices.
+    `mode="tree"` routes to `induced_velocity_tree` (hierarchical far field, default order)."""
+    if mode == "tree":
+        if vc4_per_source is not None or np.size(circulation) == 1:
+            raise ValueError("mode='tree' needs one circulation per vortex and a single core radius")
+        return induced_velocity_tree(circulation, xw, zw, xp, zp, v_core if viscous == True else 0.0, ctx=ctx)  # noqa: E712
     ctx = ctx or _lib.default_context()
     g, xw, zw, xp, zp = (f64(np.atleast_1d(a)) for a in (circulation, xw, zw, xp, zp))
     if xw.size != zw.size or xp.size != zp.size or g.size not in (1, xw.size):

@@ -99,6 +99,9 @@ def test_tree_small_and_degenerate_inputs():
     assert np.allclose(u, uo, rtol=1e-12, atol=1e-15) and np.allclose(w, wo, rtol=1e-12, atol=1e-15)
     u, w = ops.induced_velocity_tree(np.zeros(0), np.zeros(0), np.zeros(0), np.array([1.0]), np.array([2.0]), VC)
     assert u[0] == 0.0 and w[0] == 0.0
+    g, x, z = _cloud(5000, 77)
+    a, b = ops.induced_velocity(g, x, z, x, z, VC, mode="tree"), ops.induced_velocity_tree(g, x, z, x, z, VC)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
 
 
 def test_tree_bitwise_reproducible_and_shard_independent():
