@@ -123,8 +123,8 @@ int ludvm_selfconv_step_p2p(ludvm_ctx *ctx, int mode, const double *gamma, const
  * vortices at its tensor Chebyshev points (barycentric Lagrange anterpolation, nested over the levels), one-cell
  * separation lists; near field and proxies are evaluated with the LUDVM_FAST_F64 pair arithmetic.  `order` 2..24
  * (<= 0: 18) sets the accuracy -- measured against the all-pairs sum, relative to sum |terms|: order 12 ~ 2e-11,
- * 16 ~ 5e-14, 18 ~ 3e-15 -- and `leaf` the wanted mean number of vortices per leaf cell (<= 0: twice the proxies per
- * cell).  Results are bitwise reproducible and do not depend on how target rows are split over GPUs.
+ * 16 ~ 5e-14, 18 ~ 3e-15 -- and `leaf` the wanted mean number of vortices per leaf cell (<= 0: the proxies per cell,
+ * (order + 1)^2).  Results are bitwise reproducible and do not depend on how target rows are split over GPUs.
  * stats (host pointer, nullable) receives 8 doubles: leaf level, leaf side, pair evaluations done, np * nw, proxies per
  * cell, device arena bytes, ms of tree build + upward pass, ms of the evaluation kernel; asking for it synchronises the
  * stream.

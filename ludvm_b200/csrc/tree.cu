@@ -47,6 +47,7 @@ struct TreeGeom {
     double vc4;
     double tdens;            // targets per unit area when they are a uniform grid (0: unknown): cells that hold more than P2
                              // grid points carry a local field even where they hold few sources
+    int pth;                 // a cell with more than pth source vortices is represented by proxies (and carries a local field)
     int L, P1, P2, generic_up;   // generic_up = 1: children's proxies go through the tile loop of k_tree_up too (A/B)
     double s[TR_MAX_P1];     // Chebyshev points of the second kind on [-1, 1], exactly antisymmetric
     double bw[TR_MAX_P1];    // barycentric weights
@@ -258,7 +259,7 @@ __global__ void __launch_bounds__(TU_THREADS) k_tree_up(const __grid_constant__ 
 {
     const int c = blockIdx.x, sh = 2 * (G.L - l), tid = threadIdx.x;
     const int b = startS[(long)c << sh], e = startS[((long)c + 1) << sh];
-    if (e - b <= G.P2) return;
+    if (e - b <= G.pth) return;
     __shared__ double Lx[TU_TILE][TR_MAX_P1], Lz[TU_TILE][TR_MAX_P1], gt[TU_TILE];
     __shared__ int seg_type[4], seg_a[4], seg_pre[5], nseg_s, prox_ch[4], prox_cell[4], nprox_s;
     __shared__ double Tq[2][TR_MAX_P1][TR_MAX_P1], Qc[TR_MAX_P1 * TR_MAX_P1], Tm[TR_MAX_P1 * TR_MAX_P1];
@@ -277,9 +278,9 @@ __global__ void __launch_bounds__(TU_THREADS) k_tree_up(const __grid_constant__ 
                 const long cc = 4L * c + ch;
                 const int cb = startS[cc << (sh - 2)], ce = startS[(cc + 1) << (sh - 2)], n = ce - cb;
                 if (n == 0) continue;
-                if (n > P2 && G.generic_up == 0) { prox_ch[np] = ch; prox_cell[np] = (int)cc; np++; continue; }
+                if (n > G.pth && G.generic_up == 0) { prox_ch[np] = ch; prox_cell[np] = (int)cc; np++; continue; }
                 seg_pre[ns] = run;
-                if (n > P2) { seg_type[ns] = 1 + ch; seg_a[ns] = (int)cc; run += P2; }
+                if (n > G.pth) { seg_type[ns] = 1 + ch; seg_a[ns] = (int)cc; run += P2; }
                 else { seg_type[ns] = 0; seg_a[ns] = cb; run += n; }
                 ns++;
             }
@@ -504,7 +505,7 @@ __device__ __forceinline__ int tree_build_list(const TreeGeom &G, const TreeEval
                     if (max(abs(jx - cxl), abs(jz - czl)) > 1) {
                         const int cc = morton2(jx, jz), sh = 2 * (L - l);
                         const int b = A.startS[(long)cc << sh], n = A.startS[((long)cc + 1) << sh] - b;
-                        if (n > P2) { a = cc; len = skip_proxies ? 0 : P2; lvl = l; }
+                        if (n > G.pth) { a = cc; len = skip_proxies ? 0 : P2; lvl = l; }
                         else { a = b; len = n; }
                     }
                 }
@@ -620,7 +621,7 @@ __device__ __forceinline__ void tree_eval_item(const TreeGeom &G, const TreeEval
 __device__ __forceinline__ bool tree_has_local(const TreeGeom &G, const int *startS, int l, long c)
 {
     const int sh = 2 * (G.L - l);
-    if (startS[(c + 1) << sh] - startS[c << sh] > G.P2) return true;
+    if (startS[(c + 1) << sh] - startS[c << sh] > G.pth) return true;
     const double a = ldexp(G.side, -l);
     return G.tdens * a * a > (double)G.P2;
 }
@@ -771,7 +772,7 @@ __global__ void __launch_bounds__(256, 2) k_tree_m2l_gemm(const __grid_constant_
                 const int ax = (int)compact16((unsigned)a), az = (int)compact16((unsigned)a >> 1), bx = ax + dx, bz = az + dz;
                 if (bx >= 0 && bz >= 0 && bx < nc && bz < nc && abs((bx >> 1) - (ax >> 1)) <= 1 && abs((bz >> 1) - (az >> 1)) <= 1) {
                     const long bc = morton2(bx, bz);
-                    if (startS[(bc + 1) << sh] - startS[bc << sh] > P2) bcell = (int)bc;
+                    if (startS[(bc + 1) << sh] - startS[bc << sh] > G.pth) bcell = (int)bc;
                 }
             }
             Bcell[tid] = bcell;
@@ -905,7 +906,7 @@ __global__ void __launch_bounds__(256, 2) k_tree_m2l_dmma(const __grid_constant_
                 const int ax = (int)compact16((unsigned)a), az = (int)compact16((unsigned)a >> 1), bx = ax + dx, bz = az + dz;
                 if (bx >= 0 && bz >= 0 && bx < nc && bz < nc) {
                     const long bc = morton2(bx, bz);
-                    if (startS[(bc + 1) << sh] - startS[bc << sh] > P2) bcell = (int)bc;
+                    if (startS[(bc + 1) << sh] - startS[bc << sh] > G.pth) bcell = (int)bc;
                 }
             }
             Bcell[tid] = bcell;
@@ -1138,10 +1139,11 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
         side = side * (1.0 + 1e-12) + 1e-300;
         if (!(side < 1e300)) return set_error(LUDVM_E_ARG, "tree: coordinates not finite");
         // leaf level from the wanted mean leaf population over the sources' own bounding box.  Per target a leaf costs
-        // 9 x population directly, a level 27 x proxies: the default population is two proxies' worth.
+        // 9 x population pair evaluations and (27 x P2^2 / population) tensor-core FMA: the default population is P2
+        // (the depth is an integer, so the actual population lands between P2 / 2 and 2 P2).
         const int P1 = order + 1, P2 = P1 * P1;
         // (dense grid targets: the near field is what is left per target, so small leaves; M2L does not grow with them)
-        const double pop = leaf > 0 ? (double)leaf : (tdens > 0.0 ? 64.0 : 2.0 * P2);
+        const double pop = leaf > 0 ? (double)leaf : (tdens > 0.0 ? 64.0 : 1.0 * P2);
         const double area = std::max((sxh - sxl) * (szh - szl), side * side * 1e-12);
         const double a0 = std::sqrt(pop * area / (double)std::max(1L, nw));
         int L = (int)std::lround(std::log2(std::max(side / a0, 1.0)));
@@ -1150,6 +1152,11 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
         L = std::max(2, std::min(std::min(TR_MAX_LEVEL, lcap), L));
         if (const char *le = getenv("LUDVM_TREE_LEVEL")) L = std::max(2, std::min(TR_MAX_LEVEL, atoi(le)));
         G.x0 = xlo; G.z0 = zlo; G.side = side; G.inv_leaf = (double)(1 << L) / side; G.vc4 = vc4; G.tdens = tdens;
+        // proxies (and a local field) from a quarter of P2 vortices on: with M2L on the tensor cores a proxy-to-proxy
+        // interaction is ~10x cheaper than a pair evaluation, so a cell is worth representing by more proxies than it
+        // has vortices (order 14, 2^20 vortices: 7.7 -> 5.7 ms with leaves of 160; profiles/r03q_tree_probe_pth.txt)
+        G.pth = std::max(1, P2 / 4);
+        if (const char *pe = getenv("LUDVM_TREE_PROXY_MIN")) G.pth = std::max(1, std::min(P2, (int)(atof(pe) * P2)));   // fraction of P2 (A/B)
         G.L = L; G.P1 = P1; G.P2 = P2; G.generic_up = getenv("LUDVM_TREE_GENERIC_UP") ? 1 : 0;
         for (int k = 0; k < P1; k++) {
             G.s[k] = std::sin(M_PI * (double)(order - 2 * k) / (double)(2 * order));
