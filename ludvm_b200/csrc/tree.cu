@@ -13,7 +13,7 @@
 // runs on the FP64 pipe at the same rate; the only question is how many pairs are left.  Lists are the standard
 // one-cell separation: a target leaf sees its 3x3 neighbour leaves directly and, on every level l = 2 .. L, the children
 // of its parent's neighbours that are not its own neighbours (<= 27 cells), each through its proxies -- or through its
-// own vortices when it holds no more of them than proxies.  On top of that, cells with more than P2 vortices carry a local
+// own vortices when it holds at most pth = P2 / 4 of them.  On top of that, cells with more than pth vortices carry a local
 // field at their own Chebyshev points (M2L / L2L / L2P, see "evaluation" below), so that a far list acts on P2 points per
 // cell instead of on every target: the black-box FMM of Fong & Darve with this file's proxies; between two cells that both
 // carry proxies that action is a fixed matrix per level and offset, applied on the FP64 tensor cores (k_tree_m2l_dmma).
@@ -252,7 +252,7 @@ __device__ __forceinline__ void tree_basis(const TreeGeom &G, double xi, double 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// upward pass: proxies of every cell of level l that holds more than P2 vortices
+// upward pass: proxies of every cell of level l that holds more than pth vortices
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TU_THREADS) k_tree_up(const __grid_constant__ TreeGeom G, int l, const int *startS,
                                                         const double *xs, const double *zs, const double *gs, double *qhat)
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(TU_THREADS) k_tree_up(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// evaluation.  A cell with more than P2 source vortices also carries a LOCAL field: the velocity induced by everything
+// evaluation.  A cell with more than pth source vortices also carries a LOCAL field: the velocity induced by everything
 // outside its neighbourhood, sampled at its own P2 Chebyshev points (M2L: the far list of the cell's level acting on the
 // points, the same pair arithmetic; L2L: the parent's local field interpolated to the child's points).  A target then
 // takes (a) the local field of its deepest ancestor that has one, interpolated at the target (L2P), (b) the far lists of
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(TE_THREADS, 4) k_tree_eval(const __grid_consta
 // slots + MUFU of a pair evaluation, and a matrix is shared by every pair of cells with that offset: a CTA owns a
 // (TM_TI points) x (TM_TC cells) tile of the local fields of one level, walks the 40 offsets and the P2 proxies with
 // register-tiled outer products, tiles of the matrices and of the proxy strengths prefetched into registers while the
-// previous ones are consumed.  Lists entries that are plain vortices (cells with <= P2 of them) stay with k_tree_eval.
+// previous ones are consumed.  Lists entries that are plain vortices (cells with <= pth of them) stay with k_tree_eval.
 // The order of the sums is fixed (offsets, then proxies, ascending), whatever tile a cell lands in.
 // The kernel is bound by shared-memory bandwidth, not by the FP64 pipe (ncu, profiles/r03g_k_tree_m2l_gemm_*: l1tex 85 %
 // busy, FP64 45 %, top stall short scoreboard): a 2 x 4 thread tile reads 64 bytes of operands per 16 DFMA = 4 bytes
