@@ -131,7 +131,15 @@ __global__ void __launch_bounds__(256) k_tree_keys(const __grid_constant__ TreeG
     iz = max(0, min(nc - 1, iz));
     const int k = morton2(ix, iz);
     key[i] = k;
-    slot[i] = atomicAdd(cnt + k, 1);   // any free slot of the cell; k_tree_cellsort fixes the order afterwards
+    // any free slots of the cell (k_tree_cellsort fixes the order of the sources afterwards); lanes of a warp that hit the
+    // same cell -- grid targets: all of them -- take their slots with one atomic
+    const int lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(__activemask(), k);
+    const int leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(cnt + k, __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    slot[i] = base + __popc(peers & ((1u << lane) - 1u));
 }
 
 // exclusive scan of cnt[0 .. n) into start[0 .. n], and the largest count into *maxcnt; one CTA
