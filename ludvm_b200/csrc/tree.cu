@@ -1061,6 +1061,108 @@ __global__ void __launch_bounds__(128) k_tree_l2p(const __grid_constant__ TreeGe
     A.w[oi] += sw;
 }
 
+// L2P on the FP64 tensor cores (orders <= 19).  The scalar kernel above reads the cell's 2 P2 field values once PER TARGET
+// (two loads per multiply-add, ~5 ms for the 16.7M points of a 4096^2 grid); here a warp takes 8 targets of one leaf at a
+// time and the field sits in its registers as MMA B-fragments, loaded once per leaf:
+//     D[target][k1] = sum_k2 lz_k2(zeta_target) U[k1][k2]            (15 MMAs per component: k2 in 5 steps of 4, k1 in 3 tiles of 8)
+//     u_target     = sum_k1 lx_k1(xi_target) D[target][k1]          (each lane its 6 columns, then a 4-lane shuffle sum)
+// The barycentric bases are computed in the fragment layouts directly (the 4 lanes of a target share the normalisation).
+#define L2P_KS 5
+#define L2P_NT 3
+__global__ void __launch_bounds__(128) k_tree_l2p_mma(const __grid_constant__ TreeGeom G, const __grid_constant__ TreeEval A)
+{
+    const int c = blockIdx.x;                                   // target leaf
+    const int tb = A.startT[c], te = A.startT[c + 1];
+    if (tb == te) return;
+    const int l = tree_local_level(G, A.startS, c);
+    if (l < 2) return;
+    const int a = c >> (2 * (G.L - l)), P1 = G.P1;
+    const double h = ldexp(G.side, -(l + 1)), inv_h = 1.0 / h;
+    const double cx = G.x0 + (2.0 * compact16((unsigned)a) + 1.0) * h, cz = G.z0 + (2.0 * compact16((unsigned)a >> 1) + 1.0) * h;
+    const double *U = A.uloc + (level_offset(l) + a) * G.P2, *W = A.wloc + (level_offset(l) + a) * G.P2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, fr = lane >> 2, fk = lane & 3;
+    // B fragments: B[k2][k1] = U[k1][k2], this lane holds row k2 = fk + 4 s, column k1 = fr + 8 nt
+    double bu[L2P_KS][L2P_NT], bw[L2P_KS][L2P_NT];
+#pragma unroll
+    for (int s = 0; s < L2P_KS; s++)
+#pragma unroll
+        for (int nt = 0; nt < L2P_NT; nt++) {
+            const int k2 = fk + 4 * s, k1 = fr + 8 * nt;
+            const bool ok = k1 < P1 && k2 < P1;
+            bu[s][nt] = ok ? U[k1 * P1 + k2] : 0.0;
+            bw[s][nt] = ok ? W[k1 * P1 + k2] : 0.0;
+        }
+    for (int t0 = tb + 8 * warp; t0 < te; t0 += 8 * (blockDim.x >> 5)) {
+        const int t = t0 + fr;
+        const bool valid = t < te;
+        const int oi = A.permT[valid ? t : te - 1];
+        const double xi = (A.xt[oi] - cx) * inv_h, ze = (A.zt[oi] - cz) * inv_h;
+        // bases in fragment layout: lz at k2 = fk + 4 s (A fragment), lx at k1 = 8 nt + 2 fk + e (D fragment columns)
+        double az[L2P_KS], ax[L2P_NT][2];
+        double sz = 0.0, sx = 0.0;
+        int hz = -1, hx = -1;
+#pragma unroll
+        for (int s = 0; s < L2P_KS; s++) {
+            const int k = fk + 4 * s;
+            az[s] = 0.0;
+            if (k < P1) {
+                double d = ze - G.s[k];
+                if (d == 0.0) { hz = k; d = 1.0; }
+                az[s] = G.bw[k] / d;
+                sz += az[s];
+            }
+        }
+#pragma unroll
+        for (int nt = 0; nt < L2P_NT; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const int k = 8 * nt + 2 * fk + e;
+                ax[nt][e] = 0.0;
+                if (k < P1) {
+                    double d = xi - G.s[k];
+                    if (d == 0.0) { hx = k; d = 1.0; }
+                    ax[nt][e] = G.bw[k] / d;
+                    sx += ax[nt][e];
+                }
+            }
+        sz += __shfl_xor_sync(~0u, sz, 1); sz += __shfl_xor_sync(~0u, sz, 2);     // the 4 lanes of a target
+        sx += __shfl_xor_sync(~0u, sx, 1); sx += __shfl_xor_sync(~0u, sx, 2);
+        hz = max(hz, __shfl_xor_sync(~0u, hz, 1)); hz = max(hz, __shfl_xor_sync(~0u, hz, 2));
+        hx = max(hx, __shfl_xor_sync(~0u, hx, 1)); hx = max(hx, __shfl_xor_sync(~0u, hx, 2));
+        const double iz = 1.0 / sz, ix = 1.0 / sx;
+#pragma unroll
+        for (int s = 0; s < L2P_KS; s++) az[s] = hz >= 0 ? (fk + 4 * s == hz ? 1.0 : 0.0) : az[s] * iz;
+#pragma unroll
+        for (int nt = 0; nt < L2P_NT; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) ax[nt][e] = hx >= 0 ? (8 * nt + 2 * fk + e == hx ? 1.0 : 0.0) : ax[nt][e] * ix;
+        double du[L2P_NT][2], dw[L2P_NT][2];
+#pragma unroll
+        for (int nt = 0; nt < L2P_NT; nt++) du[nt][0] = du[nt][1] = dw[nt][0] = dw[nt][1] = 0.0;
+#pragma unroll
+        for (int s = 0; s < L2P_KS; s++)
+#pragma unroll
+            for (int nt = 0; nt < L2P_NT; nt++) {
+                dmma_m8n8k4(du[nt][0], du[nt][1], az[s], bu[s][nt]);
+                dmma_m8n8k4(dw[nt][0], dw[nt][1], az[s], bw[s][nt]);
+            }
+        double su = 0.0, sw = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < L2P_NT; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                su = fma(ax[nt][e], du[nt][e], su);
+                sw = fma(ax[nt][e], dw[nt][e], sw);
+            }
+        su += __shfl_xor_sync(~0u, su, 1); su += __shfl_xor_sync(~0u, su, 2);
+        sw += __shfl_xor_sync(~0u, sw, 1); sw += __shfl_xor_sync(~0u, sw, 2);
+        if (valid && fk == 0) {
+            A.u[oi] += su;
+            A.w[oi] += sw;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256) k_tree_euler(const double *x, const double *z, const double *u, const double *w, double dt,
                                                     int n, double *xo, double *zo)
 {
@@ -1262,7 +1364,8 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
                 k_tree_l2l<<<1 << (2 * l), 256, 0, st>>>(G, l, B.startS, B.startT, B.uloc, B.wloc);
                 ctx->launches++;
             }
-            k_tree_l2p<<<ceil_div(np_, 128), 128, 0, st>>>(G, A);
+            if (P1 <= 4 * L2P_KS && !getenv("LUDVM_TREE_L2P_SCALAR")) k_tree_l2p_mma<<<ncell, 128, 0, st>>>(G, A);
+            else k_tree_l2p<<<ceil_div(np_, 128), 128, 0, st>>>(G, A);
             ctx->launches++;
         }
         if (stats) CUDA_TRY(cudaEventRecord(ev[2], st));
