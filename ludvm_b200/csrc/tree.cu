@@ -75,6 +75,13 @@ __host__ __device__ __forceinline__ int morton2(int ix, int iz) { return (int)(s
 // cells of levels 2 .. l-1 precede level l in the proxy array
 __host__ __device__ __forceinline__ long level_offset(int l) { return ((1L << (2 * l)) - 16) / 3; }
 
+// D (8 x 8) += A (8 x 4) B (4 x 8) on the FP64 tensor cores; fragments (PTX ISA, m8n8k4 .f64): A[row = lane >> 2][k = lane & 3],
+// B[k = lane & 3][col = lane >> 2], D[row = lane >> 2][col = 2 (lane & 3) + {0, 1}]
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 // ---------------------------------------------------------------------------------------------------
 // bounding box: order-preserving map double -> uint64, atomicMin / atomicMax
 // ---------------------------------------------------------------------------------------------------
@@ -394,6 +401,85 @@ __global__ void __launch_bounds__(TU_THREADS) k_tree_up(const __grid_constant__ 
     for (int q = 0; q < 3; q++) {
         const int k = tid + q * TU_THREADS;
         if (k < P2) out[k] = acc[q];
+    }
+}
+
+// Leaf level of the upward pass on the FP64 tensor cores (orders <= 23): qhat[k1][k2] = sum_j (lx_k1(xi_j) Gamma_j) lz_k2(zeta_j)
+// is a (P1 x n) x (n x P1) product per cell.  A warp takes 4 vortices per step: the lanes with lane & 3 = q hold vortex q's
+// basis values at k = (lane >> 2) + 8 t, t < 3, in exactly the A- (rows k1) and B- (columns k2) fragment layouts, the
+// normalisation sums run over those 8 lanes by shuffles, and 9 MMAs add the step to the 3 x 3 tiles of the result.  The
+// four warps of the CTA split the cell's vortices and are summed in warp order.  (k_tree_up: 5 % of the DFMA rate, the
+// tile loop is bound by shared-memory loads.)
+__global__ void __launch_bounds__(128) k_tree_up_leaf_mma(const __grid_constant__ TreeGeom G, const int *startS, const double *xs,
+                                                          const double *zs, const double *gs, double *qhat)
+{
+    const int c = blockIdx.x, b = startS[c], e = startS[c + 1];
+    if (e - b <= G.pth) return;
+    const int P1 = G.P1, l = G.L;
+    const double h = ldexp(G.side, -(l + 1)), inv_h = 1.0 / h;
+    const double cx = G.x0 + (2.0 * compact16((unsigned)c) + 1.0) * h, cz = G.z0 + (2.0 * compact16((unsigned)c >> 1) + 1.0) * h;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, fr = lane >> 2, fk = lane & 3;
+    double acc[3][3][2];
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+#pragma unroll
+        for (int n = 0; n < 3; n++) acc[m][n][0] = acc[m][n][1] = 0.0;
+    for (int j0 = b + 4 * warp; j0 < e; j0 += 16) {
+        const int j = j0 + fk;
+        const bool valid = j < e;
+        const int jj = valid ? j : e - 1;
+        const double xi = (xs[jj] - cx) * inv_h, ze = (zs[jj] - cz) * inv_h, g = valid ? gs[jj] : 0.0;
+        double ax[3], bz[3], sx = 0.0, sz = 0.0;
+        int hx = -1, hz = -1;
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const int k = fr + 8 * t;
+            ax[t] = bz[t] = 0.0;
+            if (k < P1) {
+                double dx = xi - G.s[k], dz = ze - G.s[k];
+                if (dx == 0.0) { hx = k; dx = 1.0; }
+                if (dz == 0.0) { hz = k; dz = 1.0; }
+                ax[t] = G.bw[k] / dx;
+                bz[t] = G.bw[k] / dz;
+                sx += ax[t];
+                sz += bz[t];
+            }
+        }
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {      // the 8 lanes of a vortex: lane & 3 fixed
+            sx += __shfl_xor_sync(~0u, sx, o);
+            sz += __shfl_xor_sync(~0u, sz, o);
+            hx = max(hx, __shfl_xor_sync(~0u, hx, o));
+            hz = max(hz, __shfl_xor_sync(~0u, hz, o));
+        }
+        const double ix = g / sx, iz = 1.0 / sz;
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+            const int k = fr + 8 * t;
+            ax[t] = hx >= 0 ? (k == hx ? g : 0.0) : ax[t] * ix;      // lx_k1 Gamma_j
+            bz[t] = hz >= 0 ? (k == hz ? 1.0 : 0.0) : bz[t] * iz;
+        }
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+#pragma unroll
+            for (int n = 0; n < 3; n++) dmma_m8n8k4(acc[m][n][0], acc[m][n][1], ax[m], bz[n]);
+    }
+    // sum the four warps in warp order (fixed), then write the P1 x P1 corner
+    __shared__ double red[4][3][3][2][32];
+#pragma unroll
+    for (int m = 0; m < 3; m++)
+#pragma unroll
+        for (int n = 0; n < 3; n++) {
+            red[warp][m][n][0][lane] = acc[m][n][0];
+            red[warp][m][n][1][lane] = acc[m][n][1];
+        }
+    __syncthreads();
+    double *out = qhat + (level_offset(l) + c) * G.P2;
+    for (int idx = threadIdx.x; idx < 3 * 3 * 2 * 32; idx += blockDim.x) {
+        const int ln = idx & 31, ee = (idx >> 5) & 1, n = (idx >> 6) % 3, m = (idx >> 6) / 3;
+        const int k1 = 8 * m + (ln >> 2), k2 = 8 * n + 2 * (ln & 3) + ee;
+        if (k1 < P1 && k2 < P1)
+            out[k1 * P1 + k2] = ((red[0][m][n][ee][ln] + red[1][m][n][ee][ln]) + red[2][m][n][ee][ln]) + red[3][m][n][ee][ln];
     }
 }
 
@@ -866,10 +952,6 @@ __global__ void __launch_bounds__(256, 2) k_tree_m2l_gemm(const __grid_constant_
 #define TD_TC 64
 #define TD_JC 16
 #define TD_LD 68
-__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
-{
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 __global__ void __launch_bounds__(256, 2) k_tree_m2l_dmma(const __grid_constant__ TreeGeom G, const int *startS, const int *alist,
                                                           const int *acount, const double *Mu, const double *Mw,
@@ -1326,7 +1408,8 @@ static int tree_velocity_device(ludvm_ctx *ctx, const double *g, const double *x
             ctx->launches++;
         }
         for (int l = L; l >= 2; l--) {
-            k_tree_up<<<1 << (2 * l), TU_THREADS, 0, st>>>(G, l, B.startS, B.xs, B.zs, B.gs, B.qhat);
+            if (l == L && P1 <= 24 && !getenv("LUDVM_TREE_UP_SCALAR")) k_tree_up_leaf_mma<<<ncell, 128, 0, st>>>(G, B.startS, B.xs, B.zs, B.gs, B.qhat);
+            else k_tree_up<<<1 << (2 * l), TU_THREADS, 0, st>>>(G, l, B.startS, B.xs, B.zs, B.gs, B.qhat);
             ctx->launches++;
         }
         TreeEval A = {B.startS, B.startT, B.permT, B.keyT, B.xs, B.zs, B.gs, B.qhat, xp, zp, u, w, B.uloc, B.wloc, B.pairs,
